@@ -1,0 +1,206 @@
+/* abt_b200.h -- C ABI of the B200-native Audio Barlow Twins hot path (libabt_b200.so).
+ *
+ * Drop-in boundary for the per-step data-parallel path of jonahanton/SSL_audio (reference tree
+ * at /root/reference; citations below are relative to it).  The reference is pure Python and
+ * has no FFI of its own: the interface these entry points replace is the set of Python calls
+ * listed per function, and the binding a maintainer adds is the ctypes stub in INTEGRATION.md
+ * (ssl_audio_b200/_lib.py is that stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless marked [host];
+ *   - every function returns 0 on success or a negative abt_status; abt_last_error() returns a
+ *     thread-local, human-readable message for the last failure; no exception crosses the ABI;
+ *   - functions taking abt_stream_t enqueue asynchronously on that CUDA stream (a cudaStream_t)
+ *     and never allocate device memory: the caller provides outputs and workspaces;
+ *   - there is no CPU fallback: on a non-sm_100 device the compute entry points return
+ *     ABT_ERR_DEVICE.
+ */
+#ifndef ABT_B200_H
+#define ABT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABT_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef void* abt_stream_t; /* cudaStream_t */
+
+typedef enum {
+    ABT_OK = 0,
+    ABT_ERR_ARG = -1,    /* invalid argument (shape, alignment, null pointer) -> Python ValueError */
+    ABT_ERR_CUDA = -2,   /* CUDA runtime / driver error                        -> Python RuntimeError */
+    ABT_ERR_DEVICE = -3, /* current device is not sm_100                       -> Python RuntimeError */
+    ABT_ERR_STATE = -4   /* object used in the wrong state                     -> Python RuntimeError */
+} abt_status;
+
+typedef enum { ABT_DTYPE_BF16 = 0, ABT_DTYPE_F16 = 1, ABT_DTYPE_F32 = 2 } abt_dtype;
+
+int abt_version(void);
+const char* abt_last_error(void);
+/* 0 iff the current CUDA device has compute capability 10.x */
+int abt_device_check(void);
+
+/* ===================================================================================== *
+ *  Frontend: wav -> power STFT -> mel -> log -> normalise
+ *  replaces torchaudio.transforms.MelSpectrogram as constructed at datasets.py:39-48 plus
+ *  `(mel + eps).log()` (datasets.py:115, old/data_manager/wav_to_lms.py:58-61) and the
+ *  dataset z-score (datasets.py:118-119, :353-354).
+ * ===================================================================================== */
+typedef struct {
+    int32_t sample_rate; /* 16000 */
+    int32_t n_fft;       /* must be 1024 */
+    int32_t win_length;  /* <= n_fft; centre-padded like torch.stft */
+    int32_t hop_length;  /* 160 */
+    int32_t n_mels;      /* must be 64 */
+    float f_min, f_max;  /* 60, 7800 */
+    int32_t apply_norm;  /* 1: out = (log_mel - norm_mean) / norm_std */
+    float norm_mean, norm_std;
+} abt_mel_config;
+
+typedef struct abt_logmel_plan abt_logmel_plan; /* device tables: window, sparse mel filterbank */
+
+int abt_logmel_plan_create(const abt_mel_config* cfg, abt_logmel_plan** plan);
+int abt_logmel_plan_destroy(abt_logmel_plan* plan);
+
+/* Full log-mel ("mode F"): wav (n_clips, n_samples) fp32 row-major -> out (n_clips, n_mels, 1 + n_samples/hop). */
+int abt_logmel_fwd(const abt_logmel_plan* plan, const float* wav, int n_clips, int n_samples, float* out, abt_stream_t stream);
+
+/* Crop-first log-mel ("mode C"): only frames [frame_start[b], frame_start[b] + n_frames) of clip b
+ * are computed (frames beyond the clip end are written as the normalised value of 0.0, mirroring
+ * the right zero-pad at datasets.py:346-350 BEFORE normalisation).  Clip b is the n_samples-long
+ * waveform at wav + b * wav_row_stride + wav_offset[b] (wav_offset may be NULL; it carries the
+ * random unit crop of datasets.py:110-113, so reflect padding happens at the unit's edges as in
+ * the reference).  Clip b is written to out_base + out_slot[b] * out_slot_stride (floats), laid
+ * out (n_mels, n_frames); out_slot may be NULL (= identity).  This lets the frontend write
+ * straight into the Mixup ring.  frame_start may be NULL (= 0). */
+int abt_logmel_crop_fwd(const abt_logmel_plan* plan, const float* wav, int64_t wav_row_stride, const int32_t* wav_offset, int n_clips,
+                        int n_samples, const int32_t* frame_start, int n_frames, float* out_base, const int32_t* out_slot,
+                        int64_t out_slot_stride, abt_stream_t stream);
+
+/* Crop / right-pad a precomputed log-mel and z-score it: datasets.py:342-354.
+ * lms (n_clips, n_mels, t_full) -> out slots as above, (n_mels, n_frames) each. */
+int abt_lms_crop_norm(const float* lms, int n_clips, int n_mels, int t_full, const int32_t* frame_start, int n_frames, int apply_norm,
+                      float norm_mean, float norm_std, float* out_base, const int32_t* out_slot, int64_t out_slot_stride,
+                      abt_stream_t stream);
+
+/* ===================================================================================== *
+ *  Views: Mixup -> RandomResizeCrop -> RandomLinearFader, one launch for all clips and views
+ *  replaces MixupBYOLA.forward (augmentations.py:103-117), log_mixup_exp (:81-85),
+ *  RandomResizeCrop.forward (:40-55) and RandomLinearFader.forward (:69-74) as sequenced by
+ *  AudioPairTransform.forward (utils/transforms.py:49-58).
+ * ===================================================================================== */
+typedef struct {
+    int32_t z_kind; /* 0: no mixup partner, 1: partner is bank slot z_index, 2: partner is clip z_index of this batch */
+    int32_t z_index;
+    float w_x, w_z;           /* fp32 weights of exp(x), exp(z): float32(1-alpha), float32(1-(1-alpha)) */
+    int32_t i, j, h, w;       /* crop box on the virtual canvas (RandomResizeCrop.get_params) */
+    float head, tail;         /* fader end points */
+    int32_t flags;            /* bit0: mixup on, bit1: resize-crop on, bit2: fader on */
+    int32_t out_index;        /* which output tensor of `outs` this view is written to */
+} abt_view_params;            /* 48 bytes */
+
+typedef struct {
+    int32_t n_clips, n_views; /* params has n_clips * n_views entries, clip-major */
+    int32_t in_h, in_w;       /* 64, 96 */
+    int32_t canvas_h, canvas_w; /* int(in_h * vcs[0]), int(in_w * vcs[1]) */
+    int32_t out_h, out_w;     /* resize target (n_mels, crop_frames) or local_crops_size */
+    const float* x;           /* clip b at x + x_slot[b] * x_slot_stride, (in_h, in_w) fp32; x_slot may be NULL */
+    const int32_t* x_slot;
+    int64_t x_slot_stride;
+    const float* bank;        /* bank slot s at bank + s * bank_slot_stride */
+    int64_t bank_slot_stride;
+    const abt_view_params* params; /* device */
+    float* outs[8];           /* output tensor k: (n_clips, 1, out_h, out_w) contiguous */
+} abt_views_args;
+
+int abt_views_fwd(const abt_views_args* args, abt_stream_t stream);
+
+/* copy clips into bank slots: bank[slot[b]] = x[b]  (MixupBYOLA's `memory_bank + [x]`, augmentations.py:115) */
+int abt_bank_push(const float* x, int64_t x_stride, int n_clips, int clip_elems, float* bank, int64_t bank_slot_stride,
+                  const int32_t* slot, abt_stream_t stream);
+
+/* ===================================================================================== *
+ *  Host planner [host]: replays the reference's RNG draw order (numpy legacy MT19937 global
+ *  state + CPython `random` MT19937) for a whole batch and emits the parameter table.
+ *  Bit-exact against np.random.* / random.randint as called at augmentations.py:34-37,70,105,108
+ *  and datasets.py:89,112,344.
+ * ===================================================================================== */
+typedef struct abt_planner abt_planner;
+
+typedef struct {
+    int32_t mixup, rrc, rlf;      /* args.mixup / args.RRC / args.RLF */
+    double mixup_ratio_d;         /* 0.2 (python float) */
+    int32_t n_memory;             /* 2048: length of the virtual FIFO (MixupBYOLA.n) */
+    int32_t ring_slots;           /* physical ring size; must be >= n_memory + largest batch */
+    int32_t n_global;             /* global views per clip (2 for AudioPairTransform, 1 for a bare module) */
+    int32_t in_h, in_w;           /* 64, 96 */
+    int32_t canvas_h, canvas_w;   /* 64, 144 */
+    double freq_scale[2], time_scale[2]; /* (0.6, 1.5) */
+    int32_t n_local;              /* local crops per clip */
+    int32_t local_h, local_w;     /* local_crops_size */
+    double local_scale[2];        /* (0.05, 0.6) */
+    double fader_gain;            /* 1.0 */
+} abt_plan_config;
+
+int abt_planner_create(const abt_plan_config* cfg, abt_planner** p);
+int abt_planner_destroy(abt_planner* p);
+/* numpy legacy state: key[624], pos in [0,624]  (np.random.get_state()[1:3]) */
+int abt_planner_set_numpy_state(abt_planner* p, const uint32_t* key624, int pos);
+int abt_planner_get_numpy_state(const abt_planner* p, uint32_t* key624, int* pos);
+/* CPython random state: the 625-tuple of random.getstate()[1] (624 words + index) */
+int abt_planner_set_pyrandom_state(abt_planner* p, const uint32_t* key624, int pos);
+int abt_planner_get_pyrandom_state(const abt_planner* p, uint32_t* key624, int* pos);
+/* bank bookkeeping (virtual FIFO of clip uids, mirrors MixupBYOLA.memory_bank) */
+int abt_planner_bank_len(const abt_planner* p);
+int abt_planner_bank_reset(abt_planner* p);
+/* Plan one batch.  time_crop_range > 0 draws `np.random.randint(time_crop_range)` per clip before its
+ * views (datasets.py:344); wav_crop_range > 0 draws `random.randint(0, wav_crop_range)` (datasets.py:112).
+ * Outputs [host]: starts[n_clips] (-1 if not drawn), wav_starts[n_clips], params[n_clips*(2+n_local)],
+ * slots[n_clips] = bank ring slot each clip must be stored in (uid % ring_slots). */
+int abt_planner_plan_batch(abt_planner* p, int n_clips, int time_crop_range, int wav_crop_range, int32_t* starts,
+                           int32_t* wav_starts, abt_view_params* params, int32_t* slots);
+
+/* ===================================================================================== *
+ *  Barlow Twins objective forward + backward
+ *  replaces BarlowTwinsLoss.forward_loss (utils/loss.py:15-30: BatchNorm1d(affine=False) on
+ *  both views, c = bn(z1).T @ bn(z2) / N, on/off-diagonal loss) AND its autograd backward,
+ *  plus the BatchNorm running-stat side effect (utils/loss.py:13,17).
+ * ===================================================================================== */
+typedef struct {
+    const void* z1;       /* (n_rows, n_dims) row-major, dtype below */
+    const void* z2;
+    int32_t dtype;        /* abt_dtype; the tensor cores consume bf16: f16/f32 inputs are rounded to bf16 */
+    int32_t n_rows;       /* N >= 2 */
+    int32_t n_dims;       /* D, multiple of 64 */
+    float alpha, lambda;  /* cfg.alpha, cfg.lmbda */
+    int32_t hsic;         /* cfg.HSIC */
+    float eps;            /* BatchNorm eps (1e-5) */
+    float momentum;       /* BatchNorm momentum (0.1) */
+    float grad_scale;     /* gradients are multiplied by this (1.0 = d loss) */
+    int32_t need_grad_mask; /* bit0: dz1, bit1: dz2 */
+    float* loss_out;      /* device scalar */
+    void* dz1;            /* (n_rows, n_dims) same dtype as z, or NULL */
+    void* dz2;
+    float* running_mean;  /* (n_dims) BatchNorm buffers updated z1 then z2, or NULL */
+    float* running_var;
+    void* workspace;      /* abt_bt_workspace_bytes() bytes, 256-byte aligned */
+    size_t workspace_bytes;
+} abt_bt_args;
+
+int abt_bt_workspace_bytes(int n_rows, int n_dims, int dtype, size_t* bytes);
+int abt_bt_loss_fwd_bwd(const abt_bt_args* args, abt_stream_t stream);
+
+/* ===================================================================================== *
+ *  Debug hooks (not part of the drop-in surface; used by tools/gpu_diag.py)
+ * ===================================================================================== */
+int abt_debug_set(int key, int value);
+int abt_debug_ws_offsets(int n_rows, int n_dims, int dtype, size_t* out8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABT_B200_H */

@@ -1,0 +1,18 @@
+"""ssl_audio_b200 -- B200-native (sm_100a) hot path of Audio Barlow Twins.
+
+Host-side mirror of the reference's interfaces for the path named in BASELINE.json:
+    AudioPairTransform, RandomResizeCrop, RandomLinearFader, MixupBYOLA, log_mixup_exp   (views)
+    LogMelSpectrogram, BatchFrontend                                                     (frontend)
+    BarlowTwinsLoss, off_diagonal                                                        (objective)
+All compute runs in hand-written CUDA behind the C ABI of include/abt_b200.h; importing this package
+never falls back to PyTorch/CPU implementations.
+"""
+from .augmentations import MixGaussianNoise, MixupBYOLA, RandomLinearFader, RandomResizeCrop, log_mixup_exp
+from .frontend import BatchFrontend, LogMelSpectrogram
+from .loss import BarlowTwinsLoss, bt_loss_fwd_bwd, off_diagonal
+from .transforms import AudioPairTransform
+
+__all__ = [
+    "AudioPairTransform", "RandomResizeCrop", "RandomLinearFader", "MixupBYOLA", "MixGaussianNoise", "log_mixup_exp",
+    "LogMelSpectrogram", "BatchFrontend", "BarlowTwinsLoss", "bt_loss_fwd_bwd", "off_diagonal",
+]

@@ -1,0 +1,744 @@
+// Barlow Twins objective, forward + backward, for sm_100a.
+//
+// Replaces utils/loss.py:15-30 (BarlowTwinsLoss.forward_loss) and its autograd backward
+// (reference: /root/reference).  Closed form, N rows, D columns:
+//   zh = (z - mu) * r,  r = 1/sqrt(var_biased + eps)           (nn.BatchNorm1d, affine=False)
+//   C  = zh1^T zh2 / N
+//   L  = alpha * sum_i (C_ii - 1)^2 + lambda * sum_{i!=j} (C_ij + h)^2     (h = 1 iff HSIC)
+//   G  = dL/dC,  dL/dzh1 = zh2 G^T / N,  dL/dzh2 = zh1 G / N,  then batch-norm backward.
+//
+// The D x D matrix is never materialised in fp32.  Four launches:
+//   1. bt_stats_kernel     column statistics of both views (+ bf16 copies of non-bf16 inputs,
+//                          BatchNorm running-stat update, fp32 diagonal C_ii)
+//   2. bt_umma_kernel CORR S = z1^T z2 on the tensor cores (tcgen05, RAW bf16 operands straight
+//                          from the row-major embeddings as MN-major TMA tiles, fp32 TMEM
+//                          accumulator); epilogue applies batch-norm as a rank-1 correction,
+//                          reduces the off-diagonal loss and emits
+//                          H_ij = G_ij r1_i r2_j / N in bf16 (diagonal excluded).
+//   3. bt_umma_kernel GRAD g1^T = H z2 (K-major A) and g2^T = H^T z1 (MN-major A over the
+//                          same H), fp32 out.  6 N D^2 executed FLOP = the algorithmic count.
+//   4. bt_finalize_kernel  adds the fp32 diagonal term, batch-norm backward, output cast, loss.
+#include "abt_internal.h"
+#include "sm100_ptx.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace abt {
+
+// ------------------------------------------------------------------------------------------
+// column-statistics layout inside the workspace (float arrays of length D each)
+// ------------------------------------------------------------------------------------------
+enum StatSlot {
+    S_MU1 = 0, S_R1, S_MU2, S_R2, S_CDIAG,
+    S_NMU1,   // -N * mu1            (CORR row constant)
+    S_AROW,   // 2*lambda*r1^2/N^2   (CORR row scale of H)
+    S_ROWC,   // r1^2/N^2            (CORR row scale of sum c^2)
+    S_RHO1,   // r1/N                (CORR row scale of sum c, HSIC only)
+    S_BCOL,   // r2^2                (CORR column scale)
+    S_COUNT
+};
+
+template <typename T> struct Ld2;
+template <> struct Ld2<__nv_bfloat16> {
+    static __device__ __forceinline__ float2 ld(const __nv_bfloat16* p) {
+        return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float a, float b) {
+        *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+    }
+};
+template <> struct Ld2<__half> {
+    static __device__ __forceinline__ float2 ld(const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
+    static __device__ __forceinline__ void st(__half* p, float a, float b) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b); }
+};
+template <> struct Ld2<float> {
+    static __device__ __forceinline__ float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
+    static __device__ __forceinline__ void st(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+};
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+constexpr int kColsPerBlock = 64;   // 32 lanes x 2 columns
+constexpr int kRowGroups = 8;       // 256 threads
+
+// ------------------------------------------------------------------------------------------
+// 1. statistics
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bt_stats_kernel(const T* __restrict__ z1, const T* __restrict__ z2, int N, int D, float eps,
+                                                       float lambda, float momentum, float* __restrict__ stats,
+                                                       __nv_bfloat16* __restrict__ zb1, __nv_bfloat16* __restrict__ zb2,
+                                                       float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                       double* __restrict__ loss_acc, unsigned int* __restrict__ counters) {
+    __shared__ float red[kRowGroups][5][kColsPerBlock];
+    __shared__ float shift[2][kColsPerBlock];
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int col = blockIdx.x * kColsPerBlock + lane * 2;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        loss_acc[0] = 0.0; loss_acc[1] = 0.0; loss_acc[2] = 0.0;
+        counters[0] = 0u;
+    }
+    float s1[2] = {0, 0}, q1[2] = {0, 0}, s2[2] = {0, 0}, q2[2] = {0, 0}, x12[2] = {0, 0};
+    float k1[2] = {0, 0}, k2[2] = {0, 0};
+    const bool ok = col < D;
+    if (ok) {
+        // shifted-data sums: subtract row 0 so that |mu| >> sigma does not cancel in fp32
+        float2 a = Ld2<T>::ld(z1 + col), b = Ld2<T>::ld(z2 + col);
+        k1[0] = bf16_round(a.x); k1[1] = bf16_round(a.y);
+        k2[0] = bf16_round(b.x); k2[1] = bf16_round(b.y);
+        if (rg == 0) {
+            shift[0][lane * 2] = k1[0]; shift[0][lane * 2 + 1] = k1[1];
+            shift[1][lane * 2] = k2[0]; shift[1][lane * 2 + 1] = k2[1];
+        }
+#pragma unroll 4
+        for (int n = rg; n < N; n += kRowGroups) {
+            float2 a2 = Ld2<T>::ld(z1 + (size_t)n * D + col), b2 = Ld2<T>::ld(z2 + (size_t)n * D + col);
+            // the tensor cores consume bf16: statistics are those of the bf16-rounded embeddings
+            float av[2] = {bf16_round(a2.x), bf16_round(a2.y)}, bv[2] = {bf16_round(b2.x), bf16_round(b2.y)};
+            if (zb1 != nullptr) {
+                Ld2<__nv_bfloat16>::st(zb1 + (size_t)n * D + col, av[0], av[1]);
+                Ld2<__nv_bfloat16>::st(zb2 + (size_t)n * D + col, bv[0], bv[1]);
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float da = av[c] - k1[c], db = bv[c] - k2[c];
+                s1[c] += da; q1[c] = fmaf(da, da, q1[c]);
+                s2[c] += db; q2[c] = fmaf(db, db, q2[c]);
+                x12[c] = fmaf(da, db, x12[c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        red[rg][0][lane * 2 + c] = s1[c]; red[rg][1][lane * 2 + c] = q1[c];
+        red[rg][2][lane * 2 + c] = s2[c]; red[rg][3][lane * 2 + c] = q2[c];
+        red[rg][4][lane * 2 + c] = x12[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < kColsPerBlock) {
+        const int c = threadIdx.x, gc = blockIdx.x * kColsPerBlock + c;
+        if (gc < D) {
+            float t[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+            for (int g = 0; g < kRowGroups; ++g)
+#pragma unroll
+                for (int k = 0; k < 5; ++k) t[k] += red[g][k][c];
+            const float invN = 1.0f / (float)N;
+            const float kk1 = shift[0][c], kk2 = shift[1][c];
+            const float m1 = t[0] * invN, m2 = t[2] * invN;
+            const float var1 = fmaxf(t[1] * invN - m1 * m1, 0.f), var2 = fmaxf(t[3] * invN - m2 * m2, 0.f);
+            const float cov = t[4] * invN - m1 * m2;
+            const float mu1 = kk1 + m1, mu2 = kk2 + m2;
+            const float r1 = rsqrtf(var1 + eps), r2 = rsqrtf(var2 + eps);
+            // one Newton step: rsqrtf is ~2 ulp, BatchNorm uses a correctly rounded 1/sqrt
+            const float r1n = r1 * (1.5f - 0.5f * (var1 + eps) * r1 * r1), r2n = r2 * (1.5f - 0.5f * (var2 + eps) * r2 * r2);
+            stats[S_MU1 * D + gc] = mu1; stats[S_R1 * D + gc] = r1n;
+            stats[S_MU2 * D + gc] = mu2; stats[S_R2 * D + gc] = r2n;
+            stats[S_CDIAG * D + gc] = cov * r1n * r2n;
+            stats[S_NMU1 * D + gc] = -(float)N * mu1;
+            const float rowc = r1n * r1n * invN * invN;
+            stats[S_ROWC * D + gc] = rowc;
+            stats[S_AROW * D + gc] = 2.0f * lambda * rowc;
+            stats[S_RHO1 * D + gc] = r1n * invN;
+            stats[S_BCOL * D + gc] = r2n * r2n;
+            if (running_mean != nullptr) {
+                // BatchNorm1d training-mode side effect, view 1 then view 2 (utils/loss.py:17)
+                const float unb = (N > 1) ? (float)N / (float)(N - 1) : 1.0f;
+                float rm = running_mean[gc], rv = running_var[gc];
+                rm = (1.f - momentum) * rm + momentum * mu1; rv = (1.f - momentum) * rv + momentum * var1 * unb;
+                rm = (1.f - momentum) * rm + momentum * mu2; rv = (1.f - momentum) * rv + momentum * var2 * unb;
+                running_mean[gc] = rm; running_var[gc] = rv;
+            }
+        }
+    }
+}
+
+// row sums of the standardised embeddings (HSIC only): R[n] = sum_j zh[n, j]
+__global__ void __launch_bounds__(256) bt_rowsum_kernel(const __nv_bfloat16* __restrict__ z, int N, int D, const float* __restrict__ mu,
+                                                        const float* __restrict__ r, float* __restrict__ out) {
+    __shared__ float red[8];
+    const int n = blockIdx.x;
+    float acc = 0.f;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) acc += (__bfloat162float(z[(size_t)n * D + c]) - mu[c]) * r[c];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        out[n] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2./3. tcgen05 GEMM kernel (persistent, warp specialised)
+// ------------------------------------------------------------------------------------------
+constexpr int BM = 128;            // UMMA M (TMEM lanes)
+constexpr int BK = 64;             // K elements per pipeline stage (one 128-byte swizzle row)
+constexpr int kStages = 4;
+constexpr int kABytes = BM * BK * 2;       // 16 KiB
+constexpr int kBBytesMax = 256 * BK * 2;   // 32 KiB
+constexpr int kStageBytes = kABytes + kBBytesMax;
+constexpr int kAccCols = 256;      // TMEM columns per accumulator stage
+constexpr int kNumThreads = 384;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// Shared-memory descriptor constants (bytes).  Overridable through abt_debug_set() so that a wrong
+// guess about the descriptor encoding can be diagnosed in one GPU session.
+struct DescCfg {
+    int mn_lbo, mn_sbo, mn_kstep;   // MN-major tiles: 64-element chunk stride, 8-row (K) group stride, bytes per UMMA_K
+    int k_lbo, k_sbo, k_kstep;      // K-major tiles
+};
+static DescCfg g_desc = {8192, 1024, 2048, 16, 1024, 32};
+
+struct UmmaParams {
+    DescCfg dc;
+    int mode;          // 0 = CORR, 1 = GRAD
+    int D, N;
+    int tiles_m, tiles_n, splits, kblocks;   // per pass
+    int pass_first, pass_count;              // GRAD: which passes run (need_grad mask)
+    int bn;            // UMMA N of this launch (multiple of 16, <= 256)
+    int hsic;
+    int write_h;
+    const float* stats;
+    __nv_bfloat16* H;
+    double* loss_acc;
+    float* g1;
+    float* g2;
+};
+
+__device__ __forceinline__ void decode_work(const UmmaParams& p, int w, int& pass, int& tm, int& tn, int& kb0, int& kb1) {
+    const int per_pass = p.tiles_m * p.tiles_n * p.splits;
+    pass = p.pass_first + w / per_pass;
+    int r = w % per_pass;
+    const int split = r % p.splits; r /= p.splits;
+    tn = r % p.tiles_n; tm = r / p.tiles_n;
+    const int per = (p.kblocks + p.splits - 1) / p.splits;
+    kb0 = split * per;
+    kb1 = min(p.kblocks, kb0 + per);
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
+               const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1, const UmmaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_work = p.tiles_m * p.tiles_n * p.splits * p.pass_count;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapB0);
+        if (p.mode == 1) { tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapB1); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps); }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // operand "major-ness": CORR reads both raw embeddings as MN-major tiles; GRAD pass 0 reads H
+    // K-major, pass 1 reads the same H MN-major (i.e. H^T); the GRAD B operand (z rows) is K-major.
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        int stage = 0; uint32_t phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            int pass, tm, tn, kb0, kb1;
+            decode_work(p, w, pass, tm, tn, kb0, kb1);
+            const bool a_mn = (p.mode == 0) || (pass == 1);
+            const bool b_mn = (p.mode == 0);
+            const CUtensorMap* mA = (p.mode == 1 && pass == 1) ? &mapA1 : &mapA0;
+            const CUtensorMap* mB = (p.mode == 1 && pass == 1) ? &mapB1 : &mapB0;
+            const uint32_t tx = kABytes + (uint32_t)p.bn * BK * 2;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sA = smem + stage * kStageBytes;
+                uint8_t* sB = sA + kABytes;
+                mbar_expect_tx(&full_bar[stage], tx);
+                if (a_mn) {
+                    tma_load_2d(sA, mA, &full_bar[stage], tm * BM, kb * BK);
+                    tma_load_2d(sA + 8192, mA, &full_bar[stage], tm * BM + 64, kb * BK);
+                } else {
+                    tma_load_2d(sA, mA, &full_bar[stage], kb * BK, tm * BM);
+                }
+                if (b_mn) {
+                    for (int c = 0; c < p.bn / 64; ++c) tma_load_2d(sB + c * 8192, mB, &full_bar[stage], tn * p.bn + c * 64, kb * BK);
+                } else {
+                    tma_load_2d(sB, mB, &full_bar[stage], kb * BK, tn * p.bn);
+                }
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer (one thread) =================
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            int pass, tm, tn, kb0, kb1;
+            decode_work(p, w, pass, tm, tn, kb0, kb1);
+            const bool a_mn = (p.mode == 0) || (pass == 1);
+            const bool b_mn = (p.mode == 0);
+            const uint32_t idesc = make_idesc_bf16(BM, p.bn, a_mn ? 1 : 0, b_mn ? 1 : 0);
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * kAccCols;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sA = smem_u32(smem + stage * kStageBytes);
+                const uint32_t sB = sA + kABytes;
+#pragma unroll
+                for (int ks = 0; ks < BK / 16; ++ks) {
+                    const uint64_t da = a_mn ? make_smem_desc_sw128(sA + ks * p.dc.mn_kstep, p.dc.mn_lbo, p.dc.mn_sbo)
+                                             : make_smem_desc_sw128(sA + ks * p.dc.k_kstep, p.dc.k_lbo, p.dc.k_sbo);
+                    const uint64_t db = b_mn ? make_smem_desc_sw128(sB + ks * p.dc.mn_kstep, p.dc.mn_lbo, p.dc.mn_sbo)
+                                             : make_smem_desc_sw128(sB + ks * p.dc.k_kstep, p.dc.k_lbo, p.dc.k_sbo);
+                    umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[stage]);   // frees the smem stage when these MMAs retire
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: TMEM -> registers -> global =================
+        const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const int hf = (warp - 4) >> 2;      // which half of the 32-column chunks
+        int acc = 0; uint32_t acc_phase = 0;
+        const int D = p.D;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            int pass, tm, tn, kb0, kb1;
+            decode_work(p, w, pass, tm, tn, kb0, kb1);
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + acc * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+            const int row = tm * BM + q * 32 + lane;     // dimension index owned by this thread
+            const bool row_ok = row < D;
+            if (p.mode == 0) {
+                // ---- CORR: v = S - N mu1_i mu2_j;  c = v r1_i r2_j / N;  H = 2 lambda c r1_i r2_j / N
+                const float* st = p.stats;
+                const float nmu = row_ok ? st[S_NMU1 * D + row] : 0.f;
+                const float arow = row_ok ? st[S_AROW * D + row] : 0.f;
+                const float rowc = row_ok ? st[S_ROWC * D + row] : 0.f;
+                const float rho = row_ok ? st[S_RHO1 * D + row] : 0.f;
+                const float* mu2 = st + S_MU2 * D;
+                const float* r2 = st + S_R2 * D;
+                const float* bcol = st + S_BCOL * D;
+                float l2 = 0.f, l1 = 0.f;
+                const int nchunks = p.bn / 32;
+                for (int ch = hf; ch < nchunks; ch += 2) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_addr + ch * 32, r);
+                    tmem_ld_wait();
+                    const int j0 = tn * p.bn + ch * 32;
+                    if (j0 < D && row_ok) {
+                        uint32_t packed[16];
+#pragma unroll
+                        for (int t4 = 0; t4 < 8; ++t4) {
+                            const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu2 + j0) + t4);
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bcol + j0) + t4);
+                            const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                            float hh[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int t = t4 * 4 + u;
+                                float v = fmaf(nmu, mm[u], __uint_as_float(r[t]));
+                                v = (j0 + t == row) ? 0.f : v;      // diagonal handled in fp32 by the finalize kernel
+                                const float e = v * bb[u];
+                                l2 = fmaf(e, v, l2);
+                                hh[u] = e * arow;
+                                if (p.hsic) l1 = fmaf(v, __ldg(r2 + j0 + t), l1);
+                            }
+                            packed[t4 * 2] = pack_bf16x2(hh[0], hh[1]);
+                            packed[t4 * 2 + 1] = pack_bf16x2(hh[2], hh[3]);
+                        }
+                        if (p.write_h) {
+                            uint4* dst = reinterpret_cast<uint4*>(p.H + (size_t)row * D + j0);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) dst[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+                        }
+                    }
+                }
+                l2 *= rowc; l1 *= rho;
+                l2 = warp_sum(l2);
+                if (p.hsic) l1 = warp_sum(l1);
+                if (lane == 0) {
+                    atomicAdd(p.loss_acc + 0, (double)l2);
+                    if (p.hsic) atomicAdd(p.loss_acc + 1, (double)l1);
+                }
+            } else {
+                // ---- GRAD: fp32 accumulator (dimension row, sample n) -> g[n][row]
+                float* g = (pass == 0) ? p.g1 : p.g2;
+                const int nchunks = (p.bn + 31) / 32;
+                for (int ch = hf; ch < nchunks; ch += 2) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_addr + ch * 32, r);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) {
+                            const int n = tn * p.bn + ch * 32 + t;
+                            if (ch * 32 + t < p.bn && n < p.N) {
+                                float* dst = g + (size_t)n * D + row;
+                                if (p.splits > 1) atomicAdd(dst, __uint_as_float(r[t]));
+                                else *dst = __uint_as_float(r[t]);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// 4. finalize: diagonal term (fp32), batch-norm backward, cast, loss scalar
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bt_finalize_kernel(const T* __restrict__ z1, const T* __restrict__ z2, int N, int D, float alpha,
+                                                          float lambda, int hsic, float grad_scale, int need_mask,
+                                                          const float* __restrict__ stats, const float* __restrict__ g1,
+                                                          const float* __restrict__ g2, const float* __restrict__ rowsum1,
+                                                          const float* __restrict__ rowsum2, T* __restrict__ dz1, T* __restrict__ dz2,
+                                                          double* __restrict__ loss_acc, unsigned int* __restrict__ counters,
+                                                          float* __restrict__ loss_out) {
+    __shared__ float red[kRowGroups][4][kColsPerBlock];
+    __shared__ float mean_s[4][kColsPerBlock];
+    __shared__ float on_red[2];
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int col = blockIdx.x * kColsPerBlock + lane * 2;
+    const bool ok = col < D;
+    const float invN = 1.0f / (float)N;
+    float mu1[2], r1[2], mu2[2], r2[2], gd[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int gc = ok ? col + c : 0;
+        mu1[c] = stats[S_MU1 * D + gc]; r1[c] = stats[S_R1 * D + gc];
+        mu2[c] = stats[S_MU2 * D + gc]; r2[c] = stats[S_R2 * D + gc];
+        gd[c] = 2.0f * alpha * (stats[S_CDIAG * D + gc] - 1.0f) * invN;   // G_ii / N
+    }
+    const float hs = hsic ? 2.0f * lambda * invN : 0.f;
+
+    // gf1[n,i] = g1raw/r1_i + (G_ii/N) zh2[n,i] (+ HSIC: (2 lambda/N)(R2[n] - zh2[n,i]))
+    auto side_grad = [&](int c, float zh_other, float graw, float r_own, float rs_other) -> float {
+        float g = graw / r_own + gd[c] * zh_other;
+        if (hsic) g += hs * (rs_other - zh_other);
+        return g;
+    };
+
+    if (need_mask != 0) {
+        float a1[2] = {0, 0}, b1[2] = {0, 0}, a2[2] = {0, 0}, b2[2] = {0, 0};
+        if (ok) {
+            for (int n = rg; n < N; n += kRowGroups) {
+                const size_t o = (size_t)n * D + col;
+                const float2 za = Ld2<T>::ld(z1 + o), zb = Ld2<T>::ld(z2 + o);
+                const float zav[2] = {bf16_round(za.x), bf16_round(za.y)}, zbv[2] = {bf16_round(zb.x), bf16_round(zb.y)};
+                float2 ga = make_float2(0, 0), gb = make_float2(0, 0);
+                if (need_mask & 1) ga = *reinterpret_cast<const float2*>(g1 + o);
+                if (need_mask & 2) gb = *reinterpret_cast<const float2*>(g2 + o);
+                const float gav[2] = {ga.x, ga.y}, gbv[2] = {gb.x, gb.y};
+                const float rs1 = hsic ? rowsum1[n] : 0.f, rs2 = hsic ? rowsum2[n] : 0.f;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const float zh1 = (zav[c] - mu1[c]) * r1[c], zh2 = (zbv[c] - mu2[c]) * r2[c];
+                    const float gf1 = side_grad(c, zh2, gav[c], r1[c], rs2);
+                    const float gf2 = side_grad(c, zh1, gbv[c], r2[c], rs1);
+                    a1[c] += gf1; b1[c] = fmaf(gf1, zh1, b1[c]);
+                    a2[c] += gf2; b2[c] = fmaf(gf2, zh2, b2[c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            red[rg][0][lane * 2 + c] = a1[c]; red[rg][1][lane * 2 + c] = b1[c];
+            red[rg][2][lane * 2 + c] = a2[c]; red[rg][3][lane * 2 + c] = b2[c];
+        }
+        __syncthreads();
+        if (threadIdx.x < kColsPerBlock) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float t = 0.f;
+#pragma unroll
+                for (int g = 0; g < kRowGroups; ++g) t += red[g][k][threadIdx.x];
+                mean_s[k][threadIdx.x] = t * invN;
+            }
+        }
+        __syncthreads();
+        if (ok) {
+            for (int n = rg; n < N; n += kRowGroups) {
+                const size_t o = (size_t)n * D + col;
+                const float2 za = Ld2<T>::ld(z1 + o), zb = Ld2<T>::ld(z2 + o);
+                const float zav[2] = {bf16_round(za.x), bf16_round(za.y)}, zbv[2] = {bf16_round(zb.x), bf16_round(zb.y)};
+                float2 ga = make_float2(0, 0), gb = make_float2(0, 0);
+                if (need_mask & 1) ga = *reinterpret_cast<const float2*>(g1 + o);
+                if (need_mask & 2) gb = *reinterpret_cast<const float2*>(g2 + o);
+                const float gav[2] = {ga.x, ga.y}, gbv[2] = {gb.x, gb.y};
+                const float rs1 = hsic ? rowsum1[n] : 0.f, rs2 = hsic ? rowsum2[n] : 0.f;
+                float o1[2], o2[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const float zh1 = (zav[c] - mu1[c]) * r1[c], zh2 = (zbv[c] - mu2[c]) * r2[c];
+                    const float gf1 = side_grad(c, zh2, gav[c], r1[c], rs2);
+                    const float gf2 = side_grad(c, zh1, gbv[c], r2[c], rs1);
+                    const int cc = lane * 2 + c;
+                    o1[c] = r1[c] * (gf1 - mean_s[0][cc] - zh1 * mean_s[1][cc]) * grad_scale;
+                    o2[c] = r2[c] * (gf2 - mean_s[2][cc] - zh2 * mean_s[3][cc]) * grad_scale;
+                }
+                if (need_mask & 1) Ld2<T>::st(dz1 + o, o1[0], o1[1]);
+                if (need_mask & 2) Ld2<T>::st(dz2 + o, o2[0], o2[1]);
+            }
+        }
+    }
+    // on-diagonal loss: sum_i (C_ii - 1)^2, one column per thread of the first 64 threads
+    float on = 0.f;
+    if (threadIdx.x < kColsPerBlock) {
+        const int gc = blockIdx.x * kColsPerBlock + threadIdx.x;
+        if (gc < D) { const float d = stats[S_CDIAG * D + gc] - 1.0f; on = d * d; }
+    }
+    on = warp_sum(on);
+    if (threadIdx.x < kColsPerBlock && lane == 0) on_red[threadIdx.x >> 5] = on;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(loss_acc + 2, (double)(on_red[0] + on_red[1]));
+        __threadfence();
+        const unsigned int done = atomicAdd(counters, 1u);
+        if (done == gridDim.x - 1) {
+            __threadfence();
+            const double off2 = *((volatile double*)(loss_acc + 0));
+            const double off1 = *((volatile double*)(loss_acc + 1));
+            const double ond = *((volatile double*)(loss_acc + 2));
+            double off = off2;
+            if (hsic) off = off2 + 2.0 * off1 + (double)D * (double)(D - 1);
+            *loss_out = (float)((double)alpha * ond + (double)lambda * off);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || sym == nullptr) return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// bf16 row-major matrix (rows x cols), box = (box_cols x box_rows) with 128-byte swizzle
+static int make_map_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return set_error(ABT_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(ABT_ERR_CUDA, "cuTensorMapEncodeTiled failed (code %d)", (int)r);
+    return 0;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct WsLayout {
+    size_t stats, H, g1, g2, zb1, zb2, rs1, rs2, misc, total;
+};
+
+static WsLayout ws_layout(int N, int D, int dtype) {
+    WsLayout L{};
+    size_t off = 0;
+    L.misc = off; off += 256;
+    L.stats = off; off = align_up(off + sizeof(float) * S_COUNT * (size_t)D, 256);
+    L.rs1 = off; off = align_up(off + sizeof(float) * (size_t)N, 256);
+    L.rs2 = off; off = align_up(off + sizeof(float) * (size_t)N, 256);
+    L.g1 = off; off = align_up(off + sizeof(float) * (size_t)N * D, 256);
+    L.g2 = off; off = align_up(off + sizeof(float) * (size_t)N * D, 256);
+    L.zb1 = off; if (dtype != ABT_DTYPE_BF16) off = align_up(off + 2 * (size_t)N * D, 256);
+    L.zb2 = off; if (dtype != ABT_DTYPE_BF16) off = align_up(off + 2 * (size_t)N * D, 256);
+    L.H = off; off = align_up(off + 2 * (size_t)D * D, 256);
+    L.total = off;
+    return L;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <typename T>
+static int launch_all(const abt_bt_args* a, const WsLayout& L, cudaStream_t stream) {
+    const int N = a->n_rows, D = a->n_dims;
+    uint8_t* ws = static_cast<uint8_t*>(a->workspace);
+    float* stats = reinterpret_cast<float*>(ws + L.stats);
+    double* loss_acc = reinterpret_cast<double*>(ws + L.misc);
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws + L.misc + 64);
+    float* g1 = reinterpret_cast<float*>(ws + L.g1);
+    float* g2 = reinterpret_cast<float*>(ws + L.g2);
+    float* rs1 = reinterpret_cast<float*>(ws + L.rs1);
+    float* rs2 = reinterpret_cast<float*>(ws + L.rs2);
+    __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(ws + L.H);
+    const bool is_bf16 = (a->dtype == ABT_DTYPE_BF16);
+    __nv_bfloat16* zb1 = is_bf16 ? nullptr : reinterpret_cast<__nv_bfloat16*>(ws + L.zb1);
+    __nv_bfloat16* zb2 = is_bf16 ? nullptr : reinterpret_cast<__nv_bfloat16*>(ws + L.zb2);
+    const __nv_bfloat16* zq1 = is_bf16 ? static_cast<const __nv_bfloat16*>(a->z1) : zb1;
+    const __nv_bfloat16* zq2 = is_bf16 ? static_cast<const __nv_bfloat16*>(a->z2) : zb2;
+    const int need = a->need_grad_mask & 3;
+    const int col_blocks = (D + kColsPerBlock - 1) / kColsPerBlock;
+
+    bt_stats_kernel<T><<<col_blocks, 256, 0, stream>>>(static_cast<const T*>(a->z1), static_cast<const T*>(a->z2), N, D, a->eps, a->lambda,
+                                                        a->momentum, stats, zb1, zb2, a->running_mean, a->running_var, loss_acc, counters);
+    if (a->hsic) {
+        bt_rowsum_kernel<<<N, 256, 0, stream>>>(zq1, N, D, stats + S_MU1 * D, stats + S_R1 * D, rs1);
+        bt_rowsum_kernel<<<N, 256, 0, stream>>>(zq2, N, D, stats + S_MU2 * D, stats + S_R2 * D, rs2);
+    }
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(bt_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+
+    // ---- CORR
+    {
+        CUtensorMap mA, mB;
+        if (int rc = make_map_bf16(&mA, zq1, N, D, 64, 64)) return rc;
+        if (int rc = make_map_bf16(&mB, zq2, N, D, 64, 64)) return rc;
+        UmmaParams p{};
+        p.dc = g_desc;
+        p.mode = 0; p.D = D; p.N = N;
+        p.bn = 256;
+        p.tiles_m = (D + BM - 1) / BM; p.tiles_n = (D + p.bn - 1) / p.bn; p.splits = 1;
+        p.kblocks = (N + BK - 1) / BK;
+        p.pass_first = 0; p.pass_count = 1;
+        p.hsic = a->hsic; p.write_h = need != 0;
+        p.stats = stats; p.H = H; p.loss_acc = loss_acc; p.g1 = g1; p.g2 = g2;
+        const int total = p.tiles_m * p.tiles_n;
+        const int grid = total < num_sms() ? total : num_sms();
+        bt_umma_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(mA, mB, mA, mB, p);
+    }
+    // ---- GRAD
+    if (need != 0) {
+        int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
+        CUtensorMap mHk, mHmn, mZ2, mZ1;
+        if (int rc = make_map_bf16(&mHk, H, D, D, 64, 128)) return rc;
+        if (int rc = make_map_bf16(&mHmn, H, D, D, 64, 64)) return rc;
+        if (int rc = make_map_bf16(&mZ2, zq2, N, D, 64, bn)) return rc;
+        if (int rc = make_map_bf16(&mZ1, zq1, N, D, 64, bn)) return rc;
+        UmmaParams p{};
+        p.dc = g_desc;
+        p.mode = 1; p.D = D; p.N = N; p.bn = bn;
+        p.tiles_m = (D + BM - 1) / BM; p.tiles_n = (N + bn - 1) / bn;
+        p.kblocks = (D + BK - 1) / BK;
+        p.pass_first = (need & 1) ? 0 : 1;
+        p.pass_count = (need == 3) ? 2 : 1;
+        const int tiles = p.tiles_m * p.tiles_n * p.pass_count;
+        int splits = num_sms() / tiles;
+        if (splits < 1) splits = 1;
+        while (splits > 1 && p.kblocks / splits < 8) --splits;      // keep >= 8 k-blocks per split
+        {   // no empty split: every work item must issue at least one MMA
+            const int per = (p.kblocks + splits - 1) / splits;
+            splits = (p.kblocks + per - 1) / per;
+        }
+        p.splits = splits;
+        p.hsic = a->hsic; p.write_h = 0;
+        p.stats = stats; p.H = H; p.loss_acc = loss_acc; p.g1 = g1; p.g2 = g2;
+        if (splits > 1) {
+            if (need & 1) cudaMemsetAsync(g1, 0, sizeof(float) * (size_t)N * D, stream);
+            if (need & 2) cudaMemsetAsync(g2, 0, sizeof(float) * (size_t)N * D, stream);
+        }
+        const int total = tiles * splits;
+        const int grid = total < num_sms() ? total : num_sms();
+        bt_umma_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(mHk, mZ2, mHmn, mZ1, p);
+    }
+    bt_finalize_kernel<T><<<col_blocks, 256, 0, stream>>>(static_cast<const T*>(a->z1), static_cast<const T*>(a->z2), N, D, a->alpha, a->lambda,
+                                                           a->hsic, a->grad_scale, need, stats, g1, g2, rs1, rs2, static_cast<T*>(a->dz1),
+                                                           static_cast<T*>(a->dz2), loss_acc, counters, a->loss_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "bt loss launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace abt
+
+using namespace abt;
+
+extern "C" int abt_debug_set(int key, int value) {
+    int* f[6] = {&g_desc.mn_lbo, &g_desc.mn_sbo, &g_desc.mn_kstep, &g_desc.k_lbo, &g_desc.k_sbo, &g_desc.k_kstep};
+    if (key < 0 || key >= 6) return set_error(ABT_ERR_ARG, "unknown debug key %d", key);
+    *f[key] = value;
+    return 0;
+}
+
+// Debug view of the workspace layout (byte offsets), used by tools/gpu_diag.py only.
+extern "C" int abt_debug_ws_offsets(int n_rows, int n_dims, int dtype, size_t* out8) {
+    const WsLayout L = ws_layout(n_rows, n_dims, dtype);
+    out8[0] = L.stats; out8[1] = L.H; out8[2] = L.g1; out8[3] = L.g2; out8[4] = L.zb1; out8[5] = L.zb2; out8[6] = L.misc; out8[7] = L.total;
+    return 0;
+}
+
+extern "C" int abt_bt_workspace_bytes(int n_rows, int n_dims, int dtype, size_t* bytes) {
+    if (bytes == nullptr) return set_error(ABT_ERR_ARG, "bytes is null");
+    if (n_rows < 2 || n_dims < 64 || (n_dims % 64) != 0) return set_error(ABT_ERR_ARG, "need n_rows >= 2 and n_dims a multiple of 64 (got %d x %d)", n_rows, n_dims);
+    if (dtype < 0 || dtype > 2) return set_error(ABT_ERR_ARG, "unknown dtype %d", dtype);
+    *bytes = ws_layout(n_rows, n_dims, dtype).total;
+    return 0;
+}
+
+extern "C" int abt_bt_loss_fwd_bwd(const abt_bt_args* a, abt_stream_t stream) {
+    if (a == nullptr) return set_error(ABT_ERR_ARG, "args is null");
+    if (a->n_rows < 2 || a->n_dims < 64 || (a->n_dims % 64) != 0)
+        return set_error(ABT_ERR_ARG, "need n_rows >= 2 and n_dims a multiple of 64 (got %d x %d)", a->n_rows, a->n_dims);
+    if (a->z1 == nullptr || a->z2 == nullptr || a->loss_out == nullptr || a->workspace == nullptr) return set_error(ABT_ERR_ARG, "null pointer argument");
+    if ((a->need_grad_mask & 1) && a->dz1 == nullptr) return set_error(ABT_ERR_ARG, "dz1 is null but requested");
+    if ((a->need_grad_mask & 2) && a->dz2 == nullptr) return set_error(ABT_ERR_ARG, "dz2 is null but requested");
+    const WsLayout L = ws_layout(a->n_rows, a->n_dims, a->dtype);
+    if (a->workspace_bytes < L.total) return set_error(ABT_ERR_ARG, "workspace too small: %zu < %zu", a->workspace_bytes, L.total);
+    if ((reinterpret_cast<uintptr_t>(a->workspace) & 255) != 0) return set_error(ABT_ERR_ARG, "workspace must be 256-byte aligned");
+    if (int rc = check_device_sm100()) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    switch (a->dtype) {
+        case ABT_DTYPE_BF16: return launch_all<__nv_bfloat16>(a, L, s);
+        case ABT_DTYPE_F16: return launch_all<__half>(a, L, s);
+        case ABT_DTYPE_F32: return launch_all<float>(a, L, s);
+        default: return set_error(ABT_ERR_ARG, "unknown dtype %d", a->dtype);
+    }
+}

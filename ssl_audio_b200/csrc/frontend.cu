@@ -1,0 +1,535 @@
+// Audio frontend for sm_100a: wav -> power STFT -> HTK mel -> log -> z-score, fused in one kernel.
+//
+// Replaces torchaudio.transforms.MelSpectrogram as the reference constructs it at
+// datasets.py:39-48 (n_fft 1024, hop 160, periodic Hann, center/reflect, power 2, 64 HTK mel
+// bands without norm), `(mel + eps).log()` (datasets.py:115) and `(lms - mean)/std`
+// (datasets.py:118-119).  Reference tree: /root/reference.
+//
+// Kernel shape (HBM/FP32-bound, no tensor cores: a 1024-point DFT in split bf16/tf32 fails the
+// 1e-3 log-mel tolerance):
+//   * one CTA = one clip x 32 consecutive frames; the (31*hop + 1024)-sample span is staged once
+//     in shared memory with coalesced loads (reflect padding resolved by index mirroring);
+//   * one warp = two frames at a time, packed as re/im of ONE 1024-point complex FFT
+//     (two-for-one real FFT).  1024 = 32 x 32: each lane runs an in-register 32-point FFT, the
+//     warp transposes through a padded (bank-conflict-free) shared tile, each lane runs a second
+//     32-point FFT;  X[k] and X[1024-k] are recombined into the two power spectra;
+//   * the mel projection uses the filterbank's sparsity (<= 2 filters per bin, 970 non-zeros of
+//     32832): each lane gathers two mel bands from the shared power spectrum (CSR);
+//   * log, z-score, and a staged, time-contiguous (coalesced) store.
+#include "abt_internal.h"
+#include "fft32_gen.cuh"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+struct abt_logmel_plan {
+    abt_mel_config cfg;
+    float* d_window;   // n_fft, win_length window centre-padded
+    float2* d_twiddle; // [k2][n1] -> exp(-2 pi i n1 k2 / 1024)
+    int* d_mel_start;  // 64
+    int* d_mel_len;    // 64
+    int* d_mel_off;    // 64, offset into d_mel_w
+    float* d_mel_w;    // nnz
+    int nnz;
+    int max_len;
+};
+
+namespace abt {
+
+constexpr int kNfft = 1024;
+constexpr int kMels = 64;
+constexpr int kTileFrames = 32;
+constexpr int kWarps = 8;
+constexpr int kScratchFloats = 2 * 32 * 33;   // per warp
+constexpr float kF32Eps = 1.1920928955078125e-07f;
+
+struct LogmelArgs {
+    const float* wav;
+    long long row_stride;
+    const int* wav_offset;
+    int n_samples;
+    int n_frames_total;    // 1 + n_samples / hop
+    int hop;
+    const int* frame_start;   // mode C: first frame per clip; nullptr in mode F
+    int n_frames_out;         // frames written per clip (mode F: n_frames_total)
+    float* out_base;
+    const int* out_slot;
+    long long out_slot_stride;
+    int apply_norm;
+    float norm_mean, inv_std;
+    float pad_value;          // value of frames beyond the clip end (already normalised)
+    const float* window;
+    const float2* twiddle;
+    const int* mel_start;
+    const int* mel_len;
+    const int* mel_off;
+    const float* mel_w;
+    int nnz;
+};
+
+__global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs a) {
+    extern __shared__ float smem[];
+    const int span = (kTileFrames - 1) * a.hop + kNfft;
+    float* s_x = smem;                                  // span samples (padded coordinates)
+    float* s_scratch = s_x + ((span + 31) & ~31);       // kWarps * kScratchFloats
+    float* s_out = s_scratch + kWarps * kScratchFloats; // kMels * (kTileFrames + 1)
+    float* s_melw = s_out + kMels * (kTileFrames + 1);  // nnz
+    int* s_mel_start = reinterpret_cast<int*>(s_melw + a.nnz);   // 64 start, 64 len, 64 off
+
+    const int clip = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f_first = (a.frame_start ? a.frame_start[clip] : 0) + tile * kTileFrames;   // absolute frame index
+    const float* wav = a.wav + (long long)clip * a.row_stride + (a.wav_offset ? a.wav_offset[clip] : 0);
+
+    // ---- stage the sample span (reflect padding: padded index s -> original s - n_fft/2, mirrored)
+    const long long s0 = (long long)f_first * a.hop;
+    for (int s = tid; s < span; s += blockDim.x) {
+        long long o = s0 + s - kNfft / 2;
+        if (o < 0) o = -o;
+        if (o >= a.n_samples) o = 2LL * (a.n_samples - 1) - o;
+        float v = 0.f;
+        if (o >= 0 && o < a.n_samples) v = __ldg(wav + o);
+        s_x[s] = v;
+    }
+    for (int i = tid; i < a.nnz; i += blockDim.x) s_melw[i] = a.mel_w[i];
+    if (tid < kMels) {
+        s_mel_start[tid] = a.mel_start[tid];
+        s_mel_start[kMels + tid] = a.mel_len[tid];
+        s_mel_start[2 * kMels + tid] = a.mel_off[tid];
+    }
+    __syncthreads();
+
+    float* sre = s_scratch + warp * kScratchFloats;
+    float* sim = sre + 32 * 33;
+
+    for (int round = 0; round < kTileFrames / (2 * kWarps); ++round) {
+        const int fa = round * 2 * kWarps + 2 * warp;     // local frame indices of this warp's pair
+        const int fb = fa + 1;
+        const bool any_valid = (f_first + fa) < a.n_frames_total && (tile * kTileFrames + fa) < a.n_frames_out;
+        if (any_valid) {   // warp-uniform
+            float re[32], im[32];
+            // frame a -> real part, frame b -> imaginary part; lane = n1, register = n2, n = n1 + 32 n2
+            const float* xa = s_x + fa * a.hop;
+            const float* xb = s_x + fb * a.hop;
+#pragma unroll
+            for (int n2 = 0; n2 < 32; ++n2) {
+                const int n = lane + 32 * n2;
+                const float w = __ldg(a.window + n);
+                re[n2] = xa[n] * w;
+                im[n2] = xb[n] * w;
+            }
+            fft32(re, im);   // register p: Y[n1 = lane][k2 = bitrev(p)]
+            // twiddle W1024^(n1 k2) and transpose through shared memory
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                const int k2 = bitrev5(p);
+                const float2 w = __ldg(a.twiddle + k2 * 32 + lane);
+                const float yr = re[p] * w.x - im[p] * w.y;
+                const float yi = re[p] * w.y + im[p] * w.x;
+                sre[lane * 33 + k2] = yr;
+                sim[lane * 33 + k2] = yi;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {     // lane = k2, register = n1
+                re[n1] = sre[n1 * 33 + lane];
+                im[n1] = sim[n1 * 33 + lane];
+            }
+            fft32(re, im);   // register p: X[32 k1 + k2], k1 = bitrev(p), k2 = lane
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                const int k1 = bitrev5(p);
+                sre[k1 * 33 + lane] = re[p];
+                sim[k1 * 33 + lane] = im[p];
+            }
+            __syncwarp();
+            // power spectra of the two real frames for bins k = 32 k1 + lane, k1 < 16 (and k = 512 on lane 0)
+            float pa[17], pb[17];
+            const int lp = (32 - lane) & 31;
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                const int k1 = bitrev5(p);
+                if (k1 < 16) {
+                    const int k1p = (lane == 0) ? ((32 - k1) & 31) : (31 - k1);
+                    const float qr = sre[k1p * 33 + lp], qi = sim[k1p * 33 + lp];   // X[1024 - k]
+                    const float ar = re[p] + qr, ai = im[p] - qi;     // 2 A[k]
+                    const float br = im[p] + qi, bi = qr - re[p];     // 2 B[k]
+                    pa[k1] = 0.25f * (ar * ar + ai * ai);
+                    pb[k1] = 0.25f * (br * br + bi * bi);
+                }
+                if (k1 == 16) {   // k = 512 lives on lane 0; X[512] pairs with itself
+                    pa[16] = re[p] * re[p];
+                    pb[16] = im[p] * im[p];
+                }
+            }
+            __syncwarp();
+            float* spa = sre;            // 520 floats per frame
+            float* spb = sre + 520;
+#pragma unroll
+            for (int k1 = 0; k1 < 16; ++k1) {
+                spa[32 * k1 + lane] = pa[k1];
+                spb[32 * k1 + lane] = pb[k1];
+            }
+            if (lane == 0) { spa[512] = pa[16]; spb[512] = pb[16]; }
+            __syncwarp();
+            // sparse mel projection: this lane owns bands `lane` and `63 - lane`
+#pragma unroll
+            for (int hm = 0; hm < 2; ++hm) {
+                const int m = hm == 0 ? lane : (kMels - 1 - lane);
+                const int ks = s_mel_start[m], kl = s_mel_start[kMels + m];
+                const float* w = s_melw + s_mel_start[2 * kMels + m];
+                float ma = 0.f, mb = 0.f;
+                for (int t = 0; t < kl; ++t) {
+                    const float wt = w[t];
+                    ma = fmaf(wt, spa[ks + t], ma);
+                    mb = fmaf(wt, spb[ks + t], mb);
+                }
+                float la = logf(ma + kF32Eps), lb = logf(mb + kF32Eps);
+                if (a.apply_norm) { la = (la - a.norm_mean) * a.inv_std; lb = (lb - a.norm_mean) * a.inv_std; }
+                s_out[m * (kTileFrames + 1) + fa] = la;
+                s_out[m * (kTileFrames + 1) + fb] = lb;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // ---- coalesced store: rows of up to 32 consecutive frames per mel band
+    const long long slot = a.out_slot ? a.out_slot[clip] : clip;
+    float* out = a.out_base + slot * a.out_slot_stride;
+    const int t_base = tile * kTileFrames;       // frame offset inside the output row
+    for (int idx = tid; idx < kMels * kTileFrames; idx += blockDim.x) {
+        const int m = idx / kTileFrames, f = idx % kTileFrames;
+        const int t_out = t_base + f;
+        if (t_out < a.n_frames_out) {
+            const bool real = (f_first + f) < a.n_frames_total;
+            out[(size_t)m * a.n_frames_out + t_out] = real ? s_out[m * (kTileFrames + 1) + f] : a.pad_value;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// precomputed log-mel: time crop / right pad + z-score  (datasets.py:342-354)
+// ------------------------------------------------------------------------------------------
+__global__ void lms_crop_norm_kernel(const float* __restrict__ lms, int n_mels, int t_full, const int* __restrict__ frame_start, int n_frames,
+                                     int apply_norm, float mean, float inv_std, float* __restrict__ out_base,
+                                     const int* __restrict__ out_slot, long long out_slot_stride) {
+    const int clip = blockIdx.y;
+    const int start = frame_start ? frame_start[clip] : 0;
+    const long long slot = out_slot ? out_slot[clip] : clip;
+    float* out = out_base + slot * out_slot_stride;
+    const float* src = lms + (size_t)clip * n_mels * t_full;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_mels * n_frames; idx += gridDim.x * blockDim.x) {
+        const int m = idx / n_frames, t = idx % n_frames;
+        const int ts = (start < 0 ? 0 : start) + t;
+        float v = (ts < t_full) ? src[(size_t)m * t_full + ts] : 0.0f;   // right zero-pad BEFORE normalisation
+        if (apply_norm) v = (v - mean) * inv_std;
+        out[idx] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// views: Mixup -> RandomResizeCrop (bicubic, align_corners) -> RandomLinearFader
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cubic1(float x) {   // |x| <= 1, A = -0.75
+    return ((-0.75f + 2.0f) * x - (-0.75f + 3.0f)) * x * x + 1.0f;
+}
+__device__ __forceinline__ float cubic2(float x) {   // 1 < |x| < 2
+    return ((-0.75f * x - 5.0f * -0.75f) * x + 8.0f * -0.75f) * x - 4.0f * -0.75f;
+}
+
+__global__ void __launch_bounds__(256) views_kernel(const abt_views_args a) {
+    extern __shared__ float smem[];
+    float* canvas = smem;                                     // canvas_h * canvas_w
+    float* coef = canvas + a.canvas_h * a.canvas_w;           // (out_w + out_h) * 4 coefficients
+    int* tap = reinterpret_cast<int*>(coef + (a.out_w + a.out_h) * 4);   // (out_w + out_h) * 4 clamped taps
+    const int clip = blockIdx.x, view = blockIdx.y;
+    const int tid = threadIdx.x;
+    const abt_view_params p = a.params[clip * a.n_views + view];
+    const long long xs = a.x_slot ? a.x_slot[clip] : clip;
+    const float* x = a.x + xs * a.x_slot_stride;
+    const float* z = nullptr;
+    if ((p.flags & 1) && p.z_kind == 1) z = a.bank + (long long)p.z_index * a.bank_slot_stride;
+    if ((p.flags & 1) && p.z_kind == 2) z = a.x + (long long)(a.x_slot ? a.x_slot[p.z_index] : p.z_index) * a.x_slot_stride;
+
+    const int y0 = (a.canvas_h - a.in_h) / 2, x0 = (a.canvas_w - a.in_w) / 2;
+    for (int idx = tid; idx < a.canvas_h * a.canvas_w; idx += blockDim.x) canvas[idx] = 0.f;
+    __syncthreads();
+    // log-mixup-exp into the centre of the virtual canvas (augmentations.py:43-48, :81-85)
+    const int n_in = a.in_h * a.in_w;
+    for (int idx = tid * 4; idx < n_in; idx += blockDim.x * 4) {
+        float4 xv = *reinterpret_cast<const float4*>(x + idx);
+        float v[4] = {xv.x, xv.y, xv.z, xv.w};
+        if (z != nullptr) {
+            const float4 zv = *reinterpret_cast<const float4*>(z + idx);
+            const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = logf(p.w_x * expf(v[k]) + p.w_z * expf(zz[k]) + kF32Eps);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = idx + k, r = e / a.in_w, c = e % a.in_w;
+            canvas[(y0 + r) * a.canvas_w + x0 + c] = v[k];
+        }
+    }
+    // bicubic tables (ATen upsample_bicubic2d, align_corners=True): src = dst * (in-1)/(out-1)
+    const bool rrc = (p.flags & 2) != 0;
+    const int ci = rrc ? p.i : y0, cj = rrc ? p.j : x0, chh = rrc ? p.h : a.in_h, cww = rrc ? p.w : a.in_w;
+    if (tid < a.out_w + a.out_h) {
+        const bool is_x = tid < a.out_w;
+        const int o = is_x ? tid : tid - a.out_w;
+        const int n_in_ax = is_x ? cww : chh, n_out_ax = is_x ? a.out_w : a.out_h;
+        const float scale = n_out_ax > 1 ? (float)(n_in_ax - 1) / (float)(n_out_ax - 1) : 0.f;
+        const float pos = scale * (float)o;
+        const float fl = floorf(pos);
+        const float t = pos - fl;
+        const int base = (int)fl;
+        const float c4[4] = {cubic2(t + 1.0f), cubic1(t), cubic1(1.0f - t), cubic2(2.0f - t)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int s = base - 1 + k;
+            s = s < 0 ? 0 : (s > n_in_ax - 1 ? n_in_ax - 1 : s);
+            tap[tid * 4 + k] = s + (is_x ? cj : ci);
+            coef[tid * 4 + k] = c4[k];
+        }
+    }
+    __syncthreads();
+    // fader: torch.linspace(head, tail, T) evaluated from both ends with one rounding (fma)
+    const bool fade = (p.flags & 4) != 0;
+    const float step = a.out_w > 1 ? (p.tail - p.head) / (float)(a.out_w - 1) : 0.f;
+    float* out = a.outs[p.out_index] + (size_t)clip * a.out_h * a.out_w;
+    const int n_out = a.out_h * a.out_w;
+    for (int idx = tid; idx < n_out; idx += blockDim.x) {
+        const int oy = idx / a.out_w, ox = idx % a.out_w;
+        const int* tx = tap + ox * 4;
+        const float* cx = coef + ox * 4;
+        const int* ty = tap + (a.out_w + oy) * 4;
+        const float* cy = coef + (a.out_w + oy) * 4;
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float* row = canvas + ty[r] * a.canvas_w;
+            const float hsum = row[tx[0]] * cx[0] + row[tx[1]] * cx[1] + row[tx[2]] * cx[2] + row[tx[3]] * cx[3];
+            acc += hsum * cy[r];
+        }
+        if (fade) {
+            const float s = (ox < a.out_w / 2) ? fmaf(step, (float)ox, p.head) : fmaf(-step, (float)(a.out_w - 1 - ox), p.tail);
+            acc += s;
+        }
+        out[idx] = acc;
+    }
+}
+
+__global__ void bank_push_kernel(const float* __restrict__ x, long long x_stride, int clip_elems, float* __restrict__ bank,
+                                 long long bank_slot_stride, const int* __restrict__ slot) {
+    const int clip = blockIdx.y;
+    const float4* src = reinterpret_cast<const float4*>(x + (long long)clip * x_stride);
+    float4* dst = reinterpret_cast<float4*>(bank + (long long)slot[clip] * bank_slot_stride);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < clip_elems / 4; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// host: plan tables
+// ------------------------------------------------------------------------------------------
+static std::vector<float> linspace_f32(double start, double end, int steps) {
+    // torch.linspace(dtype=float32): fp32 step, halves evaluated from each end with one rounding
+    std::vector<float> v(steps);
+    const float s32 = (float)start, e32 = (float)end;
+    if (steps == 1) { v[0] = s32; return v; }
+    const float step = (e32 - s32) / (float)(steps - 1);
+    for (int i = 0; i < steps; ++i)
+        v[i] = (i < steps / 2) ? (float)((double)s32 + (double)step * i) : (float)((double)e32 - (double)step * (steps - 1 - i));
+    return v;
+}
+
+}  // namespace abt
+
+using namespace abt;
+
+#define ABT_CUDA_OK(expr)                                                                  \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess) return set_error(ABT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" int abt_logmel_plan_create(const abt_mel_config* cfg, abt_logmel_plan** plan_out) {
+    if (cfg == nullptr || plan_out == nullptr) return set_error(ABT_ERR_ARG, "null argument");
+    if (cfg->n_fft != kNfft) return set_error(ABT_ERR_ARG, "n_fft must be 1024 (got %d)", cfg->n_fft);
+    if (cfg->n_mels != kMels) return set_error(ABT_ERR_ARG, "n_mels must be 64 (got %d)", cfg->n_mels);
+    if (cfg->win_length < 1 || cfg->win_length > kNfft) return set_error(ABT_ERR_ARG, "win_length must be in [1, 1024]");
+    if (cfg->hop_length < 1 || cfg->hop_length > 1024) return set_error(ABT_ERR_ARG, "hop_length must be in [1, 1024]");
+    if (cfg->apply_norm && !(cfg->norm_std > 0.f)) return set_error(ABT_ERR_ARG, "norm_std must be > 0");
+    if (int rc = check_device_sm100()) return rc;
+
+    // window: periodic Hann(win_length), centre-padded to n_fft (torch.stft)
+    std::vector<float> win(kNfft, 0.f);
+    const int left = (kNfft - cfg->win_length) / 2;
+    for (int n = 0; n < cfg->win_length; ++n) win[left + n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * n / cfg->win_length));
+    // twiddles [k2][n1]
+    std::vector<float2> tw(1024);
+    for (int k2 = 0; k2 < 32; ++k2)
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const double ang = -2.0 * M_PI * (double)(n1 * k2) / 1024.0;
+            tw[k2 * 32 + n1] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+    // HTK mel filterbank, norm=None (torchaudio/functional/functional.py:518-587), as CSR per band
+    const int n_freqs = kNfft / 2 + 1;
+    std::vector<float> all_freqs = linspace_f32(0.0, (double)(cfg->sample_rate / 2), n_freqs);
+    const double m_min = 2595.0 * std::log10(1.0 + (double)cfg->f_min / 700.0);
+    const double m_max = 2595.0 * std::log10(1.0 + (double)cfg->f_max / 700.0);
+    std::vector<float> m_pts = linspace_f32(m_min, m_max, kMels + 2);
+    std::vector<float> f_pts(kMels + 2);
+    for (int i = 0; i < kMels + 2; ++i) f_pts[i] = 700.0f * (std::pow(10.0f, m_pts[i] / 2595.0f) - 1.0f);
+    std::vector<int> start(kMels), len(kMels), off(kMels);
+    std::vector<float> weights;
+    int max_len = 0;
+    for (int m = 0; m < kMels; ++m) {
+        const float fd0 = f_pts[m + 1] - f_pts[m], fd1 = f_pts[m + 2] - f_pts[m + 1];
+        int first = -1, last = -1;
+        std::vector<float> col(n_freqs);
+        for (int k = 0; k < n_freqs; ++k) {
+            const float down = -(f_pts[m] - all_freqs[k]) / fd0;
+            const float up = (f_pts[m + 2] - all_freqs[k]) / fd1;
+            const float v = std::fmax(0.0f, std::fmin(down, up));
+            col[k] = v;
+            if (v > 0.f) { if (first < 0) first = k; last = k; }
+        }
+        start[m] = first < 0 ? 0 : first;
+        len[m] = first < 0 ? 0 : last - first + 1;
+        off[m] = (int)weights.size();
+        for (int k = 0; k < len[m]; ++k) weights.push_back(col[start[m] + k]);
+        if (len[m] > max_len) max_len = len[m];
+    }
+
+    abt_logmel_plan* pl = static_cast<abt_logmel_plan*>(std::calloc(1, sizeof(abt_logmel_plan)));
+    if (pl == nullptr) return set_error(ABT_ERR_ARG, "out of host memory");
+    pl->cfg = *cfg;
+    pl->nnz = (int)weights.size();
+    pl->max_len = max_len;
+    ABT_CUDA_OK(cudaMalloc(&pl->d_window, sizeof(float) * kNfft));
+    ABT_CUDA_OK(cudaMalloc(&pl->d_twiddle, sizeof(float2) * 1024));
+    ABT_CUDA_OK(cudaMalloc(&pl->d_mel_start, sizeof(int) * kMels));
+    ABT_CUDA_OK(cudaMalloc(&pl->d_mel_len, sizeof(int) * kMels));
+    ABT_CUDA_OK(cudaMalloc(&pl->d_mel_off, sizeof(int) * kMels));
+    ABT_CUDA_OK(cudaMalloc(&pl->d_mel_w, sizeof(float) * (weights.empty() ? 1 : weights.size())));
+    ABT_CUDA_OK(cudaMemcpy(pl->d_window, win.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
+    ABT_CUDA_OK(cudaMemcpy(pl->d_twiddle, tw.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice));
+    ABT_CUDA_OK(cudaMemcpy(pl->d_mel_start, start.data(), sizeof(int) * kMels, cudaMemcpyHostToDevice));
+    ABT_CUDA_OK(cudaMemcpy(pl->d_mel_len, len.data(), sizeof(int) * kMels, cudaMemcpyHostToDevice));
+    ABT_CUDA_OK(cudaMemcpy(pl->d_mel_off, off.data(), sizeof(int) * kMels, cudaMemcpyHostToDevice));
+    if (!weights.empty()) ABT_CUDA_OK(cudaMemcpy(pl->d_mel_w, weights.data(), sizeof(float) * weights.size(), cudaMemcpyHostToDevice));
+    *plan_out = pl;
+    return 0;
+}
+
+extern "C" int abt_logmel_plan_destroy(abt_logmel_plan* pl) {
+    if (pl == nullptr) return 0;
+    cudaFree(pl->d_window); cudaFree(pl->d_twiddle); cudaFree(pl->d_mel_start);
+    cudaFree(pl->d_mel_len); cudaFree(pl->d_mel_off); cudaFree(pl->d_mel_w);
+    std::free(pl);
+    return 0;
+}
+
+static int launch_logmel(const abt_logmel_plan* pl, const float* wav, int64_t row_stride, const int32_t* wav_offset, int n_clips, int n_samples,
+                         const int32_t* frame_start, int n_frames_out,
+                         float* out_base, const int32_t* out_slot, int64_t out_slot_stride, cudaStream_t stream) {
+    if (pl == nullptr || wav == nullptr || out_base == nullptr) return set_error(ABT_ERR_ARG, "null argument");
+    if (n_clips < 0 || n_frames_out < 0) return set_error(ABT_ERR_ARG, "negative size");
+    if (n_clips == 0 || n_frames_out == 0) return 0;
+    if (n_samples <= kNfft / 2) return set_error(ABT_ERR_ARG, "n_samples must exceed n_fft/2 = 512 for reflect padding (got %d)", n_samples);
+    if (n_clips > 65535) return set_error(ABT_ERR_ARG, "n_clips must be <= 65535 per call");
+    if (int rc = check_device_sm100()) return rc;
+    LogmelArgs a{};
+    a.wav = wav; a.row_stride = row_stride; a.wav_offset = wav_offset; a.n_samples = n_samples; a.hop = pl->cfg.hop_length;
+    a.n_frames_total = 1 + n_samples / pl->cfg.hop_length;
+    a.frame_start = frame_start; a.n_frames_out = n_frames_out;
+    a.out_base = out_base; a.out_slot = out_slot; a.out_slot_stride = out_slot_stride;
+    a.apply_norm = pl->cfg.apply_norm; a.norm_mean = pl->cfg.norm_mean;
+    a.inv_std = pl->cfg.apply_norm ? 1.0f / pl->cfg.norm_std : 1.0f;
+    a.pad_value = pl->cfg.apply_norm ? (0.0f - pl->cfg.norm_mean) / pl->cfg.norm_std : 0.0f;
+    a.window = pl->d_window; a.twiddle = pl->d_twiddle;
+    a.mel_start = pl->d_mel_start; a.mel_len = pl->d_mel_len; a.mel_off = pl->d_mel_off; a.mel_w = pl->d_mel_w; a.nnz = pl->nnz;
+    const int span = (kTileFrames - 1) * a.hop + kNfft;
+    const size_t smem = sizeof(float) * (((span + 31) & ~31) + kWarps * kScratchFloats + kMels * (kTileFrames + 1) + pl->nnz) + sizeof(int) * 3 * kMels;
+    if (smem > 227 * 1024) return set_error(ABT_ERR_ARG, "hop_length %d needs %zu bytes of shared memory (> 227 KiB)", a.hop, smem);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        ABT_CUDA_OK(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    dim3 grid((n_frames_out + kTileFrames - 1) / kTileFrames, n_clips);
+    logmel_kernel<<<grid, kWarps * 32, smem, stream>>>(a);
+    ABT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int abt_logmel_fwd(const abt_logmel_plan* plan, const float* wav, int n_clips, int n_samples, float* out, abt_stream_t stream) {
+    if (plan == nullptr) return set_error(ABT_ERR_ARG, "plan is null");
+    const int n_frames = 1 + n_samples / plan->cfg.hop_length;
+    return launch_logmel(plan, wav, n_samples, nullptr, n_clips, n_samples, nullptr, n_frames, out, nullptr, (int64_t)kMels * n_frames,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int abt_logmel_crop_fwd(const abt_logmel_plan* plan, const float* wav, int64_t wav_row_stride, const int32_t* wav_offset, int n_clips,
+                                   int n_samples, const int32_t* frame_start, int n_frames, float* out_base, const int32_t* out_slot,
+                                   int64_t out_slot_stride, abt_stream_t stream) {
+    if (plan == nullptr) return set_error(ABT_ERR_ARG, "plan is null");
+    if (out_slot_stride < (int64_t)kMels * n_frames) return set_error(ABT_ERR_ARG, "out_slot_stride smaller than one clip");
+    if (wav_row_stride < n_samples) return set_error(ABT_ERR_ARG, "wav_row_stride smaller than n_samples");
+    return launch_logmel(plan, wav, wav_row_stride, wav_offset, n_clips, n_samples, frame_start, n_frames, out_base, out_slot, out_slot_stride,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int abt_lms_crop_norm(const float* lms, int n_clips, int n_mels, int t_full, const int32_t* frame_start, int n_frames, int apply_norm,
+                                 float norm_mean, float norm_std, float* out_base, const int32_t* out_slot, int64_t out_slot_stride,
+                                 abt_stream_t stream) {
+    if (lms == nullptr || out_base == nullptr) return set_error(ABT_ERR_ARG, "null argument");
+    if (n_clips == 0) return 0;
+    if (n_clips < 0 || n_clips > 65535 || n_mels < 1 || t_full < 1 || n_frames < 1) return set_error(ABT_ERR_ARG, "bad shape");
+    if (apply_norm && !(norm_std > 0.f)) return set_error(ABT_ERR_ARG, "norm_std must be > 0");
+    if (int rc = check_device_sm100()) return rc;
+    dim3 grid((n_mels * n_frames + 255) / 256, n_clips);
+    lms_crop_norm_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(lms, n_mels, t_full, frame_start, n_frames, apply_norm, norm_mean,
+                                                                                    apply_norm ? 1.0f / norm_std : 1.0f, out_base, out_slot,
+                                                                                    out_slot_stride);
+    ABT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int abt_views_fwd(const abt_views_args* a, abt_stream_t stream) {
+    if (a == nullptr || a->x == nullptr || a->params == nullptr) return set_error(ABT_ERR_ARG, "null argument");
+    if (a->n_clips == 0 || a->n_views == 0) return 0;
+    if (a->n_clips < 0 || a->n_views < 0 || a->n_views > 65535) return set_error(ABT_ERR_ARG, "bad n_clips / n_views");
+    if (a->in_h < 1 || a->in_w < 1 || (a->in_h * a->in_w) % 4 != 0) return set_error(ABT_ERR_ARG, "in_h * in_w must be a positive multiple of 4");
+    if (a->canvas_h < a->in_h || a->canvas_w < a->in_w) return set_error(ABT_ERR_ARG, "canvas smaller than input");
+    if (a->out_h < 1 || a->out_w < 1 || a->out_h + a->out_w > 256) return set_error(ABT_ERR_ARG, "out_h + out_w must be in [2, 256]");
+    if ((a->x_slot_stride % 4) != 0 || (a->bank_slot_stride % 4) != 0) return set_error(ABT_ERR_ARG, "slot strides must be multiples of 4 floats");
+    if (int rc = check_device_sm100()) return rc;
+    const size_t smem = sizeof(float) * ((size_t)a->canvas_h * a->canvas_w + (size_t)(a->out_w + a->out_h) * 4) + sizeof(int) * (size_t)(a->out_w + a->out_h) * 4;
+    if (smem > 200 * 1024) return set_error(ABT_ERR_ARG, "canvas too large for shared memory");
+    static size_t smem_set = 48 * 1024;
+    if (smem > smem_set) {
+        ABT_CUDA_OK(cudaFuncSetAttribute(views_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    dim3 grid(a->n_clips, a->n_views);
+    views_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    ABT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int abt_bank_push(const float* x, int64_t x_stride, int n_clips, int clip_elems, float* bank, int64_t bank_slot_stride,
+                             const int32_t* slot, abt_stream_t stream) {
+    if (x == nullptr || bank == nullptr || slot == nullptr) return set_error(ABT_ERR_ARG, "null argument");
+    if (n_clips == 0) return 0;
+    if (n_clips < 0 || n_clips > 65535 || clip_elems < 4 || clip_elems % 4 != 0 || x_stride % 4 != 0 || bank_slot_stride % 4 != 0)
+        return set_error(ABT_ERR_ARG, "bad shape (clip_elems and strides must be multiples of 4)");
+    if (int rc = check_device_sm100()) return rc;
+    dim3 grid((clip_elems / 4 + 255) / 256, n_clips);
+    bank_push_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, x_stride, clip_elems, bank, bank_slot_stride, slot);
+    ABT_CUDA_OK(cudaGetLastError());
+    return 0;
+}

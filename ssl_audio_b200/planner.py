@@ -1,0 +1,119 @@
+"""Host planner wrapper: draws the reference's random parameters for a whole batch.
+
+The reference draws per sample, inside `Dataset.__getitem__`, from numpy's global legacy
+generator and CPython's `random` (augmentations.py:34-37,70,105,108; datasets.py:89,112,344).
+`ViewPlanner.plan` imports the state of those two global generators into the native planner
+(csrc/planner.cpp), lets it replay the exact draw order for `n_clips` samples, and writes the
+advanced states back, so `np.random.seed(s); random.seed(s)` means what it means for the
+reference run with `num_workers=0`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import random as _pyrandom
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+VIEW_DTYPE = np.dtype([
+    ("z_kind", np.int32), ("z_index", np.int32), ("w_x", np.float32), ("w_z", np.float32),
+    ("i", np.int32), ("j", np.int32), ("h", np.int32), ("w", np.int32),
+    ("head", np.float32), ("tail", np.float32), ("flags", np.int32), ("out_index", np.int32),
+])
+assert VIEW_DTYPE.itemsize == C.sizeof(_lib.ViewParams) == 48
+
+FLAG_MIXUP, FLAG_RRC, FLAG_RLF = 1, 2, 4
+
+
+def _numpy_global_state_address() -> int:
+    bitgen = np.random.mtrand._rand._bit_generator
+    if type(bitgen).__name__ != "MT19937":
+        raise RuntimeError("numpy's global RandomState is not MT19937-backed; cannot replay the reference's draws")
+    return int(bitgen.ctypes.state_address)
+
+
+@dataclass
+class BatchPlan:
+    starts: np.ndarray       # (B,) int32 time-crop start per clip, -1 if none was drawn
+    wav_starts: np.ndarray   # (B,) int32 wav-crop start per clip, -1 if none was drawn
+    params: np.ndarray       # (B, n_views) VIEW_DTYPE
+    slots: np.ndarray        # (B,) int32 bank ring slot of each clip
+
+
+class ViewPlanner:
+    def __init__(self, *, mixup: bool, rrc: bool, rlf: bool, mixup_ratio: float = 0.2, n_memory: int = 2048,
+                 ring_slots: Optional[int] = None, n_global: int = 2, in_hw: Tuple[int, int] = (64, 96),
+                 canvas_hw: Tuple[int, int] = (64, 144), freq_scale: Sequence[float] = (0.6, 1.5),
+                 time_scale: Sequence[float] = (0.6, 1.5), n_local: int = 0, local_hw: Tuple[int, int] = (16, 16),
+                 local_scale: Sequence[float] = (0.05, 0.6), fader_gain: float = 1.0):
+        lib = _lib.load()
+        cfg = _lib.PlanConfig()
+        cfg.mixup, cfg.rrc, cfg.rlf = int(bool(mixup)), int(bool(rrc)), int(bool(rlf))
+        cfg.mixup_ratio_d = float(mixup_ratio)
+        cfg.n_memory = int(n_memory)
+        cfg.ring_slots = int(ring_slots if ring_slots is not None else n_memory + 1024)
+        cfg.n_global = int(n_global)
+        cfg.in_h, cfg.in_w = int(in_hw[0]), int(in_hw[1])
+        cfg.canvas_h, cfg.canvas_w = int(canvas_hw[0]), int(canvas_hw[1])
+        cfg.freq_scale[0], cfg.freq_scale[1] = float(freq_scale[0]), float(freq_scale[1])
+        cfg.time_scale[0], cfg.time_scale[1] = float(time_scale[0]), float(time_scale[1])
+        cfg.n_local = int(n_local)
+        cfg.local_h, cfg.local_w = int(local_hw[0]), int(local_hw[1])
+        cfg.local_scale[0], cfg.local_scale[1] = float(local_scale[0]), float(local_scale[1])
+        cfg.fader_gain = float(fader_gain)
+        self.cfg = cfg
+        self.n_views = cfg.n_global + cfg.n_local
+        self.ring_slots = cfg.ring_slots
+        self.n_memory = cfg.n_memory
+        self._uses_numpy = bool(mixup or rrc or rlf or n_local)
+        self._uses_pyrandom = bool(rrc or n_local)
+        self._h = C.c_void_p()
+        _lib.check(lib.abt_planner_create(C.byref(cfg), C.byref(self._h)))
+        self._lib = lib
+        self._key = np.empty(624, dtype=np.uint32)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.abt_planner_destroy(h)
+            self._h = C.c_void_p()
+
+    # -- bank bookkeeping (mirrors len(MixupBYOLA.memory_bank)) -------------------------------
+    def bank_len(self) -> int:
+        return int(self._lib.abt_planner_bank_len(self._h))
+
+    def bank_reset(self) -> None:
+        self._lib.abt_planner_bank_reset(self._h)
+
+    # -- planning ------------------------------------------------------------------------------
+    def plan(self, n_clips: int, time_crop_range: int = 0, wav_crop_range: int = 0) -> BatchPlan:
+        lib, h = self._lib, self._h
+        use_np = self._uses_numpy or time_crop_range > 0
+        use_py = self._uses_pyrandom or wav_crop_range > 0
+        if use_np:
+            # numpy's global legacy generator, accessed in place: its bit generator exposes the address of
+            # `struct { uint32_t key[624]; int pos; }` (numpy/random/src/mt19937/mt19937.h)
+            np_addr = _numpy_global_state_address()
+            np_pos = C.c_int.from_address(np_addr + 624 * 4)
+            _lib.check(lib.abt_planner_set_numpy_state(h, np_addr, int(np_pos.value)))
+        if use_py:
+            pst = _pyrandom.getstate()
+            pkey = np.array(pst[1][:624], dtype=np.uint32)
+            _lib.check(lib.abt_planner_set_pyrandom_state(h, pkey.ctypes.data, int(pst[1][624])))
+        starts = np.empty(n_clips, dtype=np.int32)
+        wav_starts = np.empty(n_clips, dtype=np.int32)
+        slots = np.empty(n_clips, dtype=np.int32)
+        params = np.empty((n_clips, self.n_views), dtype=VIEW_DTYPE)
+        _lib.check(lib.abt_planner_plan_batch(h, n_clips, int(time_crop_range), int(wav_crop_range), starts.ctypes.data,
+                                              wav_starts.ctypes.data, params.ctypes.data, slots.ctypes.data))
+        pos = C.c_int()
+        if use_np:
+            _lib.check(lib.abt_planner_get_numpy_state(h, np_addr, C.byref(pos)))
+            np_pos.value = pos.value
+        if use_py:
+            _lib.check(lib.abt_planner_get_pyrandom_state(h, self._key.ctypes.data, C.byref(pos)))
+            _pyrandom.setstate((pst[0], tuple(self._key.tolist()) + (pos.value,), pst[2]))
+        return BatchPlan(starts, wav_starts, params, slots)

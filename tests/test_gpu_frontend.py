@@ -1,0 +1,199 @@
+"""GPU parity of the frontend and view kernels (through the C ABI) against the golden fixtures
+generated from the reference and against the numpy oracle.  Tolerance (BASELINE.json:north_star):
+log-mel within 1e-3 relative, taken as |d| <= 1e-3 * max(1, |ref|); crop and mixup indices bit-exact."""
+import os
+import random
+import types
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import abt_oracle as O  # noqa: E402
+
+TOL = 1e-3
+AS_STATS = (-0.8294, 4.6230)
+
+
+def _args(**kw):
+    base = dict(mixup=True, Gnoise=False, RRC=True, RLF=True, n_mels=64, crop_frames=96, virtual_crop_scale=[1.0, 1.5],
+                local_crops_number=0, local_crops_size=[16, 16], sample_rate=16000, n_fft=1024, win_length=1024,
+                hop_length=160, f_min=60, f_max=7800, unit_sec=0.95)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+def _relerr(a, b):
+    return float((np.abs(a - b) / np.maximum(1.0, np.abs(b))).max())
+
+
+def test_logmel_matches_torchaudio_golden(golden_dir):
+    import ssl_audio_b200 as S
+    g = np.load(os.path.join(golden_dir, "logmel.npz"))
+    mel = S.LogMelSpectrogram(16000, 1024, 1024, 160, 64, 60, 7800)
+    out = mel(torch.from_numpy(g["wav"]).cuda()).cpu().numpy()
+    assert out.shape == g["lms"].shape
+    assert _relerr(out, g["lms"]) < TOL, _relerr(out, g["lms"])
+    # mel POWER relative error where the signal is not at the eps floor
+    loud = g["lms"] > -10
+    assert np.abs(np.expm1(out[loud] - g["lms"][loud])).max() < TOL
+
+
+def test_logmel_long_clip_and_short_window(golden_dir):
+    import ssl_audio_b200 as S
+    g = np.load(os.path.join(golden_dir, "logmel.npz"))
+    wav = O.synth_wave(1, 160000, seed=int(g["wav10_seed"]))
+    mel = S.LogMelSpectrogram(16000, 1024, 1024, 160, 64, 60, 7800)
+    out = mel(torch.from_numpy(wav).cuda()).cpu().numpy()
+    assert tuple(out.shape) == tuple(g["lms10_shape"])
+    assert _relerr(out[0][:, g["lms10_frames"]], g["lms10_cols"]) < TOL
+    assert _relerr(out, O.log_mel(wav)) < TOL                     # every frame, against the oracle
+    mel400 = S.LogMelSpectrogram(16000, 1024, 400, 160, 64, 60, 7800)
+    out400 = mel400(torch.from_numpy(g["wav"][:1]).cuda()).cpu().numpy()
+    assert _relerr(out400, g["lms_win400"]) < TOL
+
+
+def test_logmel_ragged_batch_shapes_and_errors():
+    import ssl_audio_b200 as S
+    mel = S.LogMelSpectrogram(16000, 1024, 1024, 160, 64, 60, 7800, norm_stats=AS_STATS)
+    for L in (513, 1000, 15200, 16001):
+        wav = O.synth_wave(2, L, seed=L)
+        out = mel(torch.from_numpy(wav).cuda()).cpu().numpy()
+        ref = O.normalise(O.log_mel(wav), AS_STATS)
+        assert out.shape == ref.shape == (2, 64, 1 + L // 160)
+        assert _relerr(out, ref) < TOL, (L, _relerr(out, ref))
+    assert mel(torch.zeros(0, 2000).cuda()).shape == (0, 64, 13)
+    with pytest.raises(ValueError):
+        mel(torch.zeros(1, 512).cuda())                            # reflect pad needs L > n_fft/2, like torch.stft
+    with pytest.raises(RuntimeError):
+        mel(torch.zeros(1, 2000))                                  # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        S.LogMelSpectrogram(16000, 512, 512, 160, 64, 60, 7800)(torch.zeros(1, 2000).cuda())
+
+
+def test_pair_transform_sequence_matches_reference(golden_dir):
+    import ssl_audio_b200 as S
+    g = np.load(os.path.join(golden_dir, "views.npz"))
+    seed = int(g["seed"])
+    x = torch.from_numpy(g["x"]).cuda()
+    # (a) whole batch in one call
+    np.random.seed(seed); random.seed(seed)
+    tf = S.AudioPairTransform(_args())
+    v = tf(x)
+    assert len(v) == 2 and tuple(v[0].shape) == (6, 1, 64, 96)
+    got = torch.stack(v, 1).cpu().numpy()
+    assert np.abs(got - g["views"]).max() < TOL, np.abs(got - g["views"]).max()
+    assert tf.memory_bank_len == 12
+    # (b) sample by sample, like Dataset.__getitem__ does
+    np.random.seed(seed); random.seed(seed)
+    tf = S.AudioPairTransform(_args())
+    for b in range(6):
+        crops = tf(x[b])
+        assert tuple(crops[0].shape) == (1, 64, 96)
+        assert np.abs(torch.stack(crops).cpu().numpy() - g["views"][b]).max() < TOL
+    # the global generators advanced exactly as in the reference run
+    a, c = np.random.random(), random.random()
+    np.random.seed(seed); random.seed(seed)
+    st = O.MixupState()
+    for b in range(6):
+        O.audio_pair_transform(g["x"][b], O.PairTransformConfig(), st)
+    assert a == np.random.random() and c == random.random()
+
+
+def test_lms_path_time_crop(golden_dir):
+    import ssl_audio_b200 as S
+    g = np.load(os.path.join(golden_dir, "views.npz"))
+    np.random.seed(77); random.seed(77)
+    fe = S.BatchFrontend(_args(), norm_stats=AS_STATS, path="lms")
+    v = fe.forward_lms(torch.from_numpy(g["lms_full"]).cuda())
+    got = torch.stack(v, 1).cpu().numpy()
+    assert np.abs(got - g["lms_views"]).max() < TOL
+
+
+def test_multicrop_local_views(golden_dir):
+    import ssl_audio_b200 as S
+    g = np.load(os.path.join(golden_dir, "views.npz"))
+    np.random.seed(5); random.seed(5)
+    tf = S.AudioPairTransform(_args(mixup=False, local_crops_number=2))
+    crops = tf(torch.from_numpy(g["x"][0]).cuda())
+    assert [tuple(c.shape) for c in crops] == [(1, 64, 96)] * 2 + [(1, 16, 16)] * 2
+    assert np.abs(torch.stack(crops[:2]).cpu().numpy() - g["mc_global"]).max() < TOL
+    assert np.abs(torch.stack(crops[2:]).cpu().numpy() - g["mc_local"]).max() < TOL
+
+
+def test_standalone_modules_match_oracle(golden_dir):
+    import ssl_audio_b200 as S
+    g = np.load(os.path.join(golden_dir, "views.npz"))
+    x = g["x"][:3]
+    xd = torch.from_numpy(x).cuda()
+    np.random.seed(3); random.seed(3)
+    rrc = S.RandomResizeCrop()
+    got = rrc(xd).cpu().numpy()
+    np.random.seed(3); random.seed(3)
+    for b in range(3):
+        ref, _ = O.random_resize_crop(x[b])
+        assert np.abs(got[b] - ref).max() < TOL
+    np.random.seed(4)
+    rlf = S.RandomLinearFader()
+    got = rlf(xd[0]).cpu().numpy()
+    np.random.seed(4)
+    ref, _ = O.linear_fader(x[0])
+    assert np.abs(got - ref).max() < 1e-6
+    np.random.seed(8)
+    mix = S.MixupBYOLA()
+    outs = [mix(xd[b]).cpu().numpy() for b in range(3)]
+    np.random.seed(8)
+    st = O.MixupState()
+    for b in range(3):
+        ref, _ = O.mixup_byola(x[b], st)
+        assert np.abs(outs[b] - ref).max() < 1e-4
+    assert len(mix.memory_bank) == 3 and torch.equal(mix.memory_bank[0], xd[0])
+    lm = S.log_mixup_exp(xd[0], xd[1], 0.7).cpu().numpy()
+    assert np.abs(lm - O.log_mixup_exp(x[0], x[1], 0.7)).max() < 1e-4
+    # identity crop is an exact copy (reference property)
+    i, j, h, w = S.RandomResizeCrop.get_params((64, 144), (64, 96), (0.6, 1.5), (0.6, 1.5))
+    assert 1 <= h <= 64 and 1 <= w <= 144 and 0 <= i <= 64 - h and 0 <= j <= 144 - w
+
+
+def test_crop_first_equals_full_then_crop_and_wav_path():
+    import ssl_audio_b200 as S
+    wav = O.synth_wave(5, 48000, seed=11)
+    wd = torch.from_numpy(wav).cuda()
+    outs = {}
+    for mode in ("crop", "full"):
+        np.random.seed(21); random.seed(21)
+        fe = S.BatchFrontend(_args(), norm_stats=AS_STATS, path="lms", mode=mode)
+        outs[mode] = torch.stack(fe(wd), 1).cpu().numpy()
+    assert np.abs(outs["crop"] - outs["full"]).max() < 1e-4
+    # against the oracle's per-sample replay of AudioSet.__getitem__ on the full log-mel
+    np.random.seed(21); random.seed(21)
+    st = O.MixupState()
+    lms = O.log_mel(wav)
+    for b in range(5):
+        views, _, _ = O.frontend_clip_lms_path(lms[b], AS_STATS, O.PairTransformConfig(), st)
+        assert np.abs(outs["crop"][b] - np.stack(views)).max() < 2e-3
+    # wav path (datasets.py:98-122): short clip is centre padded, long clip is unit-cropped
+    for L in (9000, 20000):
+        w = O.synth_wave(3, L, seed=L)
+        np.random.seed(2); random.seed(2)
+        fe = S.BatchFrontend(_args(), norm_stats=AS_STATS, path="wav")
+        got = torch.stack(fe(torch.from_numpy(w).cuda()), 1).cpu().numpy()
+        np.random.seed(2); random.seed(2)
+        st = O.MixupState()
+        for b in range(3):
+            views, _, _ = O.frontend_clip_wav_path(w[b], O.MelConfig(), 0.95, AS_STATS, O.PairTransformConfig(), st)
+            assert np.abs(got[b] - np.stack(views)).max() < 2e-3, (L, b)
+
+
+def test_short_clip_is_padded_before_normalisation():
+    import ssl_audio_b200 as S
+    wav = O.synth_wave(2, 8000, seed=1)                     # 51 frames < 96
+    np.random.seed(0); random.seed(0)
+    fe = S.BatchFrontend(_args(mixup=False, RRC=False, RLF=False), norm_stats=AS_STATS, path="lms")
+    v = fe(torch.from_numpy(wav).cuda())
+    ref, _ = O.lms_trim_pad(O.log_mel(wav)[:, None], 96)
+    ref = O.normalise(ref, AS_STATS)
+    assert np.abs(v[0].cpu().numpy() - ref).max() < TOL
+    assert torch.equal(v[0], v[1])

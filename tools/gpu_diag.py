@@ -1,0 +1,65 @@
+"""First-light diagnostics on a real B200: runs the loss kernels on small problems and prints where
+(stats / C tile / H / gradient GEMMs / finalize) the numbers diverge from the float64 closed form."""
+import ctypes as C
+import sys
+import os
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import abt_oracle as O
+from ssl_audio_b200 import _lib
+from ssl_audio_b200.loss import _WS, bt_loss_fwd_bwd
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def run(n, d, lam=0.005):
+    z1, z2 = O.synth_embeddings(n, d, seed=n + d)
+    t1 = torch.from_numpy(z1).cuda().bfloat16()
+    t2 = torch.from_numpy(z2).cuda().bfloat16()
+    loss, dz1, dz2 = bt_loss_fwd_bwd(t1, t2, 1.0, lam, False)
+    torch.cuda.synchronize()
+    rl, r1, r2, c = O.bt_loss_forward_backward(z1, z2, 1.0, lam)
+    lib = _lib.load()
+    offs = (C.c_size_t * 8)()
+    lib.abt_debug_ws_offsets(n, d, 0, offs)
+    buf, ptr = _WS.get(t1.device, n, d, 0)
+    base = ptr - buf.data_ptr()
+    raw = buf.cpu().numpy()
+    stats = raw[base + offs[0]: base + offs[0] + 10 * d * 4].view(np.float32).reshape(10, d)
+    H = torch.from_numpy(raw[base + offs[1]: base + offs[1] + 2 * d * d].copy()).view(torch.bfloat16).float().numpy().reshape(d, d)
+    g1 = raw[base + offs[2]: base + offs[2] + 4 * n * d].view(np.float32).reshape(n, d)
+    g2 = raw[base + offs[3]: base + offs[3] + 4 * n * d].view(np.float32).reshape(n, d)
+    h1, mu1, _, rr1 = O.batchnorm_train(z1.astype(np.float64))
+    h2, mu2, _, rr2 = O.batchnorm_train(z2.astype(np.float64))
+    print(f"--- N={n} D={d}: loss {float(loss):.6f} ref {rl:.6f}  rel {abs(float(loss)-rl)/rl:.2e}")
+    print("    stats mu1", rel(stats[0], mu1), "r1", rel(stats[1], rr1), "mu2", rel(stats[2], mu2), "cdiag", rel(stats[4], np.diagonal(c)))
+    G = 2 * lam * c
+    np.fill_diagonal(G, 0.0)
+    Href = G * rr1[:, None] * rr2[None, :] / n
+    print("    H rel", rel(H, Href), " H^T rel (transposition bug?)", rel(H.T, Href), " |H|", np.abs(H).max(), np.abs(Href).max())
+    g1ref = Href @ z2.astype(np.float64).T     # (D, N)
+    g2ref = Href.T @ z1.astype(np.float64).T
+    print("    g1 rel", rel(g1, g1ref.T), " g2 rel", rel(g2, g2ref.T))
+    # GEMM-only check of the GRAD kernel with the H that was actually produced
+    print("    g1 vs own H", rel(g1, (H.astype(np.float64) @ z2.astype(np.float64).T).T), " g2 vs own H",
+          rel(g2, (H.astype(np.float64).T @ z1.astype(np.float64).T).T))
+    print("    dz1 rel", rel(dz1.float().cpu().numpy(), r1), " dz2 rel", rel(dz2.float().cpu().numpy(), r2))
+    if rel(H, Href) > 0.05:
+        e = np.abs(H - Href)
+        bad = np.argwhere(e > 0.05 * np.abs(Href).max())
+        print("    bad H entries:", len(bad), "first", bad[:6].tolist(), "rows", sorted(set(bad[:, 0] // 8))[:10], "cols", sorted(set(bad[:, 1] // 8))[:10])
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0))
+    for n, d in [(32, 64), (128, 256), (64, 512), (300, 512)]:
+        try:
+            run(n, d)
+        except Exception as e:  # keep going: later shapes may still tell us something
+            print("FAILED", n, d, repr(e))
+            break
