@@ -1,0 +1,354 @@
+"""Hot-path benchmark (BASELINE.json metric: two-view clips/sec for log-mel + augmentation + Barlow Twins
+loss fwd/bwd, with the fraction of the HBM / tensor-core roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" per GPU = one pass of the hot path over one batch of synthetic input:
+    frontend  B = 1024 clips of 10 s @16 kHz -> crop-first 64-mel log-spectrogram -> two augmented 96-frame views
+              (BASELINE config 2; the Mixup ring is warm)
+    objective Barlow Twins loss forward + backward on (B, D = 8192) bf16 projector outputs (the encoder between the
+              two is out of scope and stays PyTorch; embeddings are synthetic)
+Under torchrun (N > 1) every rank runs this step on its own shard of the batch (weak scaling).
+Prints ONE JSON line (see the contract in the task description).  `--impl reference` times the CPU port of the
+reference path (oracle/torch_port.py) on the host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "two_view_clips_per_sec"
+UNIT = "clips/s"
+AS_STATS = (-0.8294, 4.6230)
+
+
+def _args_ns(dim):
+    return types.SimpleNamespace(mixup=True, Gnoise=False, RRC=True, RLF=True, n_mels=64, crop_frames=96,
+                                 virtual_crop_scale=[1.0, 1.5], local_crops_number=0, local_crops_size=[16, 16],
+                                 sample_rate=16000, n_fft=1024, win_length=1024, hop_length=160, f_min=60, f_max=7800,
+                                 unit_sec=0.95, projector_out_dim=dim, HSIC=False, alpha=1.0, lmbda=0.005)
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]), tf_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    source="MEASURED_PEAKS.json")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for k, n in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm: the CPU port of the reference path on the host cores
+# ----------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import torch_port as P
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, D, L = args.batch, args.dim, int(args.clip_seconds * 16000)
+    workers = cores
+    sample_clips = max(workers, min(B, workers * args.ref_clips_per_worker))
+    n_steps = args.steps + args.warmup
+    vals = []
+    fe_rate = loss_s = None
+    for s in range(n_steps):
+        fe_rate = P.time_frontend(sample_clips, L, workers)                # clips/s on `workers` processes
+        loss_s = P.time_loss(min(B, args.ref_loss_rows), D)                # seconds for fwd+bwd on the row sample
+        loss_s_full = loss_s * (B / min(B, args.ref_loss_rows))            # the GEMMs are linear in the row count
+        step_s = B / fe_rate + loss_s_full
+        if s >= args.warmup:
+            vals.append(B / step_s)
+    value = sum(vals) / len(vals)
+    sample = (f"per step: frontend timed on {sample_clips} of {B} clips ({workers} single-threaded worker processes, the reference's "
+              f"DataLoader model), loss fwd+bwd timed on {min(B, args.ref_loss_rows)} of {B} rows at D={D} (fp32, {cores} threads) and scaled linearly")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * B / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "frontend_clips_per_s": fe_rate, "loss_fwd_bwd_s": loss_s},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _config(args):
+    return {"workload": f"hot-path step: frontend (BASELINE config 2: {args.batch} clips x {args.clip_seconds:g} s @16 kHz -> crop-first 64-mel log-mel -> "
+                        f"two 96-frame views) + Barlow Twins loss fwd/bwd (N={args.batch} rows/GPU, D={args.dim}, bf16 in / fp32 accumulate)",
+            "per_gpu_batch": args.batch, "clip_seconds": args.clip_seconds, "projector_out_dim": args.dim, "frontend_mode": "crop-first (mode C)",
+            "l2": "inputs larger than L2 (655 MB of waveforms, 128 MiB correlation matrix per step)", "parallelism": f"dp{args.gpus}"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes as C
+
+    import numpy as np
+    import random
+    import torch
+    import torch.distributed as dist
+
+    import ssl_audio_b200 as S
+    from ssl_audio_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU baseline")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    B, D, L = args.batch, args.dim, int(args.clip_seconds * 16000)
+    cfg = _args_ns(D)
+
+    # ---- synthetic inputs, generated on the host once and resident in HBM for `value`
+    g = torch.Generator(device=dev).manual_seed(rank)
+    t = torch.arange(L, device=dev, dtype=torch.float32) / 16000.0
+    wav = 0.1 * torch.randn(B, L, device=dev, generator=g)
+    for amp in (0.3, 0.1, 0.03):
+        f = 100.0 + 6900.0 * torch.rand(B, 1, device=dev, generator=g)
+        ph = 6.2831853 * torch.rand(B, 1, device=dev, generator=g)
+        wav += amp * torch.sin(6.2831853 * f * t[None, :] + ph)
+    wav.clamp_(-1.0, 1.0)
+    z1 = torch.randn(B, D, device=dev, generator=g)
+    z2 = (0.6 * z1 + 0.8 * torch.randn(B, D, device=dev, generator=g)).bfloat16()
+    z1 = z1.bfloat16()
+    np.random.seed(rank); random.seed(rank)
+
+    fe = S.BatchFrontend(cfg, norm_stats=AS_STATS, path="lms", mode="crop")
+    crit = S.BarlowTwinsLoss(cfg, ncrops=2).to(dev)
+
+    def step(wav_d, z1_d, z2_d):
+        views = fe(wav_d)
+        a = z1_d.detach().requires_grad_(True)
+        b = z2_d.detach().requires_grad_(True)
+        loss = crit(b, a, ngcrops_each=1)          # forward(student, teacher) as main.py:115 calls it
+        loss.backward()
+        return views, loss, a.grad, b.grad
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step(wav, z1, z2)
+    sync_all()
+
+    # ---- timed region: device-resident inputs
+    lib.abt_debug_launch_count(1)
+    _lib.check(lib.abt_debug_timing(1))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step(wav, z1, z2)
+    e1.record()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    launches = int(lib.abt_debug_launch_count(0))
+    corr_ms, grad_ms, ncalls = C.c_float(), C.c_float(), C.c_int()
+    _lib.check(lib.abt_debug_timing_read(C.byref(corr_ms), C.byref(grad_ms), C.byref(ncalls)))
+    _lib.check(lib.abt_debug_timing(0))
+    loss_val = float(out[1])
+
+    # frontend-only and loss-only device times (explain `value`; not the headline)
+    fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fe0.record()
+    for _ in range(args.steps):
+        fe(wav)
+    fe1.record()
+    torch.cuda.synchronize(dev)
+    fe_ms = fe0.elapsed_time(fe1) / args.steps
+
+    # ---- e2e: host buffers in pinned memory, H2D of the step's inputs and D2H of its result inside the timed region
+    wav_h = wav.cpu().pin_memory()
+    z1_h, z2_h = z1.cpu().pin_memory(), z2.cpu().pin_memory()
+    loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(dev)
+    bufs = [(torch.empty_like(wav), torch.empty_like(z1), torch.empty_like(z2)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(k):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[k])
+            bufs[k][0].copy_(wav_h, non_blocking=True)
+            bufs[k][1].copy_(z1_h, non_blocking=True)
+            bufs[k][2].copy_(z2_h, non_blocking=True)
+            ready[k].record(copy_stream)
+
+    def e2e_loop(n):
+        for k in range(2):
+            freed[k].record()
+        upload(0)
+        for s in range(n):
+            k = s & 1
+            if s + 1 < n:
+                upload(k ^ 1)                        # next step's H2D overlaps this step's kernels
+            torch.cuda.current_stream(dev).wait_event(ready[k])
+            _, loss, _, _ = step(*bufs[k])
+            loss_h.copy_(loss.detach(), non_blocking=True)
+            freed[k].record()
+        torch.cuda.synchronize(dev)
+
+    e2e_loop(2)
+    sync_all()
+    e2e_steps = max(2, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    e2e_loop(e2e_steps)
+    e2e_s = time.perf_counter() - t0
+    h2d = wav_h.numel() * 4 + z1_h.numel() * 2 + z2_h.numel() * 2
+    d2h = 4
+
+    # ---- reduce over ranks (max time)
+    tt = torch.tensor([ms, e2e_s, corr_ms.value, grad_ms.value, fe_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, e2e_s, corr, grad, fe_ms = (float(v) for v in tt.cpu())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = _peaks()
+    ms_per_step = ms / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+    e2e_value = B * world * e2e_steps / e2e_s
+    flops = 6.0 * B * D * D                                   # algorithmic FLOPs of one loss term, per GPU
+    tc_ms = corr + grad
+    achieved = flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    fe_bytes = B * (64896 + 49152 + 49152 + 24576)            # mode C algorithmic bytes per clip
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": _config(args),
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "note": "pinned host buffers; next step's H2D overlaps the current step's kernels on a copy stream"},
+        "roofline": {"bound": "tensor", "kernel": "bt_umma_kernel (CORR + GRAD launches)", "achieved": achieved, "peak": peaks["tf_sustained"],
+                     "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"], "traffic": None,
+                     "algorithmic_flops_per_step": flops, "corr_ms": corr, "grad_ms": grad, "frac_of_burst_peak": achieved / peaks["tf_burst"],
+                     "peak_source": peaks["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)"},
+        "frontend": {"ms_per_step": fe_ms, "clips_per_s": B / (fe_ms * 1e-3), "algorithmic_bytes_per_step": fe_bytes,
+                     "achieved_gbs": fe_bytes / (fe_ms * 1e-3) / 1e9, "hbm_frac": fe_bytes / (fe_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "note": "log-mel + views launches; FP32-pipe bound (1024-pt FFT per frame), see DESIGN.md"},
+        "loss_value": loss_val,
+    }
+    if args.cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args):
+    import torch
+    from oracle import torch_port as P
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, D, L = args.batch, args.dim, int(args.clip_seconds * 16000)
+    sample_clips = max(cores, min(B, cores * args.ref_clips_per_worker))
+    fe_rate = P.time_frontend(sample_clips, L, cores)
+    rows = min(B, args.ref_loss_rows)
+    loss_s = P.time_loss(rows, D)
+    step_s = B / fe_rate + loss_s * (B / rows)
+    return {"value": B / step_s, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"frontend: {sample_clips} of {B} clips over {cores} single-threaded worker processes; loss fwd+bwd: {rows} of {B} rows at D={D}, "
+                      f"fp32, {cores} threads, scaled linearly in rows",
+            "frontend_clips_per_s": fe_rate, "loss_fwd_bwd_s": loss_s}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="clips (= embedding rows) per GPU per step")
+    ap.add_argument("--dim", type=int, default=8192, help="projector_out_dim")
+    ap.add_argument("--clip-seconds", type=float, default=10.0)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--ref-clips-per-worker", type=int, default=8)
+    ap.add_argument("--ref-loss-rows", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3                         # timing rule: at least 3 warm-up steps (also warms the Mixup ring)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

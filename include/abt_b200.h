@@ -198,6 +198,11 @@ int abt_bt_loss_fwd_bwd(const abt_bt_args* args, abt_stream_t stream);
  *  Debug hooks (not part of the drop-in surface; used by tools/gpu_diag.py)
  * ===================================================================================== */
 int abt_debug_set(int key, int value);
+/* number of kernels the library has launched (optionally resetting the counter) */
+long long abt_debug_launch_count(int reset);
+/* device timing of the two tensor-core launches of abt_bt_loss_fwd_bwd (CUDA events on the launching stream) */
+int abt_debug_timing(int enable);
+int abt_debug_timing_read(float* corr_ms, float* grad_ms, int* n_calls);
 int abt_debug_ws_offsets(int n_rows, int n_dims, int dtype, size_t* out8);
 
 #ifdef __cplusplus

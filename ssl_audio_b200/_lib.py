@@ -90,6 +90,9 @@ SIGNATURES = {
     "abt_bt_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "abt_bt_loss_fwd_bwd": (C.c_int, [C.POINTER(BtArgs), C.c_void_p]),
     "abt_debug_set": (C.c_int, [C.c_int, C.c_int]),
+    "abt_debug_launch_count": (C.c_longlong, [C.c_int]),
+    "abt_debug_timing": (C.c_int, [C.c_int]),
+    "abt_debug_timing_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "abt_debug_ws_offsets": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
 }
 

@@ -1,6 +1,7 @@
 // Version, error reporting and device check of the C ABI.
 #include "abt_internal.h"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -30,7 +31,14 @@ int check_device_sm100() {
     return 0;
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
 }  // namespace abt
+
+extern "C" long long abt_debug_launch_count(int reset) {
+    return reset ? abt::g_launches.exchange(0) : abt::g_launches.load();
+}
 
 extern "C" int abt_version(void) { return ABT_VERSION; }
 extern "C" const char* abt_last_error(void) { return abt::g_err; }

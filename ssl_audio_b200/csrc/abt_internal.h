@@ -9,4 +9,6 @@ namespace abt {
 int set_error(int code, const char* fmt, ...);
 // 0 when the current device is compute capability 10.x, else ABT_ERR_DEVICE / ABT_ERR_CUDA
 int check_device_sm100();
+// every kernel launch of the library is counted (bench.py reports it as gpu_launches)
+void count_launch(int n = 1);
 }  // namespace abt

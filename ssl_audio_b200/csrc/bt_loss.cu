@@ -13,10 +13,11 @@
 //   2. bt_umma_kernel CORR S = z1^T z2 on the tensor cores (tcgen05, RAW bf16 operands straight
 //                          from the row-major embeddings as MN-major TMA tiles, fp32 TMEM
 //                          accumulator); epilogue applies batch-norm as a rank-1 correction,
-//                          reduces the off-diagonal loss and emits
-//                          H_ij = G_ij r1_i r2_j / N in bf16 (diagonal excluded).
-//   3. bt_umma_kernel GRAD g1^T = H z2 (K-major A) and g2^T = H^T z1 (MN-major A over the
-//                          same H), fp32 out.  6 N D^2 executed FLOP = the algorithmic count.
+//                          reduces the off-diagonal loss in fp32 and emits C (|C_ij| <= 1) in fp16
+//                          with the diagonal zeroed.
+//   3. bt_umma_kernel GRAD g1^T = C zh2^T (K-major A) and g2^T = C^T zh1^T (MN-major A over the
+//                          same C) with fp16 standardised embeddings, fp32 out.
+//                          6 N D^2 executed FLOP = the algorithmic count.
 //   4. bt_finalize_kernel  adds the fp32 diagonal term, batch-norm backward, output cast, loss.
 #include "abt_internal.h"
 #include "sm100_ptx.cuh"
@@ -31,11 +32,8 @@ namespace abt {
 // ------------------------------------------------------------------------------------------
 enum StatSlot {
     S_MU1 = 0, S_R1, S_MU2, S_R2, S_CDIAG,
-    S_NMU1,   // -N * mu1            (CORR row constant)
-    S_AROW,   // 2*lambda*r1^2/N^2   (CORR row scale of H)
-    S_ROWC,   // r1^2/N^2            (CORR row scale of sum c^2)
-    S_RHO1,   // r1/N                (CORR row scale of sum c, HSIC only)
-    S_BCOL,   // r2^2                (CORR column scale)
+    S_NMU1,   // -N * mu1   (CORR row constant of the rank-1 batch-norm correction)
+    S_RHO1,   // r1 / N     (CORR row scale)
     S_COUNT
 };
 
@@ -67,12 +65,14 @@ constexpr int kRowGroups = 8;       // 256 threads
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) bt_stats_kernel(const T* __restrict__ z1, const T* __restrict__ z2, int N, int D, float eps,
-                                                       float lambda, float momentum, float* __restrict__ stats,
+                                                       float momentum, float* __restrict__ stats,
                                                        __nv_bfloat16* __restrict__ zb1, __nv_bfloat16* __restrict__ zb2,
+                                                       __half* __restrict__ zh1, __half* __restrict__ zh2,
                                                        float* __restrict__ running_mean, float* __restrict__ running_var,
                                                        double* __restrict__ loss_acc, unsigned int* __restrict__ counters) {
     __shared__ float red[kRowGroups][5][kColsPerBlock];
     __shared__ float shift[2][kColsPerBlock];
+    __shared__ float colstat[4][kColsPerBlock];   // mu1, r1, mu2, r2 of this block's columns
     const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const int col = blockIdx.x * kColsPerBlock + lane * 2;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -137,11 +137,8 @@ __global__ void __launch_bounds__(256) bt_stats_kernel(const T* __restrict__ z1,
             stats[S_MU2 * D + gc] = mu2; stats[S_R2 * D + gc] = r2n;
             stats[S_CDIAG * D + gc] = cov * r1n * r2n;
             stats[S_NMU1 * D + gc] = -(float)N * mu1;
-            const float rowc = r1n * r1n * invN * invN;
-            stats[S_ROWC * D + gc] = rowc;
-            stats[S_AROW * D + gc] = 2.0f * lambda * rowc;
             stats[S_RHO1 * D + gc] = r1n * invN;
-            stats[S_BCOL * D + gc] = r2n * r2n;
+            colstat[0][c] = mu1; colstat[1][c] = r1n; colstat[2][c] = mu2; colstat[3][c] = r2n;
             if (running_mean != nullptr) {
                 // BatchNorm1d training-mode side effect, view 1 then view 2 (utils/loss.py:17)
                 const float unb = (N > 1) ? (float)N / (float)(N - 1) : 1.0f;
@@ -150,6 +147,19 @@ __global__ void __launch_bounds__(256) bt_stats_kernel(const T* __restrict__ z1,
                 rm = (1.f - momentum) * rm + momentum * mu2; rv = (1.f - momentum) * rv + momentum * var2 * unb;
                 running_mean[gc] = rm; running_var[gc] = rv;
             }
+        }
+    }
+    // second pass: standardised embeddings in fp16 (operand B of the gradient GEMMs; |zh| <= sqrt(N))
+    __syncthreads();
+    if (ok && zh1 != nullptr) {
+        const float m1[2] = {colstat[0][lane * 2], colstat[0][lane * 2 + 1]}, q1r[2] = {colstat[1][lane * 2], colstat[1][lane * 2 + 1]};
+        const float m2[2] = {colstat[2][lane * 2], colstat[2][lane * 2 + 1]}, q2r[2] = {colstat[3][lane * 2], colstat[3][lane * 2 + 1]};
+#pragma unroll 4
+        for (int n = rg; n < N; n += kRowGroups) {
+            const size_t o = (size_t)n * D + col;
+            const float2 a2 = Ld2<T>::ld(z1 + o), b2 = Ld2<T>::ld(z2 + o);
+            Ld2<__half>::st(zh1 + o, (bf16_round(a2.x) - m1[0]) * q1r[0], (bf16_round(a2.y) - m1[1]) * q1r[1]);
+            Ld2<__half>::st(zh2 + o, (bf16_round(b2.x) - m2[0]) * q2r[0], (bf16_round(b2.y) - m2[1]) * q2r[1]);
         }
     }
 }
@@ -203,7 +213,7 @@ struct UmmaParams {
     int hsic;
     int write_h;
     const float* stats;
-    __nv_bfloat16* H;
+    __half* Cmat;      // D x D fp16, diagonal zeroed
     double* loss_acc;
     float* g1;
     float* g2;
@@ -293,7 +303,7 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             decode_work(p, w, pass, tm, tn, kb0, kb1);
             const bool a_mn = (p.mode == 0) || (pass == 1);
             const bool b_mn = (p.mode == 0);
-            const uint32_t idesc = make_idesc_bf16(BM, p.bn, a_mn ? 1 : 0, b_mn ? 1 : 0);
+            const uint32_t idesc = make_idesc_f16(BM, p.bn, a_mn ? 1 : 0, b_mn ? 1 : 0, p.mode == 0 ? 1 : 0);   // CORR: bf16, GRAD: fp16
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * kAccCols;
@@ -331,15 +341,12 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int row = tm * BM + q * 32 + lane;     // dimension index owned by this thread
             const bool row_ok = row < D;
             if (p.mode == 0) {
-                // ---- CORR: v = S - N mu1_i mu2_j;  c = v r1_i r2_j / N;  H = 2 lambda c r1_i r2_j / N
+                // ---- CORR: v = S - N mu1_i mu2_j;  c = v (r1_i / N) r2_j   (batch-norm as a rank-1 correction)
                 const float* st = p.stats;
                 const float nmu = row_ok ? st[S_NMU1 * D + row] : 0.f;
-                const float arow = row_ok ? st[S_AROW * D + row] : 0.f;
-                const float rowc = row_ok ? st[S_ROWC * D + row] : 0.f;
                 const float rho = row_ok ? st[S_RHO1 * D + row] : 0.f;
                 const float* mu2 = st + S_MU2 * D;
                 const float* r2 = st + S_R2 * D;
-                const float* bcol = st + S_BCOL * D;
                 float l2 = 0.f, l1 = 0.f;
                 const int nchunks = p.bn / 32;
                 for (int ch = hf; ch < nchunks; ch += 2) {
@@ -352,30 +359,29 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
                         for (int t4 = 0; t4 < 8; ++t4) {
                             const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu2 + j0) + t4);
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bcol + j0) + t4);
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(r2 + j0) + t4);
                             const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
-                            float hh[4];
+                            float cc[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 const int t = t4 * 4 + u;
-                                float v = fmaf(nmu, mm[u], __uint_as_float(r[t]));
-                                v = (j0 + t == row) ? 0.f : v;      // diagonal handled in fp32 by the finalize kernel
-                                const float e = v * bb[u];
-                                l2 = fmaf(e, v, l2);
-                                hh[u] = e * arow;
-                                if (p.hsic) l1 = fmaf(v, __ldg(r2 + j0 + t), l1);
+                                const float v = fmaf(nmu, mm[u], __uint_as_float(r[t]));
+                                float c = (v * rho) * bb[u];
+                                c = (j0 + t == row) ? 0.f : c;      // diagonal handled in fp32 by the finalize kernel
+                                l2 = fmaf(c, c, l2);
+                                l1 += c;
+                                cc[u] = c;
                             }
-                            packed[t4 * 2] = pack_bf16x2(hh[0], hh[1]);
-                            packed[t4 * 2 + 1] = pack_bf16x2(hh[2], hh[3]);
+                            packed[t4 * 2] = pack_f16x2(cc[0], cc[1]);
+                            packed[t4 * 2 + 1] = pack_f16x2(cc[2], cc[3]);
                         }
                         if (p.write_h) {
-                            uint4* dst = reinterpret_cast<uint4*>(p.H + (size_t)row * D + j0);
+                            uint4* dst = reinterpret_cast<uint4*>(p.Cmat + (size_t)row * D + j0);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) dst[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
                         }
                     }
                 }
-                l2 *= rowc; l1 *= rho;
                 l2 = warp_sum(l2);
                 if (p.hsic) l1 = warp_sum(l1);
                 if (lane == 0) {
@@ -440,11 +446,12 @@ __global__ void __launch_bounds__(256) bt_finalize_kernel(const T* __restrict__ 
         mu2[c] = stats[S_MU2 * D + gc]; r2[c] = stats[S_R2 * D + gc];
         gd[c] = 2.0f * alpha * (stats[S_CDIAG * D + gc] - 1.0f) * invN;   // G_ii / N
     }
-    const float hs = hsic ? 2.0f * lambda * invN : 0.f;
+    const float hs = 2.0f * lambda * invN;
 
-    // gf1[n,i] = g1raw/r1_i + (G_ii/N) zh2[n,i] (+ HSIC: (2 lambda/N)(R2[n] - zh2[n,i]))
+    // d loss / d zh1[n,i] = (2 lambda/N) sum_{j != i} C_ij zh2[n,j]  +  (G_ii/N) zh2[n,i]
+    //                       (+ HSIC: (2 lambda/N)(R2[n] - zh2[n,i]), the "+1" of every off-diagonal G_ij)
     auto side_grad = [&](int c, float zh_other, float graw, float r_own, float rs_other) -> float {
-        float g = graw / r_own + gd[c] * zh_other;
+        float g = hs * graw + gd[c] * zh_other;
         if (hsic) g += hs * (rs_other - zh_other);
         return g;
     };
@@ -555,15 +562,16 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// bf16 row-major matrix (rows x cols), box = (box_cols x box_rows) with 128-byte swizzle
-static int make_map_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
+// 16-bit row-major matrix (rows x cols), box = (box_cols x box_rows) with 128-byte swizzle
+static int make_map_16(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols,
+                       uint32_t box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) return set_error(ABT_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {cols * 2};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+    CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(ABT_ERR_CUDA, "cuTensorMapEncodeTiled failed (code %d)", (int)r);
@@ -572,8 +580,19 @@ static int make_map_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Optional per-call device timing of the two tensor-core launches (bench.py roofline): events are recorded on
+// the launching stream around CORR and GRAD of every abt_bt_loss_fwd_bwd call while enabled.
+constexpr int kTimingRing = 512;
+struct TimingState {
+    bool enabled = false;
+    int count = 0;
+    cudaEvent_t ev[kTimingRing][3];
+    bool created = false;
+};
+static TimingState g_timing;
+
 struct WsLayout {
-    size_t stats, H, g1, g2, zb1, zb2, rs1, rs2, misc, total;
+    size_t stats, H, g1, g2, zb1, zb2, zh1, zh2, rs1, rs2, misc, total;
 };
 
 static WsLayout ws_layout(int N, int D, int dtype) {
@@ -587,6 +606,8 @@ static WsLayout ws_layout(int N, int D, int dtype) {
     L.g2 = off; off = align_up(off + sizeof(float) * (size_t)N * D, 256);
     L.zb1 = off; if (dtype != ABT_DTYPE_BF16) off = align_up(off + 2 * (size_t)N * D, 256);
     L.zb2 = off; if (dtype != ABT_DTYPE_BF16) off = align_up(off + 2 * (size_t)N * D, 256);
+    L.zh1 = off; off = align_up(off + 2 * (size_t)N * D, 256);
+    L.zh2 = off; off = align_up(off + 2 * (size_t)N * D, 256);
     L.H = off; off = align_up(off + 2 * (size_t)D * D, 256);
     L.total = off;
     return L;
@@ -614,7 +635,9 @@ static int launch_all(const abt_bt_args* a, const WsLayout& L, cudaStream_t stre
     float* g2 = reinterpret_cast<float*>(ws + L.g2);
     float* rs1 = reinterpret_cast<float*>(ws + L.rs1);
     float* rs2 = reinterpret_cast<float*>(ws + L.rs2);
-    __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(ws + L.H);
+    __half* Cm = reinterpret_cast<__half*>(ws + L.H);
+    __half* zh1 = reinterpret_cast<__half*>(ws + L.zh1);
+    __half* zh2 = reinterpret_cast<__half*>(ws + L.zh2);
     const bool is_bf16 = (a->dtype == ABT_DTYPE_BF16);
     __nv_bfloat16* zb1 = is_bf16 ? nullptr : reinterpret_cast<__nv_bfloat16*>(ws + L.zb1);
     __nv_bfloat16* zb2 = is_bf16 ? nullptr : reinterpret_cast<__nv_bfloat16*>(ws + L.zb2);
@@ -623,8 +646,9 @@ static int launch_all(const abt_bt_args* a, const WsLayout& L, cudaStream_t stre
     const int need = a->need_grad_mask & 3;
     const int col_blocks = (D + kColsPerBlock - 1) / kColsPerBlock;
 
-    bt_stats_kernel<T><<<col_blocks, 256, 0, stream>>>(static_cast<const T*>(a->z1), static_cast<const T*>(a->z2), N, D, a->eps, a->lambda,
-                                                        a->momentum, stats, zb1, zb2, a->running_mean, a->running_var, loss_acc, counters);
+    bt_stats_kernel<T><<<col_blocks, 256, 0, stream>>>(static_cast<const T*>(a->z1), static_cast<const T*>(a->z2), N, D, a->eps,
+                                                        a->momentum, stats, zb1, zb2, need != 0 ? zh1 : nullptr, need != 0 ? zh2 : nullptr,
+                                                        a->running_mean, a->running_var, loss_acc, counters);
     if (a->hsic) {
         bt_rowsum_kernel<<<N, 256, 0, stream>>>(zq1, N, D, stats + S_MU1 * D, stats + S_R1 * D, rs1);
         bt_rowsum_kernel<<<N, 256, 0, stream>>>(zq2, N, D, stats + S_MU2 * D, stats + S_R2 * D, rs2);
@@ -637,11 +661,15 @@ static int launch_all(const abt_bt_args* a, const WsLayout& L, cudaStream_t stre
         attr_set = true;
     }
 
+    const bool timed = g_timing.enabled && g_timing.count < kTimingRing;
+    cudaEvent_t* tev = timed ? g_timing.ev[g_timing.count] : nullptr;
+    count_launch(1 + (a->hsic ? 2 : 0));
     // ---- CORR
+    if (timed) cudaEventRecord(tev[0], stream);
     {
         CUtensorMap mA, mB;
-        if (int rc = make_map_bf16(&mA, zq1, N, D, 64, 64)) return rc;
-        if (int rc = make_map_bf16(&mB, zq2, N, D, 64, 64)) return rc;
+        if (int rc = make_map_16(&mA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, zq1, N, D, 64, 64)) return rc;
+        if (int rc = make_map_16(&mB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, zq2, N, D, 64, 64)) return rc;
         UmmaParams p{};
         p.dc = g_desc;
         p.mode = 0; p.D = D; p.N = N;
@@ -650,19 +678,21 @@ static int launch_all(const abt_bt_args* a, const WsLayout& L, cudaStream_t stre
         p.kblocks = (N + BK - 1) / BK;
         p.pass_first = 0; p.pass_count = 1;
         p.hsic = a->hsic; p.write_h = need != 0;
-        p.stats = stats; p.H = H; p.loss_acc = loss_acc; p.g1 = g1; p.g2 = g2;
+        p.stats = stats; p.Cmat = Cm; p.loss_acc = loss_acc; p.g1 = g1; p.g2 = g2;
         const int total = p.tiles_m * p.tiles_n;
         const int grid = total < num_sms() ? total : num_sms();
         bt_umma_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(mA, mB, mA, mB, p);
+        count_launch();
     }
+    if (timed) cudaEventRecord(tev[1], stream);
     // ---- GRAD
     if (need != 0) {
         int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
         CUtensorMap mHk, mHmn, mZ2, mZ1;
-        if (int rc = make_map_bf16(&mHk, H, D, D, 64, 128)) return rc;
-        if (int rc = make_map_bf16(&mHmn, H, D, D, 64, 64)) return rc;
-        if (int rc = make_map_bf16(&mZ2, zq2, N, D, 64, bn)) return rc;
-        if (int rc = make_map_bf16(&mZ1, zq1, N, D, 64, bn)) return rc;
+        if (int rc = make_map_16(&mHk, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Cm, D, D, 64, 128)) return rc;
+        if (int rc = make_map_16(&mHmn, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Cm, D, D, 64, 64)) return rc;
+        if (int rc = make_map_16(&mZ2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh2, N, D, 64, bn)) return rc;
+        if (int rc = make_map_16(&mZ1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh1, N, D, 64, bn)) return rc;
         UmmaParams p{};
         p.dc = g_desc;
         p.mode = 1; p.D = D; p.N = N; p.bn = bn;
@@ -680,7 +710,7 @@ static int launch_all(const abt_bt_args* a, const WsLayout& L, cudaStream_t stre
         }
         p.splits = splits;
         p.hsic = a->hsic; p.write_h = 0;
-        p.stats = stats; p.H = H; p.loss_acc = loss_acc; p.g1 = g1; p.g2 = g2;
+        p.stats = stats; p.Cmat = Cm; p.loss_acc = loss_acc; p.g1 = g1; p.g2 = g2;
         if (splits > 1) {
             if (need & 1) cudaMemsetAsync(g1, 0, sizeof(float) * (size_t)N * D, stream);
             if (need & 2) cudaMemsetAsync(g2, 0, sizeof(float) * (size_t)N * D, stream);
@@ -688,10 +718,13 @@ static int launch_all(const abt_bt_args* a, const WsLayout& L, cudaStream_t stre
         const int total = tiles * splits;
         const int grid = total < num_sms() ? total : num_sms();
         bt_umma_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(mHk, mZ2, mHmn, mZ1, p);
+        count_launch();
     }
+    if (timed) { cudaEventRecord(tev[2], stream); ++g_timing.count; }
     bt_finalize_kernel<T><<<col_blocks, 256, 0, stream>>>(static_cast<const T*>(a->z1), static_cast<const T*>(a->z2), N, D, a->alpha, a->lambda,
                                                            a->hsic, a->grad_scale, need, stats, g1, g2, rs1, rs2, static_cast<T*>(a->dz1),
                                                            static_cast<T*>(a->dz2), loss_acc, counters, a->loss_out);
+    count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "bt loss launch: %s", cudaGetErrorString(e));
     return 0;
@@ -700,6 +733,35 @@ static int launch_all(const abt_bt_args* a, const WsLayout& L, cudaStream_t stre
 }  // namespace abt
 
 using namespace abt;
+
+extern "C" int abt_debug_timing(int enable) {
+    if (enable && !g_timing.created) {
+        for (int i = 0; i < kTimingRing; ++i)
+            for (int k = 0; k < 3; ++k)
+                if (cudaEventCreate(&g_timing.ev[i][k]) != cudaSuccess) return set_error(ABT_ERR_CUDA, "cudaEventCreate failed");
+        g_timing.created = true;
+    }
+    g_timing.enabled = enable != 0;
+    g_timing.count = 0;
+    return 0;
+}
+
+// Average milliseconds of the CORR and GRAD launches recorded since abt_debug_timing(1); synchronises on the events.
+extern "C" int abt_debug_timing_read(float* corr_ms, float* grad_ms, int* n_calls) {
+    double c = 0, g = 0;
+    const int n = g_timing.count;
+    for (int i = 0; i < n; ++i) {
+        float a = 0, b = 0;
+        if (cudaEventSynchronize(g_timing.ev[i][2]) != cudaSuccess) return set_error(ABT_ERR_CUDA, "cudaEventSynchronize failed");
+        cudaEventElapsedTime(&a, g_timing.ev[i][0], g_timing.ev[i][1]);
+        cudaEventElapsedTime(&b, g_timing.ev[i][1], g_timing.ev[i][2]);
+        c += a; g += b;
+    }
+    if (corr_ms) *corr_ms = n ? (float)(c / n) : 0.f;
+    if (grad_ms) *grad_ms = n ? (float)(g / n) : 0.f;
+    if (n_calls) *n_calls = n;
+    return 0;
+}
 
 extern "C" int abt_debug_set(int key, int value) {
     int* f[6] = {&g_desc.mn_lbo, &g_desc.mn_sbo, &g_desc.mn_kstep, &g_desc.k_lbo, &g_desc.k_sbo, &g_desc.k_kstep};

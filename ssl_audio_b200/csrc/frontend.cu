@@ -436,9 +436,9 @@ extern "C" int abt_logmel_plan_destroy(abt_logmel_plan* pl) {
 static int launch_logmel(const abt_logmel_plan* pl, const float* wav, int64_t row_stride, const int32_t* wav_offset, int n_clips, int n_samples,
                          const int32_t* frame_start, int n_frames_out,
                          float* out_base, const int32_t* out_slot, int64_t out_slot_stride, cudaStream_t stream) {
-    if (pl == nullptr || wav == nullptr || out_base == nullptr) return set_error(ABT_ERR_ARG, "null argument");
     if (n_clips < 0 || n_frames_out < 0) return set_error(ABT_ERR_ARG, "negative size");
-    if (n_clips == 0 || n_frames_out == 0) return 0;
+    if (n_clips == 0 || n_frames_out == 0) return 0;     // empty batch: nothing to do (pointers may be null)
+    if (pl == nullptr || wav == nullptr || out_base == nullptr) return set_error(ABT_ERR_ARG, "null argument");
     if (n_samples <= kNfft / 2) return set_error(ABT_ERR_ARG, "n_samples must exceed n_fft/2 = 512 for reflect padding (got %d)", n_samples);
     if (n_clips > 65535) return set_error(ABT_ERR_ARG, "n_clips must be <= 65535 per call");
     if (int rc = check_device_sm100()) return rc;
@@ -462,6 +462,7 @@ static int launch_logmel(const abt_logmel_plan* pl, const float* wav, int64_t ro
     }
     dim3 grid((n_frames_out + kTileFrames - 1) / kTileFrames, n_clips);
     logmel_kernel<<<grid, kWarps * 32, smem, stream>>>(a);
+    count_launch();
     ABT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -486,8 +487,8 @@ extern "C" int abt_logmel_crop_fwd(const abt_logmel_plan* plan, const float* wav
 extern "C" int abt_lms_crop_norm(const float* lms, int n_clips, int n_mels, int t_full, const int32_t* frame_start, int n_frames, int apply_norm,
                                  float norm_mean, float norm_std, float* out_base, const int32_t* out_slot, int64_t out_slot_stride,
                                  abt_stream_t stream) {
-    if (lms == nullptr || out_base == nullptr) return set_error(ABT_ERR_ARG, "null argument");
     if (n_clips == 0) return 0;
+    if (lms == nullptr || out_base == nullptr) return set_error(ABT_ERR_ARG, "null argument");
     if (n_clips < 0 || n_clips > 65535 || n_mels < 1 || t_full < 1 || n_frames < 1) return set_error(ABT_ERR_ARG, "bad shape");
     if (apply_norm && !(norm_std > 0.f)) return set_error(ABT_ERR_ARG, "norm_std must be > 0");
     if (int rc = check_device_sm100()) return rc;
@@ -495,13 +496,15 @@ extern "C" int abt_lms_crop_norm(const float* lms, int n_clips, int n_mels, int 
     lms_crop_norm_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(lms, n_mels, t_full, frame_start, n_frames, apply_norm, norm_mean,
                                                                                     apply_norm ? 1.0f / norm_std : 1.0f, out_base, out_slot,
                                                                                     out_slot_stride);
+    count_launch();
     ABT_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 extern "C" int abt_views_fwd(const abt_views_args* a, abt_stream_t stream) {
-    if (a == nullptr || a->x == nullptr || a->params == nullptr) return set_error(ABT_ERR_ARG, "null argument");
+    if (a == nullptr) return set_error(ABT_ERR_ARG, "null argument");
     if (a->n_clips == 0 || a->n_views == 0) return 0;
+    if (a->x == nullptr || a->params == nullptr) return set_error(ABT_ERR_ARG, "null argument");
     if (a->n_clips < 0 || a->n_views < 0 || a->n_views > 65535) return set_error(ABT_ERR_ARG, "bad n_clips / n_views");
     if (a->in_h < 1 || a->in_w < 1 || (a->in_h * a->in_w) % 4 != 0) return set_error(ABT_ERR_ARG, "in_h * in_w must be a positive multiple of 4");
     if (a->canvas_h < a->in_h || a->canvas_w < a->in_w) return set_error(ABT_ERR_ARG, "canvas smaller than input");
@@ -517,19 +520,21 @@ extern "C" int abt_views_fwd(const abt_views_args* a, abt_stream_t stream) {
     }
     dim3 grid(a->n_clips, a->n_views);
     views_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    count_launch();
     ABT_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 extern "C" int abt_bank_push(const float* x, int64_t x_stride, int n_clips, int clip_elems, float* bank, int64_t bank_slot_stride,
                              const int32_t* slot, abt_stream_t stream) {
-    if (x == nullptr || bank == nullptr || slot == nullptr) return set_error(ABT_ERR_ARG, "null argument");
     if (n_clips == 0) return 0;
+    if (x == nullptr || bank == nullptr || slot == nullptr) return set_error(ABT_ERR_ARG, "null argument");
     if (n_clips < 0 || n_clips > 65535 || clip_elems < 4 || clip_elems % 4 != 0 || x_stride % 4 != 0 || bank_slot_stride % 4 != 0)
         return set_error(ABT_ERR_ARG, "bad shape (clip_elems and strides must be multiples of 4)");
     if (int rc = check_device_sm100()) return rc;
     dim3 grid((clip_elems / 4 + 255) / 256, n_clips);
     bank_push_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, x_stride, clip_elems, bank, bank_slot_stride, slot);
+    count_launch();
     ABT_CUDA_OK(cudaGetLastError());
     return 0;
 }

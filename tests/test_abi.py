@@ -1,0 +1,81 @@
+"""The C-ABI library loads on a machine without a GPU and exports every symbol include/abt_b200.h declares;
+argument validation and the 'no fallback' rule work without touching a device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from ssl_audio_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "abt_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(abt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 23
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in abt_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in ssl_audio_b200/_lib.py"
+    assert set(_lib.SIGNATURES) == set(names)
+
+
+def test_version_and_error_string():
+    lib = _lib.load()
+    assert lib.abt_version() == 100
+    assert isinstance(lib.abt_last_error(), bytes)
+
+
+def test_struct_sizes_match_header():
+    assert C.sizeof(_lib.ViewParams) == 48
+    assert C.sizeof(_lib.MelConfig) == 40
+    assert C.sizeof(_lib.BtArgs) == 8 * 2 + 4 * 10 + 8 * 7
+    assert C.sizeof(_lib.ViewsArgs) == 4 * 8 + 8 * 6 + 8 * 8
+    assert C.sizeof(_lib.PlanConfig) == 16 + 8 + 4 * 7 + 4 + 32 + 12 + 4 + 16 + 8
+
+
+def test_argument_validation_needs_no_gpu():
+    lib = _lib.load()
+    nbytes = C.c_size_t()
+    assert lib.abt_bt_workspace_bytes(128, 8192, 0, C.byref(nbytes)) == 0
+    assert nbytes.value > 2 * 8192 * 8192                      # H alone is 128 MiB
+    assert lib.abt_bt_workspace_bytes(128, 100, 0, C.byref(nbytes)) == _lib.ABT_ERR_ARG
+    assert b"multiple of 64" in lib.abt_last_error()
+    assert lib.abt_bt_workspace_bytes(1, 128, 0, C.byref(nbytes)) == _lib.ABT_ERR_ARG
+    with pytest.raises(ValueError):
+        _lib.check(lib.abt_bt_loss_fwd_bwd(None, None))
+    cfg = _lib.MelConfig(16000, 512, 512, 160, 64, 60.0, 7800.0, 0, 0.0, 1.0)
+    h = C.c_void_p()
+    assert lib.abt_logmel_plan_create(C.byref(cfg), C.byref(h)) == _lib.ABT_ERR_ARG   # n_fft must be 1024
+
+
+def test_no_cpu_fallback():
+    import torch
+    import ssl_audio_b200 as S
+    if torch.cuda.is_available():
+        pytest.skip("checks the behaviour of a GPU-less host")
+    assert _lib.load().abt_device_check() != 0
+    import types
+    crit = S.BarlowTwinsLoss(types.SimpleNamespace(projector_out_dim=64, HSIC=False, alpha=1.0, lmbda=0.005), ncrops=2)
+    with pytest.raises(RuntimeError):
+        crit.forward_loss(torch.zeros(8, 64), torch.zeros(8, 64))
+    with pytest.raises(RuntimeError):
+        S.LogMelSpectrogram(16000, 1024, 1024, 160, 64, 60, 7800)(torch.zeros(1, 4000))
+    with pytest.raises(RuntimeError):
+        S.RandomResizeCrop()(torch.zeros(1, 64, 96))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ssl_audio_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle for", "").replace("the oracle", "").replace("Parity oracle", ""), f

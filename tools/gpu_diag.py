@@ -31,28 +31,19 @@ def run(n, d, lam=0.005):
     base = ptr - buf.data_ptr()
     raw = buf.cpu().numpy()
     stats = raw[base + offs[0]: base + offs[0] + 10 * d * 4].view(np.float32).reshape(10, d)
-    H = torch.from_numpy(raw[base + offs[1]: base + offs[1] + 2 * d * d].copy()).view(torch.bfloat16).float().numpy().reshape(d, d)
+    Cm = torch.from_numpy(raw[base + offs[1]: base + offs[1] + 2 * d * d].copy()).view(torch.float16).float().numpy().reshape(d, d)
     g1 = raw[base + offs[2]: base + offs[2] + 4 * n * d].view(np.float32).reshape(n, d)
     g2 = raw[base + offs[3]: base + offs[3] + 4 * n * d].view(np.float32).reshape(n, d)
     h1, mu1, _, rr1 = O.batchnorm_train(z1.astype(np.float64))
     h2, mu2, _, rr2 = O.batchnorm_train(z2.astype(np.float64))
     print(f"--- N={n} D={d}: loss {float(loss):.6f} ref {rl:.6f}  rel {abs(float(loss)-rl)/rl:.2e}")
     print("    stats mu1", rel(stats[0], mu1), "r1", rel(stats[1], rr1), "mu2", rel(stats[2], mu2), "cdiag", rel(stats[4], np.diagonal(c)))
-    G = 2 * lam * c
-    np.fill_diagonal(G, 0.0)
-    Href = G * rr1[:, None] * rr2[None, :] / n
-    print("    H rel", rel(H, Href), " H^T rel (transposition bug?)", rel(H.T, Href), " |H|", np.abs(H).max(), np.abs(Href).max())
-    g1ref = Href @ z2.astype(np.float64).T     # (D, N)
-    g2ref = Href.T @ z1.astype(np.float64).T
-    print("    g1 rel", rel(g1, g1ref.T), " g2 rel", rel(g2, g2ref.T))
-    # GEMM-only check of the GRAD kernel with the H that was actually produced
-    print("    g1 vs own H", rel(g1, (H.astype(np.float64) @ z2.astype(np.float64).T).T), " g2 vs own H",
-          rel(g2, (H.astype(np.float64).T @ z1.astype(np.float64).T).T))
+    Cref = c.copy()
+    np.fill_diagonal(Cref, 0.0)
+    print("    C rel", rel(Cm, Cref), " C^T rel (transposition bug?)", rel(Cm.T, Cref))
+    print("    g1 rel", rel(g1, (Cref @ h2.T).T), " g2 rel", rel(g2, (Cref.T @ h1.T).T))
+    print("    g1 vs own C", rel(g1, (Cm.astype(np.float64) @ h2.T).T), " g2 vs own C", rel(g2, (Cm.astype(np.float64).T @ h1.T).T))
     print("    dz1 rel", rel(dz1.float().cpu().numpy(), r1), " dz2 rel", rel(dz2.float().cpu().numpy(), r2))
-    if rel(H, Href) > 0.05:
-        e = np.abs(H - Href)
-        bad = np.argwhere(e > 0.05 * np.abs(Href).max())
-        print("    bad H entries:", len(bad), "first", bad[:6].tolist(), "rows", sorted(set(bad[:, 0] // 8))[:10], "cols", sorted(set(bad[:, 1] // 8))[:10])
 
 
 if __name__ == "__main__":
