@@ -108,13 +108,15 @@ typedef struct {
     int32_t in_h, in_w;       /* 64, 96 */
     int32_t canvas_h, canvas_w; /* int(in_h * vcs[0]), int(in_w * vcs[1]) */
     int32_t out_h, out_w;     /* resize target (n_mels, crop_frames) or local_crops_size */
+    int32_t param_stride;     /* params of (clip, view) at params[clip * param_stride + view_offset + view]; 0 = n_views */
+    int32_t view_offset;
     const float* x;           /* clip b at x + x_slot[b] * x_slot_stride, (in_h, in_w) fp32; x_slot may be NULL */
     const int32_t* x_slot;
     int64_t x_slot_stride;
     const float* bank;        /* bank slot s at bank + s * bank_slot_stride */
     int64_t bank_slot_stride;
     const abt_view_params* params; /* device */
-    float* outs[8];           /* output tensor k: (n_clips, 1, out_h, out_w) contiguous */
+    float* outs[8];           /* output tensor of view k of this launch: (n_clips, 1, out_h, out_w) contiguous */
 } abt_views_args;
 
 int abt_views_fwd(const abt_views_args* args, abt_stream_t stream);
@@ -163,6 +165,13 @@ int abt_planner_bank_reset(abt_planner* p);
  * slots[n_clips] = bank ring slot each clip must be stored in (uid % ring_slots). */
 int abt_planner_plan_batch(abt_planner* p, int n_clips, int time_crop_range, int wav_crop_range, int32_t* starts,
                            int32_t* wav_starts, abt_view_params* params, int32_t* slots);
+
+/* Same, written into ONE caller-provided [host] buffer (e.g. pinned memory, uploaded with a single copy):
+ *   [abt_view_params x n_clips*(n_global+n_local)] [starts int32 x n_clips] [wav_starts int32 x n_clips] [slots int32 x n_clips]
+ * each section starting on a 16-byte boundary; abt_planner_packed_bytes() gives the size and section offsets. */
+int abt_planner_packed_bytes(const abt_planner* p, int n_clips, size_t* total, size_t* off_starts, size_t* off_wav_starts,
+                             size_t* off_slots);
+int abt_planner_plan_batch_packed(abt_planner* p, int n_clips, int time_crop_range, int wav_crop_range, void* out, size_t out_bytes);
 
 /* ===================================================================================== *
  *  Barlow Twins objective forward + backward

@@ -37,6 +37,7 @@ class ViewsArgs(C.Structure):
     _fields_ = [
         ("n_clips", C.c_int32), ("n_views", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32),
         ("canvas_h", C.c_int32), ("canvas_w", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32),
+        ("param_stride", C.c_int32), ("view_offset", C.c_int32),
         ("x", C.c_void_p), ("x_slot", C.c_void_p), ("x_slot_stride", C.c_int64),
         ("bank", C.c_void_p), ("bank_slot_stride", C.c_int64), ("params", C.c_void_p),
         ("outs", C.c_void_p * 8),
@@ -87,6 +88,9 @@ SIGNATURES = {
     "abt_planner_bank_len": (C.c_int, [C.c_void_p]),
     "abt_planner_bank_reset": (C.c_int, [C.c_void_p]),
     "abt_planner_plan_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "abt_planner_packed_bytes": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                           C.POINTER(C.c_size_t)]),
+    "abt_planner_plan_batch_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "abt_bt_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "abt_bt_loss_fwd_bwd": (C.c_int, [C.POINTER(BtArgs), C.c_void_p]),
     "abt_debug_set": (C.c_int, [C.c_int, C.c_int]),

@@ -62,74 +62,62 @@ class ViewEngine:
         return t.to(device, non_blocking=True)
 
 
-def _launch_views(lib, x: torch.Tensor, x_slot: Optional[torch.Tensor], x_slot_stride: int, ring: Optional[torch.Tensor],
-                  params_dev: torch.Tensor, n_clips: int, n_views: int, in_hw, canvas_hw, out_hw, outs: List[torch.Tensor]) -> None:
+def _launch_views(lib, x_ptr: int, x_slot_ptr: int, x_slot_stride: int, ring: Optional[torch.Tensor], params_ptr: int, param_stride: int,
+                  view_offset: int, n_clips: int, n_views: int, in_hw, canvas_hw, out_hw, outs: List[torch.Tensor], device) -> None:
     a = _lib.ViewsArgs()
     a.n_clips, a.n_views = int(n_clips), int(n_views)
     a.in_h, a.in_w = int(in_hw[0]), int(in_hw[1])
     a.canvas_h, a.canvas_w = int(canvas_hw[0]), int(canvas_hw[1])
     a.out_h, a.out_w = int(out_hw[0]), int(out_hw[1])
-    a.x = x.data_ptr()
-    a.x_slot = x_slot.data_ptr() if x_slot is not None else None
+    a.param_stride, a.view_offset = int(param_stride), int(view_offset)
+    a.x = x_ptr
+    a.x_slot = x_slot_ptr if x_slot_ptr else None
     a.x_slot_stride = int(x_slot_stride)
     a.bank = ring.data_ptr() if ring is not None else None
     a.bank_slot_stride = int(ring.shape[1]) if ring is not None else 0
-    a.params = params_dev.data_ptr()
+    a.params = params_ptr
     for k, o in enumerate(outs):
         a.outs[k] = o.data_ptr()
-    stream = torch.cuda.current_stream(x.device).cuda_stream
-    _lib.check(lib.abt_views_fwd(C.byref(a), stream))
+    _lib.check(lib.abt_views_fwd(C.byref(a), torch.cuda.current_stream(device).cuda_stream))
 
 
-def run_views(engine: ViewEngine, x: torch.Tensor, x_slot: Optional[torch.Tensor], x_slot_stride: int, plan: BatchPlan,
+def run_views(engine: ViewEngine, x: torch.Tensor, x_slot_ptr: int, x_slot_stride: int, plan: BatchPlan,
               n_global: int, n_local: int, global_out_hw, local_out_hw) -> List[torch.Tensor]:
-    """Run all views of a planned batch: one launch for the global views, one for the local crops."""
+    """Run all views of a planned (and uploaded) batch: one launch for the global views, one for the local crops."""
     lib = engine._lib
     dev = x.device
     n_clips = plan.params.shape[0]
+    n_views = n_global + n_local
     outs: List[torch.Tensor] = []
-    ring = engine.ring
     if n_global:
-        pg = np.ascontiguousarray(plan.params[:, :n_global])
-        pg["out_index"] = np.arange(n_global, dtype=np.int32)[None, :]
         g_outs = [torch.empty((n_clips, 1, global_out_hw[0], global_out_hw[1]), dtype=torch.float32, device=dev) for _ in range(n_global)]
         if n_clips:
-            _launch_views(lib, x, x_slot, x_slot_stride, ring, ViewEngine.upload(pg, dev), n_clips, n_global, engine.in_hw,
-                          engine.canvas_hw, global_out_hw, g_outs)
+            _launch_views(lib, x.data_ptr(), x_slot_ptr, x_slot_stride, engine.ring, plan.params_ptr, n_views, 0, n_clips, n_global,
+                          engine.in_hw, engine.canvas_hw, global_out_hw, g_outs, dev)
         outs += g_outs
     if n_local:
-        pl = np.ascontiguousarray(plan.params[:, n_global:])
-        pl["out_index"] = np.arange(n_local, dtype=np.int32)[None, :]
         l_outs = [torch.empty((n_clips, 1, local_out_hw[0], local_out_hw[1]), dtype=torch.float32, device=dev) for _ in range(n_local)]
         if n_clips:
             # local crops use virtual_crop_scale (1, 1): the canvas is the input itself
-            _launch_views(lib, x, x_slot, x_slot_stride, None, ViewEngine.upload(pl, dev), n_clips, n_local, engine.in_hw,
-                          engine.in_hw, local_out_hw, l_outs)
+            _launch_views(lib, x.data_ptr(), x_slot_ptr, x_slot_stride, None, plan.params_ptr, n_views, n_global, n_clips, n_local,
+                          engine.in_hw, engine.in_hw, local_out_hw, l_outs, dev)
         outs += l_outs
     return outs
 
 
-def push_bank(engine: ViewEngine, x: torch.Tensor, x_stride: int, slots: np.ndarray) -> None:
+def push_bank(engine: ViewEngine, x: torch.Tensor, x_stride: int, plan: BatchPlan) -> None:
     """bank[slot[b]] = x[b], stream-ordered AFTER the view kernel that may still read the old slot contents."""
-    n = int(slots.shape[0])
+    n = int(plan.slots.shape[0])
     if n == 0:
         return
     ring = engine.ring
-    slot_dev = ViewEngine.upload(slots, x.device)
     stream = torch.cuda.current_stream(x.device).cuda_stream
     _lib.check(engine._lib.abt_bank_push(x.data_ptr(), int(x_stride), n, int(ring.shape[1]), ring.data_ptr(), int(ring.shape[1]),
-                                         slot_dev.data_ptr(), stream))
+                                         plan.slots_ptr, stream))
 
 
 class _SingleStage(nn.Module):
-    """Shared plumbing of the three stand-alone augmentation modules."""
-
-    def _setup(self, planner: ViewPlanner, in_hw, canvas_hw):
-        self._engine = ViewEngine(planner, in_hw, canvas_hw)
-        self._in_hw = tuple(in_hw)
-
-    def _geometry(self, x4: torch.Tensor):
-        return int(x4.shape[2]), int(x4.shape[3])
+    """Base of the three stand-alone augmentation modules (they share the view kernel and the planner)."""
 
 
 class RandomResizeCrop(_SingleStage):
@@ -167,8 +155,8 @@ class RandomResizeCrop(_SingleStage):
             pl = ViewPlanner(mixup=False, rrc=True, rlf=False, n_global=1, in_hw=(F, T), canvas_hw=canvas,
                              freq_scale=self.freq_scale, time_scale=self.time_scale)
             self._engine = ViewEngine(pl, (F, T), canvas)
-        plan = self._engine.planner.plan(x4.shape[0])
-        out = run_views(self._engine, x4, None, F * T, plan, 1, 0, tuple(self.out_size), None)[0]
+        plan = self._engine.planner.plan(x4.shape[0], device=x4.device)
+        out = run_views(self._engine, x4, 0, F * T, plan, 1, 0, tuple(self.out_size), None)[0]
         return out[0] if single else out
 
     def __repr__(self):
@@ -193,8 +181,8 @@ class RandomLinearFader(_SingleStage):
         if self._engine is None or self._engine.in_hw != (F, T):
             pl = ViewPlanner(mixup=False, rrc=False, rlf=True, n_global=1, in_hw=(F, T), canvas_hw=(F, T), fader_gain=self.gain)
             self._engine = ViewEngine(pl, (F, T), (F, T))
-        plan = self._engine.planner.plan(x4.shape[0])
-        out = run_views(self._engine, x4, None, F * T, plan, 1, 0, (F, T), None)[0]
+        plan = self._engine.planner.plan(x4.shape[0], device=x4.device)
+        out = run_views(self._engine, x4, 0, F * T, plan, 1, 0, (F, T), None)[0]
         return out[0] if single else out
 
     def __repr__(self):
@@ -219,7 +207,8 @@ def log_mixup_exp(xa: torch.Tensor, xb: torch.Tensor, alpha: float) -> torch.Ten
     params["flags"] = 1
     out = torch.empty((n, 1, F, T), dtype=torch.float32, device=xa.device)
     if n:
-        _launch_views(_lib.load(), a2, None, F * T, b2, ViewEngine.upload(params, xa.device), n, 1, (F, T), (F, T), (F, T), [out])
+        pdev = ViewEngine.upload(params, xa.device)
+        _launch_views(_lib.load(), a2.data_ptr(), 0, F * T, b2, pdev.data_ptr(), 1, 0, n, 1, (F, T), (F, T), (F, T), [out], xa.device)
     return out.reshape(xa.shape)
 
 
@@ -261,9 +250,9 @@ class MixupBYOLA(_SingleStage):
             self._pushed = 0
         eng = self._engine
         eng.ensure_ring(x4.device)
-        plan = eng.planner.plan(x4.shape[0])
-        out = run_views(eng, x4, None, F * T, plan, 1, 0, (F, T), None)[0]
-        push_bank(eng, x4, F * T, plan.slots)
+        plan = eng.planner.plan(x4.shape[0], device=x4.device)
+        out = run_views(eng, x4, 0, F * T, plan, 1, 0, (F, T), None)[0]
+        push_bank(eng, x4, F * T, plan)
         self._pushed += int(x4.shape[0])
         return out[0] if single else out
 

@@ -81,8 +81,9 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
     const int clip = blockIdx.y;
     const int tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int f_first = (a.frame_start ? a.frame_start[clip] : 0) + tile * kTileFrames;   // absolute frame index
-    const float* wav = a.wav + (long long)clip * a.row_stride + (a.wav_offset ? a.wav_offset[clip] : 0);
+    // -1 in frame_start / wav_offset means "no crop was drawn" (clip not longer than the crop)
+    const int f_first = (a.frame_start ? max(a.frame_start[clip], 0) : 0) + tile * kTileFrames;   // absolute frame index
+    const float* wav = a.wav + (long long)clip * a.row_stride + (a.wav_offset ? max(a.wav_offset[clip], 0) : 0);
 
     // ---- stage the sample span (reflect padding: padded index s -> original s - n_fft/2, mirrored)
     const long long s0 = (long long)f_first * a.hop;
@@ -248,7 +249,8 @@ __global__ void __launch_bounds__(256) views_kernel(const abt_views_args a) {
     int* tap = reinterpret_cast<int*>(coef + (a.out_w + a.out_h) * 4);   // (out_w + out_h) * 4 clamped taps
     const int clip = blockIdx.x, view = blockIdx.y;
     const int tid = threadIdx.x;
-    const abt_view_params p = a.params[clip * a.n_views + view];
+    const int pstride = a.param_stride > 0 ? a.param_stride : a.n_views;
+    const abt_view_params p = a.params[(size_t)clip * pstride + a.view_offset + view];
     const long long xs = a.x_slot ? a.x_slot[clip] : clip;
     const float* x = a.x + xs * a.x_slot_stride;
     const float* z = nullptr;
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(256) views_kernel(const abt_views_args a) {
     // fader: torch.linspace(head, tail, T) evaluated from both ends with one rounding (fma)
     const bool fade = (p.flags & 4) != 0;
     const float step = a.out_w > 1 ? (p.tail - p.head) / (float)(a.out_w - 1) : 0.f;
-    float* out = a.outs[p.out_index] + (size_t)clip * a.out_h * a.out_w;
+    float* out = a.outs[view] + (size_t)clip * a.out_h * a.out_w;
     const int n_out = a.out_h * a.out_w;
     for (int idx = tid; idx < n_out; idx += blockDim.x) {
         const int oy = idx / a.out_w, ox = idx % a.out_w;
@@ -505,7 +507,8 @@ extern "C" int abt_views_fwd(const abt_views_args* a, abt_stream_t stream) {
     if (a == nullptr) return set_error(ABT_ERR_ARG, "null argument");
     if (a->n_clips == 0 || a->n_views == 0) return 0;
     if (a->x == nullptr || a->params == nullptr) return set_error(ABT_ERR_ARG, "null argument");
-    if (a->n_clips < 0 || a->n_views < 0 || a->n_views > 65535) return set_error(ABT_ERR_ARG, "bad n_clips / n_views");
+    if (a->n_clips < 0 || a->n_views < 0 || a->n_views > 8) return set_error(ABT_ERR_ARG, "bad n_clips / n_views (at most 8 views per launch)");
+    if (a->param_stride < 0 || a->view_offset < 0) return set_error(ABT_ERR_ARG, "bad param_stride / view_offset");
     if (a->in_h < 1 || a->in_w < 1 || (a->in_h * a->in_w) % 4 != 0) return set_error(ABT_ERR_ARG, "in_h * in_w must be a positive multiple of 4");
     if (a->canvas_h < a->in_h || a->canvas_w < a->in_w) return set_error(ABT_ERR_ARG, "canvas smaller than input");
     if (a->out_h < 1 || a->out_w < 1 || a->out_h + a->out_w > 256) return set_error(ABT_ERR_ARG, "out_h + out_w must be in [2, 256]");

@@ -226,3 +226,28 @@ extern "C" int abt_planner_plan_batch(abt_planner* p, int n_clips, int time_crop
     }
     return 0;
 }
+
+static size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+extern "C" int abt_planner_packed_bytes(const abt_planner* p, int n_clips, size_t* total, size_t* off_starts, size_t* off_wav_starts,
+                                        size_t* off_slots) {
+    if (p == nullptr || n_clips < 0) return abt::set_error(ABT_ERR_ARG, "bad argument");
+    const size_t n_views = (size_t)(p->cfg.n_global + p->cfg.n_local);
+    const size_t o1 = a16(sizeof(abt_view_params) * n_views * (size_t)n_clips);
+    const size_t o2 = o1 + a16(sizeof(int32_t) * (size_t)n_clips);
+    const size_t o3 = o2 + a16(sizeof(int32_t) * (size_t)n_clips);
+    if (off_starts) *off_starts = o1;
+    if (off_wav_starts) *off_wav_starts = o2;
+    if (off_slots) *off_slots = o3;
+    if (total) *total = o3 + a16(sizeof(int32_t) * (size_t)n_clips);
+    return 0;
+}
+
+extern "C" int abt_planner_plan_batch_packed(abt_planner* p, int n_clips, int time_crop_range, int wav_crop_range, void* out, size_t out_bytes) {
+    size_t total, o1, o2, o3;
+    if (int rc = abt_planner_packed_bytes(p, n_clips, &total, &o1, &o2, &o3)) return rc;
+    if (out == nullptr || out_bytes < total) return abt::set_error(ABT_ERR_ARG, "packed plan buffer too small (%zu < %zu)", out_bytes, total);
+    uint8_t* b = static_cast<uint8_t*>(out);
+    return abt_planner_plan_batch(p, n_clips, time_crop_range, wav_crop_range, reinterpret_cast<int32_t*>(b + o1),
+                                  reinterpret_cast<int32_t*>(b + o2), reinterpret_cast<abt_view_params*>(b), reinterpret_cast<int32_t*>(b + o3));
+}

@@ -90,15 +90,16 @@ class LogMelSpectrogram(nn.Module):
             _lib.check(self._lib.abt_logmel_fwd(self.plan(wav.device), w2.data_ptr(), B, L, out.data_ptr(), _stream(wav.device)))
         return out.reshape(*lead, self.n_mels, T)
 
-    def crop_into(self, wav2d: torch.Tensor, n_samples: int, wav_offset: Optional[torch.Tensor], frame_start: Optional[torch.Tensor],
-                  n_frames: int, out_base: torch.Tensor, out_slot: Optional[torch.Tensor], out_slot_stride: int) -> None:
-        """Crop-first log-mel of `n_frames` frames per clip written to out_base[out_slot[b]] (see abt_logmel_crop_fwd)."""
+    def crop_into(self, wav2d: torch.Tensor, n_samples: int, wav_offset_ptr: int, frame_start_ptr: int, n_frames: int,
+                  out_base: torch.Tensor, out_slot_ptr: int, out_slot_stride: int) -> None:
+        """Crop-first log-mel of `n_frames` frames per clip written to out_base[out_slot[b]] (see abt_logmel_crop_fwd).
+        The *_ptr arguments are device pointers to int32 arrays (0 = absent)."""
         B = int(wav2d.shape[0])
         with torch.cuda.device(wav2d.device):
             _lib.check(self._lib.abt_logmel_crop_fwd(
-                self.plan(wav2d.device), wav2d.data_ptr(), int(wav2d.stride(0)), None if wav_offset is None else wav_offset.data_ptr(),
-                B, int(n_samples), None if frame_start is None else frame_start.data_ptr(), int(n_frames), out_base.data_ptr(),
-                None if out_slot is None else out_slot.data_ptr(), int(out_slot_stride), _stream(wav2d.device)))
+                self.plan(wav2d.device), wav2d.data_ptr(), int(wav2d.stride(0)), wav_offset_ptr or None, B, int(n_samples),
+                frame_start_ptr or None, int(n_frames), out_base.data_ptr(), out_slot_ptr or None, int(out_slot_stride),
+                _stream(wav2d.device)))
 
 
 class BatchFrontend(nn.Module):
@@ -142,15 +143,14 @@ class BatchFrontend(nn.Module):
         eng = tf.engine(B)
         ring = eng.ensure_ring(lms.device)
         crop_range = T_full - self.crop_frames if T_full > self.crop_frames else 0
-        plan = eng.planner.plan(B, time_crop_range=crop_range)
-        starts = ViewEngine.upload(plan.starts, lms.device).view(torch.int32)
-        slots = ViewEngine.upload(plan.slots, lms.device).view(torch.int32)
+        plan = eng.planner.plan(B, time_crop_range=crop_range, device=lms.device)
         mean, std = self.norm_stats if self.norm_stats is not None else (0.0, 1.0)
         with torch.cuda.device(lms.device):
-            _lib.check(self._lib.abt_lms_crop_norm(lms.data_ptr(), B, F, T_full, starts.data_ptr(), self.crop_frames,
-                                                   int(self.norm_stats is not None), mean, std, ring.data_ptr(), slots.data_ptr(),
+            _lib.check(self._lib.abt_lms_crop_norm(lms.data_ptr(), B, F, T_full, plan.starts_ptr, self.crop_frames,
+                                                   int(self.norm_stats is not None), mean, std, ring.data_ptr(), plan.slots_ptr,
                                                    int(ring.shape[1]), _stream(lms.device)))
-        return tf.views_from_plan(ring, slots, int(ring.shape[1]), plan)
+        self.last_plan = plan
+        return tf.views_from_plan(ring, plan.slots_ptr, int(ring.shape[1]), plan)
 
     # -- waveform input ---------------------------------------------------------------------------
     def forward(self, wav: torch.Tensor) -> List[torch.Tensor]:
@@ -169,22 +169,18 @@ class BatchFrontend(nn.Module):
                 self.last_lms = self.logmel_raw(wav)
                 return self.forward_lms(self.last_lms)
             crop_range = T_full - self.crop_frames if T_full > self.crop_frames else 0
-            plan = eng.planner.plan(B, time_crop_range=crop_range)
-            starts = ViewEngine.upload(np.maximum(plan.starts, 0), wav.device).view(torch.int32)
-            slots = ViewEngine.upload(plan.slots, wav.device).view(torch.int32)
-            self.logmel_norm.crop_into(wav, L, None, starts, self.crop_frames, ring, slots, stride)
+            plan = eng.planner.plan(B, time_crop_range=crop_range, device=wav.device)
+            self.logmel_norm.crop_into(wav, L, 0, plan.starts_ptr, self.crop_frames, ring, plan.slots_ptr, stride)
         else:
             # datasets.py:103-113: centre pad to unit_length, then random.randint unit crop
             if L < self.unit_length:
                 adj = self.unit_length - L
                 wav = torch.nn.functional.pad(wav, (adj // 2, adj - adj // 2))
                 L = self.unit_length
-            plan = eng.planner.plan(B, wav_crop_range=L - self.unit_length)
-            offs = ViewEngine.upload(np.maximum(plan.wav_starts, 0), wav.device).view(torch.int32)
-            slots = ViewEngine.upload(plan.slots, wav.device).view(torch.int32)
+            plan = eng.planner.plan(B, wav_crop_range=L - self.unit_length, device=wav.device)
             n_frames = self.logmel_norm.n_frames(self.unit_length)
             if n_frames != self.crop_frames:
                 raise ValueError(f"unit_sec gives {n_frames} frames but crop_frames is {self.crop_frames}")
-            self.logmel_norm.crop_into(wav, self.unit_length, offs, None, n_frames, ring, slots, stride)
+            self.logmel_norm.crop_into(wav, self.unit_length, plan.wav_starts_ptr, 0, n_frames, ring, plan.slots_ptr, stride)
         self.last_plan = plan
-        return tf.views_from_plan(ring, slots, stride, plan)
+        return tf.views_from_plan(ring, plan.slots_ptr, stride, plan)

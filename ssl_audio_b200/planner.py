@@ -41,6 +41,42 @@ class BatchPlan:
     wav_starts: np.ndarray   # (B,) int32 wav-crop start per clip, -1 if none was drawn
     params: np.ndarray       # (B, n_views) VIEW_DTYPE
     slots: np.ndarray        # (B,) int32 bank ring slot of each clip
+    # device copy of the packed plan (one H2D copy), when planned with a device
+    dev: Optional["torch.Tensor"] = None
+    params_ptr: int = 0
+    starts_ptr: int = 0
+    wav_starts_ptr: int = 0
+    slots_ptr: int = 0
+
+
+class PlanStaging:
+    """Ring of pinned host buffers + device buffers for the packed plan: one cudaMemcpyAsync per batch and no
+    per-step pinned allocation.  A slot is reused only after the copy that read it has completed."""
+
+    def __init__(self, device, nbytes: int, depth: int = 4):
+        import torch
+        self.device = device
+        self.nbytes = int(nbytes)
+        self.host = [torch.empty(self.nbytes, dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self.host_np = [h.numpy() for h in self.host]
+        self.dev = [torch.empty(self.nbytes, dtype=torch.uint8, device=device) for _ in range(depth)]
+        self.done = [None] * depth
+        self.k = 0
+
+    def acquire(self):
+        k = self.k
+        self.k = (k + 1) % len(self.host)
+        if self.done[k] is not None:
+            self.done[k].synchronize()
+        return k
+
+    def upload(self, k: int, nbytes: int):
+        import torch
+        self.dev[k][:nbytes].copy_(self.host[k][:nbytes], non_blocking=True)
+        ev = self.done[k] if self.done[k] is not None else torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.done[k] = ev
+        return self.dev[k]
 
 
 class ViewPlanner:
@@ -74,6 +110,7 @@ class ViewPlanner:
         _lib.check(lib.abt_planner_create(C.byref(cfg), C.byref(self._h)))
         self._lib = lib
         self._key = np.empty(624, dtype=np.uint32)
+        self._staging = {}
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -89,10 +126,25 @@ class ViewPlanner:
         self._lib.abt_planner_bank_reset(self._h)
 
     # -- planning ------------------------------------------------------------------------------
-    def plan(self, n_clips: int, time_crop_range: int = 0, wav_crop_range: int = 0) -> BatchPlan:
+    def plan(self, n_clips: int, time_crop_range: int = 0, wav_crop_range: int = 0, device=None) -> BatchPlan:
+        """Draw the parameters of `n_clips` samples.  With `device`, the packed plan is also uploaded to that CUDA
+        device (one asynchronous copy on the current stream) and the device pointers are filled in."""
         lib, h = self._lib, self._h
         use_np = self._uses_numpy or time_crop_range > 0
         use_py = self._uses_pyrandom or wav_crop_range > 0
+        total, o1, o2, o3 = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _lib.check(lib.abt_planner_packed_bytes(h, n_clips, C.byref(total), C.byref(o1), C.byref(o2), C.byref(o3)))
+        nbytes = total.value
+        slot = -1
+        if device is not None:
+            st = self._staging.get(device)
+            if st is None or st.nbytes < nbytes:
+                st = PlanStaging(device, max(nbytes, 1 << 16))
+                self._staging[device] = st
+            slot = st.acquire()
+            buf = st.host_np[slot]
+        else:
+            buf = np.empty(max(nbytes, 16), dtype=np.uint8)
         if use_np:
             # numpy's global legacy generator, accessed in place: its bit generator exposes the address of
             # `struct { uint32_t key[624]; int pos; }` (numpy/random/src/mt19937/mt19937.h)
@@ -103,12 +155,7 @@ class ViewPlanner:
             pst = _pyrandom.getstate()
             pkey = np.array(pst[1][:624], dtype=np.uint32)
             _lib.check(lib.abt_planner_set_pyrandom_state(h, pkey.ctypes.data, int(pst[1][624])))
-        starts = np.empty(n_clips, dtype=np.int32)
-        wav_starts = np.empty(n_clips, dtype=np.int32)
-        slots = np.empty(n_clips, dtype=np.int32)
-        params = np.empty((n_clips, self.n_views), dtype=VIEW_DTYPE)
-        _lib.check(lib.abt_planner_plan_batch(h, n_clips, int(time_crop_range), int(wav_crop_range), starts.ctypes.data,
-                                              wav_starts.ctypes.data, params.ctypes.data, slots.ctypes.data))
+        _lib.check(lib.abt_planner_plan_batch_packed(h, n_clips, int(time_crop_range), int(wav_crop_range), buf.ctypes.data, buf.nbytes))
         pos = C.c_int()
         if use_np:
             _lib.check(lib.abt_planner_get_numpy_state(h, np_addr, C.byref(pos)))
@@ -116,4 +163,15 @@ class ViewPlanner:
         if use_py:
             _lib.check(lib.abt_planner_get_pyrandom_state(h, self._key.ctypes.data, C.byref(pos)))
             _pyrandom.setstate((pst[0], tuple(self._key.tolist()) + (pos.value,), pst[2]))
-        return BatchPlan(starts, wav_starts, params, slots)
+        nv = self.n_views
+        params = buf[:48 * nv * n_clips].view(VIEW_DTYPE).reshape(n_clips, nv)
+        starts = buf[o1.value:o1.value + 4 * n_clips].view(np.int32)
+        wav_starts = buf[o2.value:o2.value + 4 * n_clips].view(np.int32)
+        slots = buf[o3.value:o3.value + 4 * n_clips].view(np.int32)
+        plan = BatchPlan(starts, wav_starts, params, slots)
+        if device is not None:
+            dev = st.upload(slot, nbytes)
+            base = dev.data_ptr()
+            plan.dev = dev
+            plan.params_ptr, plan.starts_ptr, plan.wav_starts_ptr, plan.slots_ptr = base, base + o1.value, base + o2.value, base + o3.value
+        return plan

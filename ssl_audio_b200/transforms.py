@@ -78,15 +78,16 @@ class AudioPairTransform(nn.Module):
         eng = self.engine(B)
         if self._mixup:
             eng.ensure_ring(x4.device)
-        plan = eng.planner.plan(B)
-        outs = self.views_from_plan(x4, None, self._in_hw[0] * self._in_hw[1], plan)
+        plan = eng.planner.plan(B, device=x4.device)
+        outs = self.views_from_plan(x4, 0, self._in_hw[0] * self._in_hw[1], plan)
         if self._mixup:
-            push_bank(eng, x4, self._in_hw[0] * self._in_hw[1], plan.slots)
+            push_bank(eng, x4, self._in_hw[0] * self._in_hw[1], plan)
         if single:
             outs = [o[0] for o in outs]
         return outs if self.multi_transform else outs[0]
 
-    def views_from_plan(self, x, x_slot, x_slot_stride, plan) -> List[torch.Tensor]:
-        """Views of an already planned batch whose clips live at x + x_slot[b] * x_slot_stride (used by the
-        batch frontend, which lets the log-mel kernel write the clips straight into the Mixup ring)."""
-        return run_views(self._engine, x, x_slot, x_slot_stride, plan, self._n_global, self._n_local, self._in_hw, self._local_hw)
+    def views_from_plan(self, x, x_slot_ptr, x_slot_stride, plan) -> List[torch.Tensor]:
+        """Views of an already planned batch whose clips live at x + x_slot[b] * x_slot_stride (x_slot_ptr: device pointer to
+        int32 slots, 0 = identity; used by the batch frontend, which lets the log-mel kernel write the clips straight into
+        the Mixup ring)."""
+        return run_views(self._engine, x, x_slot_ptr, x_slot_stride, plan, self._n_global, self._n_local, self._in_hw, self._local_hw)

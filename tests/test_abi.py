@@ -37,7 +37,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_lib.ViewParams) == 48
     assert C.sizeof(_lib.MelConfig) == 40
     assert C.sizeof(_lib.BtArgs) == 8 * 2 + 4 * 10 + 8 * 7
-    assert C.sizeof(_lib.ViewsArgs) == 4 * 8 + 8 * 6 + 8 * 8
+    assert C.sizeof(_lib.ViewsArgs) == 4 * 10 + 8 * 6 + 8 * 8
     assert C.sizeof(_lib.PlanConfig) == 16 + 8 + 4 * 7 + 4 + 32 + 12 + 4 + 16 + 8
 
 
