@@ -203,6 +203,33 @@ typedef struct {
 int abt_bt_workspace_bytes(int n_rows, int n_dims, int dtype, size_t* bytes);
 int abt_bt_loss_fwd_bwd(const abt_bt_args* args, abt_stream_t stream);
 
+/* Row-block form for the multi-GPU objective (replaces the D x D `torch.distributed.all_reduce(c)` of
+ * utils/loss.py:20-21 with: all-gather of the embeddings -> this call -> all-to-all of the gradients -> 3-double
+ * all-reduce).  zg1 / zg2 are the rank-ordered GLOBAL batches (n_rows = N_g); this rank owns dimensions
+ * [row_begin, row_begin + row_count): it computes those rows of C and of C^T, the off-diagonal loss of its rows
+ * of C, and d loss / d z for ALL n_rows samples restricted to its dimensions (batch-norm backward is per column).
+ * Statistics (and the running-stat update) are those of the global batch and identical on every rank. */
+typedef struct {
+    const void* zg1;      /* (n_rows, n_dims) row-major gathered embeddings */
+    const void* zg2;
+    int32_t dtype, n_rows, n_dims;
+    int32_t row_begin, row_count;   /* multiples of 8 */
+    float alpha, lambda;
+    int32_t hsic;
+    float eps, momentum, grad_scale;
+    int32_t need_grad_mask;
+    double* loss_parts;   /* device, 3 doubles: sum_{i in rows, j != i} C_ij^2, sum_{i in rows, j != i} C_ij, sum_{all i} (C_ii - 1)^2 */
+    void* dzr1;           /* (n_rows, row_count) compact, same dtype as the inputs, or NULL */
+    void* dzr2;
+    float* running_mean;  /* (n_dims) or NULL */
+    float* running_var;
+    void* workspace;      /* abt_bt_rows_workspace_bytes() bytes, 256-byte aligned */
+    size_t workspace_bytes;
+} abt_bt_rows_args;
+
+int abt_bt_rows_workspace_bytes(int n_rows, int n_dims, int row_count, int dtype, size_t* bytes);
+int abt_bt_loss_rows_fwd_bwd(const abt_bt_rows_args* args, abt_stream_t stream);
+
 /* ===================================================================================== *
  *  Debug hooks (not part of the drop-in surface; used by tools/gpu_diag.py)
  * ===================================================================================== */

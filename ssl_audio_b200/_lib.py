@@ -65,6 +65,16 @@ class BtArgs(C.Structure):
     ]
 
 
+class BtRowsArgs(C.Structure):
+    _fields_ = [
+        ("zg1", C.c_void_p), ("zg2", C.c_void_p), ("dtype", C.c_int32), ("n_rows", C.c_int32), ("n_dims", C.c_int32),
+        ("row_begin", C.c_int32), ("row_count", C.c_int32), ("alpha", C.c_float), ("lambda_", C.c_float), ("hsic", C.c_int32),
+        ("eps", C.c_float), ("momentum", C.c_float), ("grad_scale", C.c_float), ("need_grad_mask", C.c_int32),
+        ("loss_parts", C.c_void_p), ("dzr1", C.c_void_p), ("dzr2", C.c_void_p), ("running_mean", C.c_void_p),
+        ("running_var", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol of include/abt_b200.h
 SIGNATURES = {
     "abt_version": (C.c_int, []),
@@ -93,6 +103,8 @@ SIGNATURES = {
     "abt_planner_plan_batch_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "abt_bt_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "abt_bt_loss_fwd_bwd": (C.c_int, [C.POINTER(BtArgs), C.c_void_p]),
+    "abt_bt_rows_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "abt_bt_loss_rows_fwd_bwd": (C.c_int, [C.POINTER(BtRowsArgs), C.c_void_p]),
     "abt_debug_set": (C.c_int, [C.c_int, C.c_int]),
     "abt_debug_launch_count": (C.c_longlong, [C.c_int]),
     "abt_debug_timing": (C.c_int, [C.c_int]),

@@ -134,8 +134,9 @@ class BarlowTwinsLoss(nn.Module):
         # holds running_mean / running_var / num_batches_tracked exactly like the reference module (utils/loss.py:13);
         # the normalisation itself happens inside the CUDA kernels
         self.bn = nn.BatchNorm1d(cfg.projector_out_dim, affine=False)
-        # multi-GPU only: local gradients are multiplied by this (world_size cancels DDP's gradient averaging)
-        self.grad_scale = 1.0
+        # multi-GPU only: local gradients are multiplied by this; None = world_size, which cancels DDP's gradient
+        # averaging so that R-rank and single-process runs give the same parameter update
+        self.grad_scale = None
 
     def forward_loss(self, z1, z2):
         if z1.shape[-1] != self.cfg.projector_out_dim:

@@ -1,0 +1,69 @@
+"""Row-block (multi-GPU) form of the objective on ONE GPU: the R ranks' calls are issued one after the other on
+the same gathered batch and their outputs assembled, which is exactly what the collectives in
+ssl_audio_b200/dist.py do across GPUs (that choreography is tested with gloo in tests/test_dist_gloo.py).
+Parity target: the single-process global-batch oracle ("Multi-GPU")."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import abt_oracle as O  # noqa: E402
+
+TOL = 1e-3
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.mark.parametrize("world,n_local,d,hsic,dtype", [
+    (2, 64, 256, False, "f32"), (4, 32, 512, False, "f32"), (8, 16, 1024, True, "f32"), (2, 160, 512, False, "bf16"),
+    (8, 128, 2048, False, "bf16"),
+])
+def test_row_blocks_assemble_to_global_objective(world, n_local, d, hsic, dtype):
+    from ssl_audio_b200 import dist as D
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    ng = world * n_local
+    z1, z2 = O.synth_embeddings(ng, d, seed=world + d)
+    zg1, zg2 = torch.from_numpy(z1).cuda().to(tdt), torch.from_numpy(z2).cuda().to(tdt)
+    off = np.zeros(2)
+    on = None
+    dz1 = np.zeros((ng, d), np.float32)
+    dz2 = np.zeros((ng, d), np.float32)
+    rm = [torch.zeros(d, device="cuda") for _ in range(world)]
+    rv = [torch.ones(d, device="cuda") for _ in range(world)]
+    for r in range(world):
+        begin, count = D.row_block(d, world, r)
+        parts, a, b = D._rows_cuda(zg1, zg2, begin, count, 1.0, 0.005, hsic, 1e-5, 0.1, 1.0, 3, rm[r], rv[r])
+        p = parts.cpu().numpy()
+        off += p[:2]
+        on = p[2] if on is None else on
+        assert abs(p[2] - on) <= 1e-9 * max(1.0, abs(on))          # identical on every rank
+        dz1[:, begin:begin + count] = a.float().cpu().numpy()
+        dz2[:, begin:begin + count] = b.float().cpu().numpy()
+    loss = on + 0.005 * (off[0] + (2 * off[1] + d * (d - 1) if hsic else 0.0))
+    rl, r1, r2, _ = O.bt_loss_forward_backward(z1, z2, 1.0, 0.005, hsic)
+    assert abs(loss - rl) <= TOL * abs(rl), (loss, rl)
+    slack = 0.0 if dtype == "f32" else 4e-3                           # bf16 output quantum
+    assert _rel(dz1, r1) < TOL + slack and _rel(dz2, r2) < TOL + slack, (_rel(dz1, r1), _rel(dz2, r2))
+    # running statistics are those of the global batch on every rank
+    m, v = O.bn_running_update(np.zeros(d), np.ones(d), z1)
+    m, v = O.bn_running_update(m, v, z2)
+    for r in range(world):
+        np.testing.assert_allclose(rm[r].cpu().numpy(), m, rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(rv[r].cpu().numpy(), v, rtol=1e-4, atol=1e-5)
+
+
+def test_row_block_one_sided_and_errors():
+    from ssl_audio_b200 import dist as D
+    z1, z2 = O.synth_embeddings(64, 256, seed=2)
+    zg1, zg2 = torch.from_numpy(z1).cuda(), torch.from_numpy(z2).cuda()
+    parts, a, b = D._rows_cuda(zg1, zg2, 128, 64, 1.0, 0.005, False, 1e-5, 0.1, 2.0, 2, None, None)
+    assert a is None
+    _, _, r2, _ = O.bt_loss_forward_backward(z1, z2)
+    assert _rel(b.cpu().numpy(), 2.0 * r2[:, 128:192]) < TOL        # grad_scale = 2
+    with pytest.raises(ValueError):
+        D._rows_cuda(zg1, zg2, 4, 64, 1.0, 0.005, False, 1e-5, 0.1, 1.0, 3, None, None)     # unaligned block
+    with pytest.raises(ValueError):
+        D._rows_cuda(zg1, zg2, 224, 64, 1.0, 0.005, False, 1e-5, 0.1, 1.0, 3, None, None)   # outside D
