@@ -222,6 +222,11 @@ struct PassCfg {
     __half* c_out;            // CORR: row-major (rows local to row0) x D, fp16, diagonal zeroed
     float* g_out;             // GRAD: g_out[n * ldg + (row - row0)]
     int ldg;
+    // Column-blocked C (multi-GPU, Dr = D / world): element (local row i, column j) lives at ((j / Dr) * Dr + i) * Dr + j % Dr, so
+    // that block q = C[rows, q Dr : (q+1) Dr] is contiguous for the all-to-all.  CORR writes it, the K-major GRAD pass reads it
+    // through a (world * Dr) x Dr tensor map.  0 = plain row-major.
+    int blocked_dr;
+    float inv_n;              // CORR on standardised fp16 operands (row_nmu == nullptr): c = S * inv_n
 };
 
 struct UmmaParams {
@@ -231,6 +236,7 @@ struct UmmaParams {
     int tiles_m, tiles_n, splits, kblocks;   // per pass
     int pass_count;
     int bn;            // UMMA N of this launch (multiple of 16, <= 256)
+    int ab_format;     // operand type of this launch: 1 = bf16, 0 = fp16
     int hsic;
     int write_c;
     double* loss_acc;
@@ -303,8 +309,13 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     tma_load_2d(sA, mA, &full_bar[stage], pc.row0 + tm * BM, kb * BK);
                     tma_load_2d(sA + 8192, mA, &full_bar[stage], pc.row0 + tm * BM + 64, kb * BK);
                 } else {
-                    // the tensor map spans the rows of the (possibly row-block compact) C matrix
-                    tma_load_2d(sA, mA, &full_bar[stage], kb * BK, tm * BM);
+                    // the tensor map spans the rows of the (possibly row-block compact / column-blocked) C matrix
+                    if (pc.blocked_dr > 0) {
+                        const int qb = (kb * BK) / pc.blocked_dr;
+                        tma_load_2d(sA, mA, &full_bar[stage], kb * BK - qb * pc.blocked_dr, qb * pc.blocked_dr + tm * BM);
+                    } else {
+                        tma_load_2d(sA, mA, &full_bar[stage], kb * BK, tm * BM);
+                    }
                 }
                 if (b_mn) {
                     for (int c = 0; c < p.bn / 64; ++c) tma_load_2d(sB + c * 8192, mB, &full_bar[stage], tn * p.bn + c * 64, kb * BK);
@@ -322,7 +333,7 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             int pass, tm, tn, kb0, kb1;
             decode_work(p, w, pass, tm, tn, kb0, kb1);
             const bool a_mn = p.pass[pass].a_mn != 0;
-            const uint32_t idesc = make_idesc_f16(BM, p.bn, a_mn ? 1 : 0, b_mn ? 1 : 0, p.mode == 0 ? 1 : 0);   // CORR: bf16, GRAD: fp16
+            const uint32_t idesc = make_idesc_f16(BM, p.bn, a_mn ? 1 : 0, b_mn ? 1 : 0, p.ab_format);
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * kAccCols;
@@ -363,8 +374,9 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const bool row_ok = row < pc.row_end;
             if (p.mode == 0) {
                 // ---- CORR: v = S - N mu_i mu'_j;  c = v (r_i / N) r'_j   (batch-norm as a rank-1 correction)
-                const float nmu = row_ok ? pc.row_nmu[row] : 0.f;
-                const float rho = row_ok ? pc.row_rho[row] : 0.f;
+                const bool raw = pc.row_nmu != nullptr;      // raw bf16 operands: apply batch-norm here; else operands are standardised
+                const float nmu = (raw && row_ok) ? pc.row_nmu[row] : 0.f;
+                const float rho = (raw && row_ok) ? pc.row_rho[row] : pc.inv_n;
                 float l2 = 0.f, l1 = 0.f;
                 const int nchunks = p.bn / 32;
                 for (int ch = hf; ch < nchunks; ch += 2) {
@@ -376,8 +388,11 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         uint32_t packed[16];
 #pragma unroll
                         for (int t4 = 0; t4 < 8; ++t4) {
-                            const float4 m4 = __ldg(reinterpret_cast<const float4*>(pc.col_mu + j0) + t4);
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(pc.col_r + j0) + t4);
+                            float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                            if (raw) {
+                                m4 = __ldg(reinterpret_cast<const float4*>(pc.col_mu + j0) + t4);
+                                b4 = __ldg(reinterpret_cast<const float4*>(pc.col_r + j0) + t4);
+                            }
                             const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
                             float cc[4];
 #pragma unroll
@@ -394,7 +409,12 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             packed[t4 * 2 + 1] = pack_f16x2(cc[2], cc[3]);
                         }
                         if (p.write_c) {
-                            uint4* dst = reinterpret_cast<uint4*>(pc.c_out + (size_t)lrow * D + j0);
+                            size_t coff = (size_t)lrow * D + j0;
+                            if (pc.blocked_dr > 0) {
+                                const int qb = j0 / pc.blocked_dr;
+                                coff = ((size_t)qb * pc.blocked_dr + lrow) * pc.blocked_dr + (j0 - qb * pc.blocked_dr);
+                            }
+                            uint4* dst = reinterpret_cast<uint4*>(pc.c_out + coff);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) dst[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
                         }
@@ -720,13 +740,13 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         UmmaParams p{};
         p.dc = g_desc;
         p.mode = 0; p.D = D; p.N = N;
-        p.bn = 256;
+        p.bn = 256; p.ab_format = 1;
         p.tiles_m = row_tiles; p.tiles_n = (D + p.bn - 1) / p.bn; p.splits = 1;
         p.kblocks = (N + BK - 1) / BK;
         p.hsic = a.hsic; p.write_c = need != 0;
         p.loss_acc = loss_acc;
-        p.pass[0] = PassCfg{1, R0, R0 + RC, stats + S_NMU1 * D, stats + S_RHO1 * D, stats + S_MU2 * D, stats + S_R2 * D, 1, C1, nullptr, 0};
-        p.pass[1] = PassCfg{1, R0, R0 + RC, stats + S_NMU2 * D, stats + S_RHO2 * D, stats + S_MU1 * D, stats + S_R1 * D, 0, C2, nullptr, 0};
+        p.pass[0] = PassCfg{1, R0, R0 + RC, stats + S_NMU1 * D, stats + S_RHO1 * D, stats + S_MU2 * D, stats + S_R2 * D, 1, C1, nullptr, 0, 0, 0.f};
+        p.pass[1] = PassCfg{1, R0, R0 + RC, stats + S_NMU2 * D, stats + S_RHO2 * D, stats + S_MU1 * D, stats + S_R1 * D, 0, C2, nullptr, 0, 0, 0.f};
         // the transposed block is only needed for dz2
         p.pass_count = (a.rows_mode && (need & 2)) ? 2 : 1;
         launch_umma(m1, m2, m2, m1, p, stream);
@@ -746,11 +766,11 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         if (int rc = make_map_16(&mZ1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh1, N, D, 64, bn)) return rc;
         UmmaParams p{};
         p.dc = g_desc;
-        p.mode = 1; p.D = D; p.N = N; p.bn = bn;
+        p.mode = 1; p.D = D; p.N = N; p.bn = bn; p.ab_format = 0;
         p.tiles_m = row_tiles; p.tiles_n = (N + bn - 1) / bn;
         p.kblocks = (D + BK - 1) / BK;
-        const PassCfg pass_dz1{0, R0, R0 + RC, nullptr, nullptr, nullptr, nullptr, 0, nullptr, g1, RC};
-        const PassCfg pass_dz2{a.rows_mode ? 0 : 1, R0, R0 + RC, nullptr, nullptr, nullptr, nullptr, 0, nullptr, g2, RC};
+        const PassCfg pass_dz1{0, R0, R0 + RC, nullptr, nullptr, nullptr, nullptr, 0, nullptr, g1, RC, 0, 0.f};
+        const PassCfg pass_dz2{a.rows_mode ? 0 : 1, R0, R0 + RC, nullptr, nullptr, nullptr, nullptr, 0, nullptr, g2, RC, 0, 0.f};
         p.pass_count = (need == 3) ? 2 : 1;
         const CUtensorMap *a0, *b0, *a1, *b1;
         if (need & 1) { p.pass[0] = pass_dz1; a0 = &mCk; b0 = &mZ2; p.pass[1] = pass_dz2; a1 = &mCt; b1 = &mZ1; }

@@ -78,4 +78,5 @@ def test_product_package_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in src.replace("oracle for", "").replace("the oracle", "").replace("Parity oracle", ""), f
+                # no import / attribute use / path of the checker anywhere in the product (prose mentions are fine)
+                assert not re.search(r"(^|\n)\s*(from|import)\s+oracle\b|\boracle\.\w|oracle/|import_module\([^)]*oracle", src), f
