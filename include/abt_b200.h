@@ -81,6 +81,20 @@ int abt_logmel_crop_fwd(const abt_logmel_plan* plan, const float* wav, int64_t w
                         int n_samples, const int32_t* frame_start, int n_frames, float* out_base, const int32_t* out_slot,
                         int64_t out_slot_stride, abt_stream_t stream);
 
+/* Crop-first input staging for HOST waveforms (the reference loads the whole clip in a DataLoader worker, datasets.py:98-116,
+ * and ships it to the GPU at main.py:69).  Only the samples the cropped frames need -- abt_wav_span_len() per clip, e.g. 16 228
+ * of 160 000 for a 96-frame crop of a 10 s clip -- are read.  With wav_on_host != 0, `wav` is a [host] pointer into MAPPED PINNED
+ * memory and the kernel reads it in place over PCIe (no staging copy of the whole clip); otherwise it is a device pointer.
+ * spans: (n_clips, span_len) fp32 device; span_origin: (n_clips) int32 device, first clip sample held by each span row.
+ * Requires n_samples >= span_len.  abt_logmel_span_fwd is abt_logmel_crop_fwd reading those spans; it gives bit-identical
+ * results (reflect padding is resolved in clip coordinates, and a span always contains the mirrored samples). */
+int abt_wav_span_len(const abt_logmel_plan* plan, int n_frames, int* span_len);
+int abt_wav_span_gather(const abt_logmel_plan* plan, const float* wav, int wav_on_host, int64_t wav_row_stride, int n_clips, int n_samples,
+                        const int32_t* frame_start, int n_frames, float* spans, int32_t* span_origin, abt_stream_t stream);
+int abt_logmel_span_fwd(const abt_logmel_plan* plan, const float* spans, const int32_t* span_origin, int n_clips, int n_samples,
+                        const int32_t* frame_start, int n_frames, float* out_base, const int32_t* out_slot, int64_t out_slot_stride,
+                        abt_stream_t stream);
+
 /* Crop / right-pad a precomputed log-mel and z-score it: datasets.py:342-354.
  * lms (n_clips, n_mels, t_full) -> out slots as above, (n_mels, n_frames) each. */
 int abt_lms_crop_norm(const float* lms, int n_clips, int n_mels, int t_full, const int32_t* frame_start, int n_frames, int apply_norm,
@@ -236,9 +250,9 @@ int abt_bt_loss_rows_fwd_bwd(const abt_bt_rows_args* args, abt_stream_t stream);
 int abt_debug_set(int key, int value);
 /* number of kernels the library has launched (optionally resetting the counter) */
 long long abt_debug_launch_count(int reset);
-/* device timing of the two tensor-core launches of abt_bt_loss_fwd_bwd (CUDA events on the launching stream) */
+/* device timing of the statistics, CORR and GRAD launches of abt_bt_loss_fwd_bwd (CUDA events on the launching stream) */
 int abt_debug_timing(int enable);
-int abt_debug_timing_read(float* corr_ms, float* grad_ms, int* n_calls);
+int abt_debug_timing_read(float* stats_ms, float* corr_ms, float* grad_ms, int* n_calls);
 int abt_debug_ws_offsets(int n_rows, int n_dims, int dtype, size_t* out8);
 
 #ifdef __cplusplus

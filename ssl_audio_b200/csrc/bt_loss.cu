@@ -8,17 +8,24 @@
 //   G  = dL/dC,  dL/dzh1 = zh2 G^T / N,  dL/dzh2 = zh1 G / N,  then batch-norm backward.
 //
 // The D x D matrix is never materialised in fp32.  Four launches:
-//   1. bt_stats_kernel     column statistics of both views, fp32 diagonal C_ii and on-diagonal loss,
-//                          BatchNorm running-stat update, bf16 copies of non-bf16 inputs and the
-//                          fp16 standardised embeddings zh used by the gradient GEMMs
-//   2. bt_umma_kernel CORR S = z1^T z2 on the tensor cores (tcgen05, RAW bf16 operands straight
-//                          from the row-major embeddings as MN-major TMA tiles, fp32 TMEM
-//                          accumulator); epilogue applies batch-norm as a rank-1 correction,
-//                          reduces the off-diagonal loss in fp32 and emits C (|C_ij| <= 1) in fp16
-//                          with the diagonal zeroed
-//   3. bt_umma_kernel GRAD g1^T = C zh2^T (K-major A) and g2^T = C^T zh1^T (MN-major A over the
-//                          same C), fp32 out: 6 N D^2 executed FLOP = the algorithmic count
-//   4. bt_finalize_kernel  adds the fp32 diagonal term, batch-norm backward, output cast, loss.
+//   1. bt_colstat_kernel   partial column sums of both views (shifted data), grid = column blocks x row chunks
+//   2. bt_normalize_kernel column statistics, fp32 diagonal C_ii and on-diagonal loss, BatchNorm running-stat
+//                          update, and the fp16 standardised embeddings zh (operand B of the gradient GEMMs)
+//   3. bt_umma_kernel CORR S = z1^T z2 on the tensor cores (tcgen05, RAW bf16 operands straight from the
+//                          row-major embeddings as MN-major TMA tiles, fp32 TMEM accumulator); the epilogue
+//                          applies batch-norm as a rank-1 correction, reduces the off-diagonal loss in fp32,
+//                          emits C (|C_ij| <= 1) in fp16 with the diagonal zeroed, and accumulates the row and
+//                          column sums of C o C (warp transpose-reduce for the columns)
+//   4. bt_umma_kernel GRAD g1^T = C zh2^T (K-major A) and g2^T = C^T zh1^T (MN-major A over the same C);
+//                          the epilogue adds the fp32 diagonal term and applies batch-norm backward straight
+//                          out of TMEM, writing dz in the caller's dtype: 6 N D^2 executed FLOP = the
+//                          algorithmic count, no fp32 gradient round trip through HBM.
+//
+// Batch-norm backward, dz = r (g - mean_n(g) - zh mean_n(g o zh)), needs two column means.  Both have closed
+// forms in C: mean_n(g) = 0 (columns of zh have zero mean), and
+//   mean_n(g1 o zh1)_i = (2 lambda / N) sum_{j != i} C_ij (C_ij + h) + (G_ii / N) C_ii
+// (g2: the same with column sums), which is why the CORR epilogue keeps the row / column sums of C o C (and of
+// C when HSIC) and no pass over the gradients is needed before they are written.
 //
 // Row-block mode (multi-GPU, abt_bt_loss_rows_fwd_bwd): the inputs are the rank-ordered gathered
 // embeddings (N_g x D); this rank owns dimensions [row_begin, row_begin + row_count) and computes
@@ -40,6 +47,14 @@ enum StatSlot {
     S_NMU1, S_RHO1,   // -N * mu1, r1 / N : row constants of the rank-1 batch-norm correction (rows = view-1 dims)
     S_NMU2, S_RHO2,   // same with the views swapped (row-block mode, C^T pass)
     S_COUNT
+};
+// accumulators zeroed at the start of every call (float arrays of length D each, after the 256-byte misc block)
+enum AccSlot {
+    A_SQ1 = 0,   // sum_{j != i} C_ij^2 over row i of C          (-> batch-norm backward of dz1)
+    A_SQ2,       // sum_{i != j} C_ij^2 over column j of C       (-> dz2)
+    A_SUM1,      // HSIC: sum_{j != i} C_ij
+    A_SUM2,
+    A_COUNT
 };
 
 template <typename T> struct Ld2;
@@ -63,48 +78,39 @@ template <> struct Ld2<float> {
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 constexpr int kColsPerBlock = 64;   // 32 lanes x 2 columns
-constexpr int kRowGroups = 32;      // 1024 threads: enough loads in flight to stream N x 64-column slabs at HBM/L2 speed
+constexpr int kRowGroups = 8;       // 256 threads per block; the grid's second dimension splits the rows
 constexpr int kColThreads = kRowGroups * 32;
+constexpr int kMaxRowSplits = 8;
 
 // ------------------------------------------------------------------------------------------
-// 1. statistics
+// 1. partial column sums: block (cb, rs) handles 64 columns x rows [rs * chunk, (rs + 1) * chunk)
+//    partials[(rs * 5 + k) * D + col], k = sum da, sum da^2, sum db, sum db^2, sum da db  (da = z1 - z1[0], shifted data)
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kColThreads) bt_stats_kernel(const T* __restrict__ z1, const T* __restrict__ z2, int N, int D, float eps,
-                                                               float momentum, float* __restrict__ stats, __nv_bfloat16* __restrict__ zb1,
-                                                               __nv_bfloat16* __restrict__ zb2, __half* __restrict__ zh1,
-                                                               __half* __restrict__ zh2, float* __restrict__ running_mean,
-                                                               float* __restrict__ running_var, double* __restrict__ loss_acc) {
+__global__ void __launch_bounds__(kColThreads) bt_colstat_kernel(const T* __restrict__ z1, const T* __restrict__ z2, int N, int D, int chunk,
+                                                                 float* __restrict__ partials, __nv_bfloat16* __restrict__ zb1,
+                                                                 __nv_bfloat16* __restrict__ zb2) {
     __shared__ float red[kRowGroups][5][kColsPerBlock];
-    __shared__ float shift[2][kColsPerBlock];
-    __shared__ float colstat[4][kColsPerBlock];   // mu1, r1, mu2, r2 of this block's columns
-    __shared__ float on_red[2];
     const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const int col = blockIdx.x * kColsPerBlock + lane * 2;
+    const int n0 = blockIdx.y * chunk, n1 = min(N, n0 + chunk);
     float s1[2] = {0, 0}, q1[2] = {0, 0}, s2[2] = {0, 0}, q2[2] = {0, 0}, x12[2] = {0, 0};
-    float k1[2] = {0, 0}, k2[2] = {0, 0};
-    const bool ok = col < D;
-    if (ok) {
+    if (col < D) {
         // shifted-data sums: subtract row 0 so that |mu| >> sigma does not cancel in fp32
-        float2 a = Ld2<T>::ld(z1 + col), b = Ld2<T>::ld(z2 + col);
-        k1[0] = bf16_round(a.x); k1[1] = bf16_round(a.y);
-        k2[0] = bf16_round(b.x); k2[1] = bf16_round(b.y);
-        if (rg == 0) {
-            shift[0][lane * 2] = k1[0]; shift[0][lane * 2 + 1] = k1[1];
-            shift[1][lane * 2] = k2[0]; shift[1][lane * 2 + 1] = k2[1];
-        }
+        const float2 a = Ld2<T>::ld(z1 + col), b = Ld2<T>::ld(z2 + col);
+        const float k1[2] = {bf16_round(a.x), bf16_round(a.y)}, k2[2] = {bf16_round(b.x), bf16_round(b.y)};
 #pragma unroll 4
-        for (int n = rg; n < N; n += kRowGroups) {
-            float2 a2 = Ld2<T>::ld(z1 + (size_t)n * D + col), b2 = Ld2<T>::ld(z2 + (size_t)n * D + col);
+        for (int n = n0 + rg; n < n1; n += kRowGroups) {
+            const float2 a2 = Ld2<T>::ld(z1 + (size_t)n * D + col), b2 = Ld2<T>::ld(z2 + (size_t)n * D + col);
             // the tensor cores consume bf16: statistics are those of the bf16-rounded embeddings
-            float av[2] = {bf16_round(a2.x), bf16_round(a2.y)}, bv[2] = {bf16_round(b2.x), bf16_round(b2.y)};
+            const float av[2] = {bf16_round(a2.x), bf16_round(a2.y)}, bv[2] = {bf16_round(b2.x), bf16_round(b2.y)};
             if (zb1 != nullptr) {
                 Ld2<__nv_bfloat16>::st(zb1 + (size_t)n * D + col, av[0], av[1]);
                 Ld2<__nv_bfloat16>::st(zb2 + (size_t)n * D + col, bv[0], bv[1]);
             }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                float da = av[c] - k1[c], db = bv[c] - k2[c];
+                const float da = av[c] - k1[c], db = bv[c] - k2[c];
                 s1[c] += da; q1[c] = fmaf(da, da, q1[c]);
                 s2[c] += db; q2[c] = fmaf(db, db, q2[c]);
                 x12[c] = fmaf(da, db, x12[c]);
@@ -118,53 +124,81 @@ __global__ void __launch_bounds__(kColThreads) bt_stats_kernel(const T* __restri
         red[rg][4][lane * 2 + c] = x12[c];
     }
     __syncthreads();
+    for (int i = threadIdx.x; i < 5 * kColsPerBlock; i += kColThreads) {
+        const int k = i / kColsPerBlock, c = i % kColsPerBlock, gc = blockIdx.x * kColsPerBlock + c;
+        if (gc < D) {
+            float t = 0.f;
+#pragma unroll
+            for (int g = 0; g < kRowGroups; ++g) t += red[g][k][c];
+            partials[((size_t)blockIdx.y * 5 + k) * D + gc] = t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2. statistics from the partial sums (fixed summation order: deterministic), then the standardised fp16 embeddings
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kColThreads) bt_normalize_kernel(const T* __restrict__ z1, const T* __restrict__ z2, int N, int D, int chunk,
+                                                                   int n_splits, float eps, float momentum, const float* __restrict__ partials,
+                                                                   float* __restrict__ stats, __half* __restrict__ zh1, __half* __restrict__ zh2,
+                                                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                                   double* __restrict__ loss_acc) {
+    __shared__ float colstat[4][kColsPerBlock];   // mu1, r1, mu2, r2 of this block's columns
+    __shared__ float on_red[2];
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int col = blockIdx.x * kColsPerBlock + lane * 2;
     float on = 0.f;
     if (threadIdx.x < kColsPerBlock) {
         const int c = threadIdx.x, gc = blockIdx.x * kColsPerBlock + c;
         if (gc < D) {
             float t[5] = {0, 0, 0, 0, 0};
+            for (int s = 0; s < n_splits; ++s)
 #pragma unroll
-            for (int g = 0; g < kRowGroups; ++g)
-#pragma unroll
-                for (int k = 0; k < 5; ++k) t[k] += red[g][k][c];
+                for (int k = 0; k < 5; ++k) t[k] += partials[((size_t)s * 5 + k) * D + gc];
             const float invN = 1.0f / (float)N;
-            const float kk1 = shift[0][c], kk2 = shift[1][c];
+            const float kk1 = bf16_round(Ld2<T>::ld(z1 + (gc & ~1)).x), kk1b = bf16_round(Ld2<T>::ld(z1 + (gc & ~1)).y);
+            const float kk2 = bf16_round(Ld2<T>::ld(z2 + (gc & ~1)).x), kk2b = bf16_round(Ld2<T>::ld(z2 + (gc & ~1)).y);
+            const float sh1 = (gc & 1) ? kk1b : kk1, sh2 = (gc & 1) ? kk2b : kk2;
             const float m1 = t[0] * invN, m2 = t[2] * invN;
             const float var1 = fmaxf(t[1] * invN - m1 * m1, 0.f), var2 = fmaxf(t[3] * invN - m2 * m2, 0.f);
             const float cov = t[4] * invN - m1 * m2;
-            const float mu1 = kk1 + m1, mu2 = kk2 + m2;
+            const float mu1 = sh1 + m1, mu2 = sh2 + m2;
             const float r1 = rsqrtf(var1 + eps), r2 = rsqrtf(var2 + eps);
             // one Newton step: rsqrtf is ~2 ulp, BatchNorm uses a correctly rounded 1/sqrt
             const float r1n = r1 * (1.5f - 0.5f * (var1 + eps) * r1 * r1), r2n = r2 * (1.5f - 0.5f * (var2 + eps) * r2 * r2);
             const float cd = cov * r1n * r2n;
-            stats[S_MU1 * D + gc] = mu1; stats[S_R1 * D + gc] = r1n;
-            stats[S_MU2 * D + gc] = mu2; stats[S_R2 * D + gc] = r2n;
-            stats[S_CDIAG * D + gc] = cd;
-            stats[S_NMU1 * D + gc] = -(float)N * mu1; stats[S_RHO1 * D + gc] = r1n * invN;
-            stats[S_NMU2 * D + gc] = -(float)N * mu2; stats[S_RHO2 * D + gc] = r2n * invN;
             colstat[0][c] = mu1; colstat[1][c] = r1n; colstat[2][c] = mu2; colstat[3][c] = r2n;
-            on = (cd - 1.0f) * (cd - 1.0f);
-            if (running_mean != nullptr) {
-                // BatchNorm1d training-mode side effect, view 1 then view 2 (utils/loss.py:17)
-                const float unb = (N > 1) ? (float)N / (float)(N - 1) : 1.0f;
-                float rm = running_mean[gc], rv = running_var[gc];
-                rm = (1.f - momentum) * rm + momentum * mu1; rv = (1.f - momentum) * rv + momentum * var1 * unb;
-                rm = (1.f - momentum) * rm + momentum * mu2; rv = (1.f - momentum) * rv + momentum * var2 * unb;
-                running_mean[gc] = rm; running_var[gc] = rv;
+            if (blockIdx.y == 0) {
+                stats[S_MU1 * D + gc] = mu1; stats[S_R1 * D + gc] = r1n;
+                stats[S_MU2 * D + gc] = mu2; stats[S_R2 * D + gc] = r2n;
+                stats[S_CDIAG * D + gc] = cd;
+                stats[S_NMU1 * D + gc] = -(float)N * mu1; stats[S_RHO1 * D + gc] = r1n * invN;
+                stats[S_NMU2 * D + gc] = -(float)N * mu2; stats[S_RHO2 * D + gc] = r2n * invN;
+                on = (cd - 1.0f) * (cd - 1.0f);
+                if (running_mean != nullptr) {
+                    // BatchNorm1d training-mode side effect, view 1 then view 2 (utils/loss.py:17)
+                    const float unb = (N > 1) ? (float)N / (float)(N - 1) : 1.0f;
+                    float rm = running_mean[gc], rv = running_var[gc];
+                    rm = (1.f - momentum) * rm + momentum * mu1; rv = (1.f - momentum) * rv + momentum * var1 * unb;
+                    rm = (1.f - momentum) * rm + momentum * mu2; rv = (1.f - momentum) * rv + momentum * var2 * unb;
+                    running_mean[gc] = rm; running_var[gc] = rv;
+                }
             }
         }
-        // on-diagonal loss sum_i (C_ii - 1)^2: one double atomic per block
+        // on-diagonal loss sum_i (C_ii - 1)^2: one double atomic per column block
         on = warp_sum(on);
         if (lane == 0) on_red[threadIdx.x >> 5] = on;
     }
     __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(loss_acc + 2, (double)(on_red[0] + on_red[1]));
-    // second pass: standardised embeddings in fp16 (operand B of the gradient GEMMs; |zh| <= sqrt(N))
-    if (ok && zh1 != nullptr) {
+    if (threadIdx.x == 0 && blockIdx.y == 0) atomicAdd(loss_acc + 2, (double)(on_red[0] + on_red[1]));
+    // standardised embeddings in fp16 (operand B of the gradient GEMMs; |zh| <= sqrt(N))
+    if (col < D && zh1 != nullptr) {
         const float m1[2] = {colstat[0][lane * 2], colstat[0][lane * 2 + 1]}, q1r[2] = {colstat[1][lane * 2], colstat[1][lane * 2 + 1]};
         const float m2[2] = {colstat[2][lane * 2], colstat[2][lane * 2 + 1]}, q2r[2] = {colstat[3][lane * 2], colstat[3][lane * 2 + 1]};
+        const int n0 = blockIdx.y * chunk, n1 = min(N, n0 + chunk);
 #pragma unroll 4
-        for (int n = rg; n < N; n += kRowGroups) {
+        for (int n = n0 + rg; n < n1; n += kRowGroups) {
             const size_t o = (size_t)n * D + col;
             const float2 a2 = Ld2<T>::ld(z1 + o), b2 = Ld2<T>::ld(z2 + o);
             Ld2<__half>::st(zh1 + o, (bf16_round(a2.x) - m1[0]) * q1r[0], (bf16_round(a2.y) - m1[1]) * q1r[1]);
@@ -191,7 +225,7 @@ __global__ void __launch_bounds__(256) bt_rowsum_kernel(const __nv_bfloat16* __r
 }
 
 // ------------------------------------------------------------------------------------------
-// 2./3. tcgen05 GEMM kernel (persistent, warp specialised)
+// 3./4. tcgen05 GEMM kernel (persistent, warp specialised)
 // ------------------------------------------------------------------------------------------
 constexpr int BM = 128;            // UMMA M (TMEM lanes)
 constexpr int BK = 64;             // K elements per pipeline stage (one 128-byte swizzle row)
@@ -200,7 +234,7 @@ constexpr int kABytes = BM * BK * 2;       // 16 KiB
 constexpr int kBBytesMax = 256 * BK * 2;   // 32 KiB
 constexpr int kStageBytes = kABytes + kBBytesMax;
 constexpr int kAccCols = 256;      // TMEM columns per accumulator stage
-constexpr int kNumThreads = 384;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
+constexpr int kNumThreads = 384;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 loss scalar, warps 4-11 epilogue
 constexpr int kEpiWarps = 8;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 
@@ -216,42 +250,120 @@ static DescCfg g_desc = {8192, 1024, 2048, 16, 1024, 32};
 struct PassCfg {
     int a_mn;                 // A operand: 1 = MN-major tiles (CORR: raw z columns; GRAD: C^T), 0 = K-major (GRAD: C rows)
     int row0, row_end;        // global dimension index of A-row 0 of the tile grid, and exclusive end of the valid rows
-    // CORR epilogue: c = (S + row_nmu[i] * col_mu[j]) * row_rho[i] * col_r[j]
+    // ---- CORR epilogue: c = (S + row_nmu[i] * col_mu[j]) * row_rho[i] * col_r[j]
     const float* row_nmu; const float* row_rho; const float* col_mu; const float* col_r;
     int accumulate_loss;
-    __half* c_out;            // CORR: row-major (rows local to row0) x D, fp16, diagonal zeroed
-    float* g_out;             // GRAD: g_out[n * ldg + (row - row0)]
-    int ldg;
-    // Column-blocked C (multi-GPU, Dr = D / world): element (local row i, column j) lives at ((j / Dr) * Dr + i) * Dr + j % Dr, so
-    // that block q = C[rows, q Dr : (q+1) Dr] is contiguous for the all-to-all.  CORR writes it, the K-major GRAD pass reads it
-    // through a (world * Dr) x Dr tensor map.  0 = plain row-major.
-    int blocked_dr;
-    float inv_n;              // CORR on standardised fp16 operands (row_nmu == nullptr): c = S * inv_n
+    __half* c_out;            // row-major (rows local to row0) x D, fp16, diagonal zeroed
+    float* row_sq;            // += sum_j c_ij^2 (j != i), indexed by the global row; may be null
+    float* row_sum;           // HSIC only: += sum_j c_ij
+    float* col_sq;            // += sum_i c_ij^2 (i != j), indexed by the global column; null when a second pass provides it
+    float* col_sum;           // HSIC only
+    // ---- GRAD epilogue (batch-norm backward out of TMEM): rows are dimensions of view `side`
+    int side;                 // 0: this pass produces dz1, 1: dz2
+    void* dz;                 // dz[n * ld_dz + (row - row0)], dtype UmmaParams::io_dtype
+    int ld_dz;
+    const float* sq;          // row_sq / col_sq accumulated by CORR for these rows (global row index)
+    const float* sm;          // HSIC: the matching sums of C
 };
 
 struct UmmaParams {
     DescCfg dc;
     int mode;          // 0 = CORR, 1 = GRAD
     int D, N;
-    int tiles_m, tiles_n, splits, kblocks;   // per pass
+    int tiles_m, tiles_n, kblocks;   // per pass
     int pass_count;
     int bn;            // UMMA N of this launch (multiple of 16, <= 256)
     int ab_format;     // operand type of this launch: 1 = bf16, 0 = fp16
     int hsic;
     int write_c;
     double* loss_acc;
+    // GRAD
+    int io_dtype;                      // abt_dtype of dz
+    const __nv_bfloat16* zq1;          // (N, D) bf16 embeddings (the inputs, or their bf16 copies)
+    const __nv_bfloat16* zq2;
+    const float* stats;                // StatSlot arrays
+    const float* rs1; const float* rs2;   // HSIC: row sums of zh1 / zh2 over all dimensions
+    float alpha, lambda, grad_scale;
+    float* loss_out;                   // written by the GRAD launch (single-GPU); may be null
     PassCfg pass[2];
 };
 
-__device__ __forceinline__ void decode_work(const UmmaParams& p, int w, int& pass, int& tm, int& tn, int& kb0, int& kb1) {
-    const int per_pass = p.tiles_m * p.tiles_n * p.splits;
+__device__ __forceinline__ void decode_work(const UmmaParams& p, int w, int& pass, int& tm, int& tn) {
+    const int per_pass = p.tiles_m * p.tiles_n;
     pass = w / per_pass;
-    int r = w % per_pass;
-    const int split = r % p.splits; r /= p.splits;
+    const int r = w % per_pass;
     tn = r % p.tiles_n; tm = r / p.tiles_n;
-    const int per = (p.kblocks + p.splits - 1) / p.splits;
-    kb0 = split * per;
-    kb1 = min(p.kblocks, kb0 + per);
+}
+
+__device__ __forceinline__ float loss_from_parts(const double* acc, float alpha, float lambda, int hsic, int D) {
+    double off = acc[0];
+    if (hsic) off = acc[0] + 2.0 * acc[1] + (double)D * (double)(D - 1);
+    return (float)((double)alpha * acc[2] + (double)lambda * off);
+}
+
+__global__ void bt_loss_scalar_kernel(const double* __restrict__ acc, float alpha, float lambda, int hsic, int D, float* __restrict__ loss_out) {
+    if (threadIdx.x == 0) *loss_out = loss_from_parts(acc, alpha, lambda, hsic, D);
+}
+
+// column sums over the 32 rows held by the lanes of a warp: on return lane l holds sum over lanes of v[l]
+// (butterfly reduce-scatter, 31 shuffles)
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int t = 0; t < s; ++t) {
+            const float send = up ? v[t] : v[t + s];
+            const float keep = up ? v[t + s] : v[t];
+            v[t] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+template <typename T> __device__ __forceinline__ void store_out(T* p, float v);
+template <> __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void store_out<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+template <> __device__ __forceinline__ void store_out<float>(float* p, float v) { *p = v; }
+
+// GRAD epilogue for one 32-sample chunk of one dimension (row): batch-norm backward and the fp32 diagonal term.
+//   d loss / d zh_self[n] = hs * acc[n] + gd * zh_other[n]  (+ HSIC: hs * (R_other[n] - zh_other[n]))
+//   dz_self[n] = r_self * (that - zh_self[n] * b) * grad_scale
+template <typename T>
+__device__ __forceinline__ void grad_chunk(const uint32_t (&acc)[32], const UmmaParams& p, const PassCfg& pc, int row, int lrow, int n_base, int n_valid,
+                                           float mu_s, float r_s, float mu_o, float r_o, float hs, float gd, float b) {
+    const __nv_bfloat16* zs = (pc.side == 0 ? p.zq1 : p.zq2) + row;
+    const __nv_bfloat16* zo = (pc.side == 0 ? p.zq2 : p.zq1) + row;
+    const float* rso = pc.side == 0 ? p.rs2 : p.rs1;
+    T* dz = static_cast<T*>(pc.dz) + lrow;
+    const float rg = r_s * p.grad_scale;
+    // 16 samples at a time, all loads first (the stores may alias as far as the compiler knows; keeping them
+    // behind the loads leaves 32+ requests in flight per thread instead of one)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        unsigned short zs_raw[16], zo_raw[16];
+        float rsv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int t = h * 16 + u;
+            const size_t n = (size_t)(n_base + (t < n_valid ? t : 0));
+            zs_raw[u] = __ldg(reinterpret_cast<const unsigned short*>(zs + n * p.D));
+            zo_raw[u] = __ldg(reinterpret_cast<const unsigned short*>(zo + n * p.D));
+            rsv[u] = p.hsic ? __ldg(rso + n) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int t = h * 16 + u;
+            if (t < n_valid) {
+                const size_t n = (size_t)(n_base + t);
+                const float zhs = (__uint_as_float((uint32_t)zs_raw[u] << 16) - mu_s) * r_s;
+                const float zho = (__uint_as_float((uint32_t)zo_raw[u] << 16) - mu_o) * r_o;
+                float g = fmaf(hs, __uint_as_float(acc[t]), gd * zho);
+                if (p.hsic) g = fmaf(hs, rsv[u] - zho, g);
+                store_out<T>(dz + n * pc.ld_dz, (g - zhs * b) * rg);
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -266,7 +378,7 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_work = p.tiles_m * p.tiles_n * p.splits * p.pass_count;
+    const int total_work = p.tiles_m * p.tiles_n * p.pass_count;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapB0);
@@ -293,13 +405,13 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // ================= TMA producer =================
         int stage = 0; uint32_t phase = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-            int pass, tm, tn, kb0, kb1;
-            decode_work(p, w, pass, tm, tn, kb0, kb1);
+            int pass, tm, tn;
+            decode_work(p, w, pass, tm, tn);
             const PassCfg& pc = p.pass[pass];
             const CUtensorMap* mA = pass == 1 ? &mapA1 : &mapA0;
             const CUtensorMap* mB = pass == 1 ? &mapB1 : &mapB0;
             const uint32_t tx = kABytes + (uint32_t)p.bn * BK * 2;
-            for (int kb = kb0; kb < kb1; ++kb) {
+            for (int kb = 0; kb < p.kblocks; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sA = smem + stage * kStageBytes;
                 uint8_t* sB = sA + kABytes;
@@ -309,13 +421,8 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     tma_load_2d(sA, mA, &full_bar[stage], pc.row0 + tm * BM, kb * BK);
                     tma_load_2d(sA + 8192, mA, &full_bar[stage], pc.row0 + tm * BM + 64, kb * BK);
                 } else {
-                    // the tensor map spans the rows of the (possibly row-block compact / column-blocked) C matrix
-                    if (pc.blocked_dr > 0) {
-                        const int qb = (kb * BK) / pc.blocked_dr;
-                        tma_load_2d(sA, mA, &full_bar[stage], kb * BK - qb * pc.blocked_dr, qb * pc.blocked_dr + tm * BM);
-                    } else {
-                        tma_load_2d(sA, mA, &full_bar[stage], kb * BK, tm * BM);
-                    }
+                    // the tensor map spans the rows of the (possibly row-block compact) C matrix
+                    tma_load_2d(sA, mA, &full_bar[stage], kb * BK, tm * BM);
                 }
                 if (b_mn) {
                     for (int c = 0; c < p.bn / 64; ++c) tma_load_2d(sB + c * 8192, mB, &full_bar[stage], tn * p.bn + c * 64, kb * BK);
@@ -330,14 +437,14 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-            int pass, tm, tn, kb0, kb1;
-            decode_work(p, w, pass, tm, tn, kb0, kb1);
+            int pass, tm, tn;
+            decode_work(p, w, pass, tm, tn);
             const bool a_mn = p.pass[pass].a_mn != 0;
             const uint32_t idesc = make_idesc_f16(BM, p.bn, a_mn ? 1 : 0, b_mn ? 1 : 0, p.ab_format);
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * kAccCols;
-            for (int kb = kb0; kb < kb1; ++kb) {
+            for (int kb = 0; kb < p.kblocks; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t sA = smem_u32(smem + stage * kStageBytes);
@@ -348,7 +455,7 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                              : make_smem_desc_sw128(sA + ks * p.dc.k_kstep, p.dc.k_lbo, p.dc.k_sbo);
                     const uint64_t db = b_mn ? make_smem_desc_sw128(sB + ks * p.dc.mn_kstep, p.dc.mn_lbo, p.dc.mn_sbo)
                                              : make_smem_desc_sw128(sB + ks * p.dc.k_kstep, p.dc.k_lbo, p.dc.k_sbo);
-                    umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+                    umma_bf16_ss(d_tmem, da, db, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[stage]);   // frees the smem stage when these MMAs retire
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -356,6 +463,9 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             umma_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+    } else if (warp == 3 && lane == 0) {
+        // the loss scalar is complete once CORR has run: the GRAD launch publishes it (single-GPU)
+        if (p.mode == 1 && blockIdx.x == 0 && p.loss_out != nullptr) *p.loss_out = loss_from_parts(p.loss_acc, p.alpha, p.lambda, p.hsic, p.D);
     } else if (warp >= 4) {
         // ================= epilogue: TMEM -> registers -> global =================
         const int q = warp & 3;              // TMEM lane quarter this warp may access
@@ -363,8 +473,8 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         int acc = 0; uint32_t acc_phase = 0;
         const int D = p.D;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-            int pass, tm, tn, kb0, kb1;
-            decode_work(p, w, pass, tm, tn, kb0, kb1);
+            int pass, tm, tn;
+            decode_work(p, w, pass, tm, tn);
             const PassCfg& pc = p.pass[pass];
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -374,51 +484,61 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const bool row_ok = row < pc.row_end;
             if (p.mode == 0) {
                 // ---- CORR: v = S - N mu_i mu'_j;  c = v (r_i / N) r'_j   (batch-norm as a rank-1 correction)
-                const bool raw = pc.row_nmu != nullptr;      // raw bf16 operands: apply batch-norm here; else operands are standardised
-                const float nmu = (raw && row_ok) ? pc.row_nmu[row] : 0.f;
-                const float rho = (raw && row_ok) ? pc.row_rho[row] : pc.inv_n;
+                const float nmu = row_ok ? pc.row_nmu[row] : 0.f;
+                const float rho = row_ok ? pc.row_rho[row] : 0.f;      // rows beyond the block give c = 0
                 float l2 = 0.f, l1 = 0.f;
                 const int nchunks = p.bn / 32;
                 for (int ch = hf; ch < nchunks; ch += 2) {
+                    const int j0 = tn * p.bn + ch * 32;
+                    if (j0 >= D) break;                                // warp-uniform
                     uint32_t r[32];
                     tmem_ld_32x32(t_addr + ch * 32, r);
                     tmem_ld_wait();
-                    const int j0 = tn * p.bn + ch * 32;
-                    if (j0 < D && row_ok) {
-                        uint32_t packed[16];
+                    uint32_t packed[16];
+                    float csq[32];
 #pragma unroll
-                        for (int t4 = 0; t4 < 8; ++t4) {
-                            float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = make_float4(1.f, 1.f, 1.f, 1.f);
-                            if (raw) {
-                                m4 = __ldg(reinterpret_cast<const float4*>(pc.col_mu + j0) + t4);
-                                b4 = __ldg(reinterpret_cast<const float4*>(pc.col_r + j0) + t4);
-                            }
-                            const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
-                            float cc[4];
+                    for (int t4 = 0; t4 < 8; ++t4) {
+                        const float4 m4 = __ldg(reinterpret_cast<const float4*>(pc.col_mu + j0) + t4);
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(pc.col_r + j0) + t4);
+                        const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                        float cc[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int t = t4 * 4 + u;
-                                const float v = fmaf(nmu, mm[u], __uint_as_float(r[t]));
-                                float c = (v * rho) * bb[u];
-                                c = (j0 + t == row) ? 0.f : c;      // diagonal handled in fp32 by the finalize kernel
-                                l2 = fmaf(c, c, l2);
-                                l1 += c;
-                                cc[u] = c;
-                            }
-                            packed[t4 * 2] = pack_f16x2(cc[0], cc[1]);
-                            packed[t4 * 2 + 1] = pack_f16x2(cc[2], cc[3]);
+                        for (int u = 0; u < 4; ++u) {
+                            const int t = t4 * 4 + u;
+                            const float v = fmaf(nmu, mm[u], __uint_as_float(r[t]));
+                            float c = (v * rho) * bb[u];
+                            c = (j0 + t == row) ? 0.f : c;      // the diagonal is handled in fp32 (cdiag from the statistics pass)
+                            csq[t] = c * c;
+                            l2 += csq[t];
+                            l1 += c;
+                            cc[u] = c;
                         }
-                        if (p.write_c) {
-                            size_t coff = (size_t)lrow * D + j0;
-                            if (pc.blocked_dr > 0) {
-                                const int qb = j0 / pc.blocked_dr;
-                                coff = ((size_t)qb * pc.blocked_dr + lrow) * pc.blocked_dr + (j0 - qb * pc.blocked_dr);
-                            }
-                            uint4* dst = reinterpret_cast<uint4*>(pc.c_out + coff);
+                        packed[t4 * 2] = pack_f16x2(cc[0], cc[1]);
+                        packed[t4 * 2 + 1] = pack_f16x2(cc[2], cc[3]);
+                    }
+                    if (p.write_c && row_ok) {
+                        uint4* dst = reinterpret_cast<uint4*>(pc.c_out + (size_t)lrow * D + j0);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) dst[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+                        for (int k = 0; k < 4; ++k) dst[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+                    }
+                    if (pc.col_sq != nullptr) {
+                        // column sums over this warp's 32 rows; lane l ends up with column j0 + l
+                        const float cs = warp_transpose_reduce(csq, lane);
+                        atomicAdd(pc.col_sq + j0 + lane, cs);
+                        if (p.hsic) {
+                            float cv[32];
+#pragma unroll
+                            for (int t = 0; t < 16; ++t) {
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&packed[t]));
+                                cv[2 * t] = f.x; cv[2 * t + 1] = f.y;
+                            }
+                            atomicAdd(pc.col_sum + j0 + lane, warp_transpose_reduce(cv, lane));
                         }
                     }
+                }
+                if (row_ok && pc.row_sq != nullptr) {
+                    atomicAdd(pc.row_sq + row, l2);
+                    if (p.hsic) atomicAdd(pc.row_sum + row, l1);
                 }
                 if (pc.accumulate_loss) {
                     l2 = warp_sum(l2);
@@ -429,24 +549,29 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                 }
             } else {
-                // ---- GRAD: fp32 accumulator (dimension row, sample n) -> g[n][row - row0]
-                float* g = pc.g_out;
+                // ---- GRAD: fp32 accumulator (dimension row, sample n) -> batch-norm backward -> dz[n][row - row0]
+                const int rr = row_ok ? row : pc.row0;
+                const float invN = 1.0f / (float)p.N;
+                const float mu1 = p.stats[S_MU1 * D + rr], r1 = p.stats[S_R1 * D + rr];
+                const float mu2 = p.stats[S_MU2 * D + rr], r2 = p.stats[S_R2 * D + rr];
+                const float cd = p.stats[S_CDIAG * D + rr];
+                const float hs = 2.0f * p.lambda * invN;
+                const float gd = 2.0f * p.alpha * (cd - 1.0f) * invN;        // G_ii / N
+                float b = fmaf(hs, pc.sq[rr], gd * cd);                        // mean_n(g o zh_self)
+                if (p.hsic) b = fmaf(hs, pc.sm[rr], b);
+                const float mu_s = pc.side == 0 ? mu1 : mu2, r_s = pc.side == 0 ? r1 : r2;
+                const float mu_o = pc.side == 0 ? mu2 : mu1, r_o = pc.side == 0 ? r2 : r1;
                 const int nchunks = (p.bn + 31) / 32;
                 for (int ch = hf; ch < nchunks; ch += 2) {
+                    const int n_base = tn * p.bn + ch * 32;
+                    if (n_base >= p.N) break;                                  // warp-uniform
                     uint32_t r[32];
                     tmem_ld_32x32(t_addr + ch * 32, r);
                     tmem_ld_wait();
-                    if (row_ok) {
-#pragma unroll
-                        for (int t = 0; t < 32; ++t) {
-                            const int n = tn * p.bn + ch * 32 + t;
-                            if (ch * 32 + t < p.bn && n < p.N) {
-                                float* dst = g + (size_t)n * pc.ldg + lrow;
-                                if (p.splits > 1) atomicAdd(dst, __uint_as_float(r[t]));
-                                else *dst = __uint_as_float(r[t]);
-                            }
-                        }
-                    }
+                    const int n_valid = row_ok ? min(32, min(p.bn - ch * 32, p.N - n_base)) : 0;
+                    if (p.io_dtype == ABT_DTYPE_BF16) grad_chunk<__nv_bfloat16>(r, p, pc, rr, lrow, n_base, n_valid, mu_s, r_s, mu_o, r_o, hs, gd, b);
+                    else if (p.io_dtype == ABT_DTYPE_F16) grad_chunk<__half>(r, p, pc, rr, lrow, n_base, n_valid, mu_s, r_s, mu_o, r_o, hs, gd, b);
+                    else grad_chunk<float>(r, p, pc, rr, lrow, n_base, n_valid, mu_s, r_s, mu_o, r_o, hs, gd, b);
                 }
             }
             tc_fence_before();
@@ -458,124 +583,6 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
-}
-
-// ------------------------------------------------------------------------------------------
-// 4. finalize: diagonal term (fp32), batch-norm backward, cast, loss scalar
-//    handles columns [col_begin, col_begin + col_count); g and dz are indexed with the local column and stride ld
-// ------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kColThreads) bt_finalize_kernel(const T* __restrict__ z1, const T* __restrict__ z2, int N, int D, int col_begin,
-                                                                  int col_count, int ld, float alpha, float lambda, int hsic, float grad_scale,
-                                                                  int need_mask, const float* __restrict__ stats, const float* __restrict__ g1,
-                                                                  const float* __restrict__ g2, const float* __restrict__ rowsum1,
-                                                                  const float* __restrict__ rowsum2, T* __restrict__ dz1, T* __restrict__ dz2,
-                                                                  double* __restrict__ loss_acc, unsigned int* __restrict__ counters,
-                                                                  float* __restrict__ loss_out) {
-    __shared__ float red[kRowGroups][4][kColsPerBlock];
-    __shared__ float mean_s[4][kColsPerBlock];
-    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    const int lcol = blockIdx.x * kColsPerBlock + lane * 2;     // local column (index into g / dz)
-    const int col = col_begin + lcol;                            // global dimension index (index into z / stats)
-    const bool ok = lcol < col_count;
-    const float invN = 1.0f / (float)N;
-    float mu1[2], r1[2], mu2[2], r2[2], gd[2];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const int gc = ok ? col + c : 0;
-        mu1[c] = stats[S_MU1 * D + gc]; r1[c] = stats[S_R1 * D + gc];
-        mu2[c] = stats[S_MU2 * D + gc]; r2[c] = stats[S_R2 * D + gc];
-        gd[c] = 2.0f * alpha * (stats[S_CDIAG * D + gc] - 1.0f) * invN;   // G_ii / N
-    }
-    const float hs = 2.0f * lambda * invN;
-
-    // d loss / d zh1[n,i] = (2 lambda/N) sum_{j != i} C_ij zh2[n,j]  +  (G_ii/N) zh2[n,i]
-    //                       (+ HSIC: (2 lambda/N)(R2[n] - zh2[n,i]), the "+1" of every off-diagonal G_ij)
-    auto side_grad = [&](int c, float zh_other, float graw, float rs_other) -> float {
-        float g = hs * graw + gd[c] * zh_other;
-        if (hsic) g += hs * (rs_other - zh_other);
-        return g;
-    };
-
-    if (need_mask != 0) {
-        float a1[2] = {0, 0}, b1[2] = {0, 0}, a2[2] = {0, 0}, b2[2] = {0, 0};
-        if (ok) {
-#pragma unroll 2
-            for (int n = rg; n < N; n += kRowGroups) {
-                const size_t oz = (size_t)n * D + col, og = (size_t)n * ld + lcol;
-                const float2 za = Ld2<T>::ld(z1 + oz), zb = Ld2<T>::ld(z2 + oz);
-                const float zav[2] = {bf16_round(za.x), bf16_round(za.y)}, zbv[2] = {bf16_round(zb.x), bf16_round(zb.y)};
-                float2 ga = make_float2(0, 0), gb = make_float2(0, 0);
-                if (need_mask & 1) ga = *reinterpret_cast<const float2*>(g1 + og);
-                if (need_mask & 2) gb = *reinterpret_cast<const float2*>(g2 + og);
-                const float gav[2] = {ga.x, ga.y}, gbv[2] = {gb.x, gb.y};
-                const float rs1 = hsic ? rowsum1[n] : 0.f, rs2 = hsic ? rowsum2[n] : 0.f;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const float zh1 = (zav[c] - mu1[c]) * r1[c], zh2 = (zbv[c] - mu2[c]) * r2[c];
-                    const float gf1 = side_grad(c, zh2, gav[c], rs2);
-                    const float gf2 = side_grad(c, zh1, gbv[c], rs1);
-                    a1[c] += gf1; b1[c] = fmaf(gf1, zh1, b1[c]);
-                    a2[c] += gf2; b2[c] = fmaf(gf2, zh2, b2[c]);
-                }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            red[rg][0][lane * 2 + c] = a1[c]; red[rg][1][lane * 2 + c] = b1[c];
-            red[rg][2][lane * 2 + c] = a2[c]; red[rg][3][lane * 2 + c] = b2[c];
-        }
-        __syncthreads();
-        if (threadIdx.x < kColsPerBlock) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float t = 0.f;
-#pragma unroll
-                for (int g = 0; g < kRowGroups; ++g) t += red[g][k][threadIdx.x];
-                mean_s[k][threadIdx.x] = t * invN;
-            }
-        }
-        __syncthreads();
-        if (ok) {
-#pragma unroll 2
-            for (int n = rg; n < N; n += kRowGroups) {
-                const size_t oz = (size_t)n * D + col, og = (size_t)n * ld + lcol;
-                const float2 za = Ld2<T>::ld(z1 + oz), zb = Ld2<T>::ld(z2 + oz);
-                const float zav[2] = {bf16_round(za.x), bf16_round(za.y)}, zbv[2] = {bf16_round(zb.x), bf16_round(zb.y)};
-                float2 ga = make_float2(0, 0), gb = make_float2(0, 0);
-                if (need_mask & 1) ga = *reinterpret_cast<const float2*>(g1 + og);
-                if (need_mask & 2) gb = *reinterpret_cast<const float2*>(g2 + og);
-                const float gav[2] = {ga.x, ga.y}, gbv[2] = {gb.x, gb.y};
-                const float rs1 = hsic ? rowsum1[n] : 0.f, rs2 = hsic ? rowsum2[n] : 0.f;
-                float o1[2], o2[2];
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const float zh1 = (zav[c] - mu1[c]) * r1[c], zh2 = (zbv[c] - mu2[c]) * r2[c];
-                    const float gf1 = side_grad(c, zh2, gav[c], rs2);
-                    const float gf2 = side_grad(c, zh1, gbv[c], rs1);
-                    const int cc = lane * 2 + c;
-                    o1[c] = r1[c] * (gf1 - mean_s[0][cc] - zh1 * mean_s[1][cc]) * grad_scale;
-                    o2[c] = r2[c] * (gf2 - mean_s[2][cc] - zh2 * mean_s[3][cc]) * grad_scale;
-                }
-                if (need_mask & 1) Ld2<T>::st(dz1 + og, o1[0], o1[1]);
-                if (need_mask & 2) Ld2<T>::st(dz2 + og, o2[0], o2[1]);
-            }
-        }
-    }
-    // single-GPU: the last block folds the three partial sums into the loss scalar
-    if (loss_out != nullptr && threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int done = atomicAdd(counters, 1u);
-        if (done == gridDim.x - 1) {
-            __threadfence();
-            const double off2 = *((volatile double*)(loss_acc + 0));
-            const double off1 = *((volatile double*)(loss_acc + 1));
-            const double ond = *((volatile double*)(loss_acc + 2));
-            double off = off2;
-            if (hsic) off = off2 + 2.0 * off1 + (double)D * (double)(D - 1);
-            *loss_out = (float)((double)alpha * ond + (double)lambda * off);
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -614,13 +621,13 @@ static int make_map_16(CUtensorMap* map, CUtensorMapDataType dt, const void* bas
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Optional per-call device timing of the two tensor-core launches (bench.py roofline): events are recorded on
-// the launching stream around CORR and GRAD of every loss call while enabled.
+// Optional per-call device timing of the launches (bench.py roofline): events are recorded on the launching
+// stream at the start of the call, before CORR, after CORR and after GRAD of every loss call while enabled.
 constexpr int kTimingRing = 512;
 struct TimingState {
     bool enabled = false;
     int count = 0;
-    cudaEvent_t ev[kTimingRing][3];
+    cudaEvent_t ev[kTimingRing][4];
     bool created = false;
 };
 static TimingState g_timing;
@@ -628,18 +635,20 @@ static TimingState g_timing;
 // Workspace layout.  `rows` = number of C rows this call materialises (D single-GPU, row_count in row-block mode);
 // `two_c` = a second C block for the transposed pass (row-block mode).
 struct WsLayout {
-    size_t misc, stats, rs1, rs2, g1, g2, zb1, zb2, zh1, zh2, c1, c2, total;
+    size_t misc, acc, stats, partials, rs1, rs2, zb1, zb2, zh1, zh2, c1, c2, total;
+    size_t zero_bytes;   // misc + acc: cleared at the start of every call
 };
 
 static WsLayout ws_layout(int N, int D, int rows, int dtype, bool two_c) {
     WsLayout L{};
     size_t off = 0;
     L.misc = off; off += 256;
+    L.acc = off; off = align_up(off + sizeof(float) * A_COUNT * (size_t)D, 256);
+    L.zero_bytes = off;
     L.stats = off; off = align_up(off + sizeof(float) * S_COUNT * (size_t)D, 256);
+    L.partials = off; off = align_up(off + sizeof(float) * 5 * kMaxRowSplits * (size_t)D, 256);
     L.rs1 = off; off = align_up(off + sizeof(float) * (size_t)N, 256);
     L.rs2 = off; off = align_up(off + sizeof(float) * (size_t)N, 256);
-    L.g1 = off; off = align_up(off + sizeof(float) * (size_t)N * rows, 256);
-    L.g2 = off; off = align_up(off + sizeof(float) * (size_t)N * rows, 256);
     L.zb1 = off; if (dtype != ABT_DTYPE_BF16) off = align_up(off + 2 * (size_t)N * D, 256);
     L.zb2 = off; if (dtype != ABT_DTYPE_BF16) off = align_up(off + 2 * (size_t)N * D, 256);
     L.zh1 = off; off = align_up(off + 2 * (size_t)N * D, 256);
@@ -673,7 +682,7 @@ static int ensure_umma_attr() {
 
 static void launch_umma(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1, const UmmaParams& p,
                         cudaStream_t stream) {
-    const int total = p.tiles_m * p.tiles_n * p.splits * p.pass_count;
+    const int total = p.tiles_m * p.tiles_n * p.pass_count;
     const int grid = total < num_sms() ? total : num_sms();
     bt_umma_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(a0, b0, a1, b1, p);
     count_launch();
@@ -698,10 +707,9 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
     const int N = a.N, D = a.D, R0 = a.row_begin, RC = a.row_count;
     uint8_t* ws = static_cast<uint8_t*>(a.workspace);
     float* stats = reinterpret_cast<float*>(ws + L.stats);
+    float* accs = reinterpret_cast<float*>(ws + L.acc);
+    float* partials = reinterpret_cast<float*>(ws + L.partials);
     double* loss_acc = reinterpret_cast<double*>(ws + L.misc);
-    unsigned int* counters = reinterpret_cast<unsigned int*>(ws + L.misc + 64);
-    float* g1 = reinterpret_cast<float*>(ws + L.g1);
-    float* g2 = reinterpret_cast<float*>(ws + L.g2);
     float* rs1 = reinterpret_cast<float*>(ws + L.rs1);
     float* rs2 = reinterpret_cast<float*>(ws + L.rs2);
     __half* C1 = reinterpret_cast<__half*>(ws + L.c1);
@@ -717,22 +725,30 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
     const int col_blocks = (D + kColsPerBlock - 1) / kColsPerBlock;
     if (int rc = ensure_umma_attr()) return rc;
 
-    cudaMemsetAsync(ws + L.misc, 0, 128, stream);     // loss partial sums + block counter
-    bt_stats_kernel<T><<<col_blocks, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, a.eps, a.momentum,
-                                                                stats, zb1, zb2, need != 0 ? zh1 : nullptr, need != 0 ? zh2 : nullptr,
-                                                                a.running_mean, a.running_var, loss_acc);
-    count_launch();
-    if (a.hsic) {
+    const bool timed = g_timing.enabled && g_timing.count < kTimingRing;
+    cudaEvent_t* tev = timed ? g_timing.ev[g_timing.count] : nullptr;
+    if (timed) cudaEventRecord(tev[0], stream);
+    cudaMemsetAsync(ws + L.misc, 0, L.zero_bytes, stream);     // loss partial sums + row / column accumulators
+    // ---- statistics
+    int splits = (N + 127) / 128;
+    if (splits > kMaxRowSplits) splits = kMaxRowSplits;
+    const int chunk = (N + splits - 1) / splits;
+    splits = (N + chunk - 1) / chunk;
+    const dim3 sgrid(col_blocks, splits);
+    bt_colstat_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, chunk, partials, zb1, zb2);
+    bt_normalize_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, chunk, splits, a.eps,
+                                                              a.momentum, partials, stats, need != 0 ? zh1 : nullptr, need != 0 ? zh2 : nullptr,
+                                                              a.running_mean, a.running_var, loss_acc);
+    count_launch(2);
+    if (a.hsic && need != 0) {
         bt_rowsum_kernel<<<N, 256, 0, stream>>>(zq1, N, D, stats + S_MU1 * D, stats + S_R1 * D, rs1);
         bt_rowsum_kernel<<<N, 256, 0, stream>>>(zq2, N, D, stats + S_MU2 * D, stats + S_R2 * D, rs2);
         count_launch(2);
     }
 
-    const bool timed = g_timing.enabled && g_timing.count < kTimingRing;
-    cudaEvent_t* tev = timed ? g_timing.ev[g_timing.count] : nullptr;
     const int row_tiles = (RC + BM - 1) / BM;
     // ---- CORR: C[rows, :] (and, in row-block mode, C^T[rows, :] with the views swapped)
-    if (timed) cudaEventRecord(tev[0], stream);
+    if (timed) cudaEventRecord(tev[1], stream);
     {
         CUtensorMap m1, m2;
         if (int rc = make_map_16(&m1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, zq1, N, D, 64, 64)) return rc;
@@ -741,20 +757,32 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         p.dc = g_desc;
         p.mode = 0; p.D = D; p.N = N;
         p.bn = 256; p.ab_format = 1;
-        p.tiles_m = row_tiles; p.tiles_n = (D + p.bn - 1) / p.bn; p.splits = 1;
+        p.tiles_m = row_tiles; p.tiles_n = (D + p.bn - 1) / p.bn;
         p.kblocks = (N + BK - 1) / BK;
         p.hsic = a.hsic; p.write_c = need != 0;
         p.loss_acc = loss_acc;
-        p.pass[0] = PassCfg{1, R0, R0 + RC, stats + S_NMU1 * D, stats + S_RHO1 * D, stats + S_MU2 * D, stats + S_R2 * D, 1, C1, nullptr, 0, 0, 0.f};
-        p.pass[1] = PassCfg{1, R0, R0 + RC, stats + S_NMU2 * D, stats + S_RHO2 * D, stats + S_MU1 * D, stats + S_R1 * D, 0, C2, nullptr, 0, 0, 0.f};
-        // the transposed block is only needed for dz2
-        p.pass_count = (a.rows_mode && (need & 2)) ? 2 : 1;
+        const bool second = a.rows_mode && (need & 2);       // the transposed block is only needed for dz2
+        PassCfg c0{}, c1{};
+        c0.a_mn = 1; c0.row0 = R0; c0.row_end = R0 + RC;
+        c0.row_nmu = stats + S_NMU1 * D; c0.row_rho = stats + S_RHO1 * D; c0.col_mu = stats + S_MU2 * D; c0.col_r = stats + S_R2 * D;
+        c0.accumulate_loss = 1; c0.c_out = C1;
+        c0.row_sq = (need & 1) ? accs + A_SQ1 * D : nullptr; c0.row_sum = accs + A_SUM1 * D;
+        c0.col_sq = (!a.rows_mode && (need & 2)) ? accs + A_SQ2 * D : nullptr; c0.col_sum = accs + A_SUM2 * D;
+        c1 = c0;
+        c1.row_nmu = stats + S_NMU2 * D; c1.row_rho = stats + S_RHO2 * D; c1.col_mu = stats + S_MU1 * D; c1.col_r = stats + S_R1 * D;
+        c1.accumulate_loss = 0; c1.c_out = C2;
+        c1.row_sq = accs + A_SQ2 * D; c1.row_sum = accs + A_SUM2 * D; c1.col_sq = nullptr; c1.col_sum = nullptr;
+        p.pass[0] = c0; p.pass[1] = c1;
+        p.pass_count = second ? 2 : 1;
         launch_umma(m1, m2, m2, m1, p, stream);
     }
-    if (timed) cudaEventRecord(tev[1], stream);
-    // ---- GRAD
+    if (timed) cudaEventRecord(tev[2], stream);
+    // ---- GRAD (+ batch-norm backward epilogue)
     if (need != 0) {
-        const int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
+        const int passes = (need == 3) ? 2 : 1;
+        int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
+        // small problems: narrower sample tiles instead of split-K, so that the epilogue always sees complete sums
+        while (bn > 32 && row_tiles * ((N + bn - 1) / bn) * passes < num_sms()) bn = ((bn / 2 + 15) / 16) * 16;
         CUtensorMap mCk, mCt, mZ2, mZ1;
         if (int rc = make_map_16(&mCk, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C1, RC, D, 64, 128)) return rc;
         if (a.rows_mode) {
@@ -769,38 +797,26 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         p.mode = 1; p.D = D; p.N = N; p.bn = bn; p.ab_format = 0;
         p.tiles_m = row_tiles; p.tiles_n = (N + bn - 1) / bn;
         p.kblocks = (D + BK - 1) / BK;
-        const PassCfg pass_dz1{0, R0, R0 + RC, nullptr, nullptr, nullptr, nullptr, 0, nullptr, g1, RC, 0, 0.f};
-        const PassCfg pass_dz2{a.rows_mode ? 0 : 1, R0, R0 + RC, nullptr, nullptr, nullptr, nullptr, 0, nullptr, g2, RC, 0, 0.f};
-        p.pass_count = (need == 3) ? 2 : 1;
-        const CUtensorMap *a0, *b0, *a1, *b1;
-        if (need & 1) { p.pass[0] = pass_dz1; a0 = &mCk; b0 = &mZ2; p.pass[1] = pass_dz2; a1 = &mCt; b1 = &mZ1; }
-        else { p.pass[0] = pass_dz2; a0 = &mCt; b0 = &mZ1; p.pass[1] = pass_dz2; a1 = &mCt; b1 = &mZ1; }
-        const int tiles = p.tiles_m * p.tiles_n * p.pass_count;
-        int splits = num_sms() / tiles;
-        if (splits < 1) splits = 1;
-        while (splits > 1 && p.kblocks / splits < 8) --splits;      // keep >= 8 k-blocks per split
-        {   // no empty split: every work item must issue at least one MMA
-            const int per = (p.kblocks + splits - 1) / splits;
-            splits = (p.kblocks + per - 1) / per;
-        }
-        p.splits = splits;
         p.hsic = a.hsic; p.write_c = 0;
         p.loss_acc = loss_acc;
-        if (splits > 1) {
-            if (need & 1) cudaMemsetAsync(g1, 0, sizeof(float) * (size_t)N * RC, stream);
-            if (need & 2) cudaMemsetAsync(g2, 0, sizeof(float) * (size_t)N * RC, stream);
-        }
+        p.io_dtype = a.dtype; p.zq1 = zq1; p.zq2 = zq2; p.stats = stats; p.rs1 = rs1; p.rs2 = rs2;
+        p.alpha = a.alpha; p.lambda = a.lambda; p.grad_scale = a.grad_scale; p.loss_out = a.loss_out;
+        PassCfg d1{}, d2{};
+        d1.a_mn = 0; d1.row0 = R0; d1.row_end = R0 + RC; d1.side = 0; d1.dz = a.dz1; d1.ld_dz = a.ld_dz;
+        d1.sq = accs + A_SQ1 * D; d1.sm = accs + A_SUM1 * D;
+        d2 = d1;
+        d2.a_mn = a.rows_mode ? 0 : 1; d2.side = 1; d2.dz = a.dz2;
+        d2.sq = accs + A_SQ2 * D; d2.sm = accs + A_SUM2 * D;
+        p.pass_count = passes;
+        const CUtensorMap *a0, *b0, *a1, *b1;
+        if (need & 1) { p.pass[0] = d1; a0 = &mCk; b0 = &mZ2; p.pass[1] = d2; a1 = &mCt; b1 = &mZ1; }
+        else { p.pass[0] = d2; a0 = &mCt; b0 = &mZ1; p.pass[1] = d2; a1 = &mCt; b1 = &mZ1; }
         launch_umma(*a0, *b0, *a1, *b1, p, stream);
-    }
-    if (timed) { cudaEventRecord(tev[2], stream); ++g_timing.count; }
-    // ---- finalize (columns of this call's dimension block)
-    if (need != 0 || a.loss_out != nullptr) {
-        const int fblocks = (RC + kColsPerBlock - 1) / kColsPerBlock;
-        bt_finalize_kernel<T><<<fblocks, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, R0, RC, a.ld_dz,
-                                                                   a.alpha, a.lambda, a.hsic, a.grad_scale, need, stats, g1, g2, rs1, rs2,
-                                                                   static_cast<T*>(a.dz1), static_cast<T*>(a.dz2), loss_acc, counters, a.loss_out);
+    } else if (a.loss_out != nullptr) {
+        bt_loss_scalar_kernel<<<1, 32, 0, stream>>>(loss_acc, a.alpha, a.lambda, a.hsic, D, a.loss_out);
         count_launch();
     }
+    if (timed) { cudaEventRecord(tev[3], stream); ++g_timing.count; }
     if (a.loss_parts_out != nullptr) cudaMemcpyAsync(a.loss_parts_out, loss_acc, 3 * sizeof(double), cudaMemcpyDeviceToDevice, stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "bt loss launch: %s", cudaGetErrorString(e));
@@ -830,7 +846,7 @@ using namespace abt;
 extern "C" int abt_debug_timing(int enable) {
     if (enable && !g_timing.created) {
         for (int i = 0; i < kTimingRing; ++i)
-            for (int k = 0; k < 3; ++k)
+            for (int k = 0; k < 4; ++k)
                 if (cudaEventCreate(&g_timing.ev[i][k]) != cudaSuccess) return set_error(ABT_ERR_CUDA, "cudaEventCreate failed");
         g_timing.created = true;
     }
@@ -839,17 +855,20 @@ extern "C" int abt_debug_timing(int enable) {
     return 0;
 }
 
-// Average milliseconds of the CORR and GRAD launches recorded since abt_debug_timing(1); synchronises on the events.
-extern "C" int abt_debug_timing_read(float* corr_ms, float* grad_ms, int* n_calls) {
-    double c = 0, g = 0;
+// Average milliseconds of the statistics launches, the CORR launch and the GRAD launch recorded since
+// abt_debug_timing(1); synchronises on the events.  Any output pointer may be null.
+extern "C" int abt_debug_timing_read(float* stats_ms, float* corr_ms, float* grad_ms, int* n_calls) {
+    double s = 0, c = 0, g = 0;
     const int n = g_timing.count;
     for (int i = 0; i < n; ++i) {
-        float a = 0, b = 0;
-        if (cudaEventSynchronize(g_timing.ev[i][2]) != cudaSuccess) return set_error(ABT_ERR_CUDA, "cudaEventSynchronize failed");
-        cudaEventElapsedTime(&a, g_timing.ev[i][0], g_timing.ev[i][1]);
-        cudaEventElapsedTime(&b, g_timing.ev[i][1], g_timing.ev[i][2]);
-        c += a; g += b;
+        float x = 0, y = 0, z = 0;
+        if (cudaEventSynchronize(g_timing.ev[i][3]) != cudaSuccess) return set_error(ABT_ERR_CUDA, "cudaEventSynchronize failed");
+        cudaEventElapsedTime(&x, g_timing.ev[i][0], g_timing.ev[i][1]);
+        cudaEventElapsedTime(&y, g_timing.ev[i][1], g_timing.ev[i][2]);
+        cudaEventElapsedTime(&z, g_timing.ev[i][2], g_timing.ev[i][3]);
+        s += x; c += y; g += z;
     }
+    if (stats_ms) *stats_ms = n ? (float)(s / n) : 0.f;
     if (corr_ms) *corr_ms = n ? (float)(c / n) : 0.f;
     if (grad_ms) *grad_ms = n ? (float)(g / n) : 0.f;
     if (n_calls) *n_calls = n;
@@ -866,7 +885,7 @@ extern "C" int abt_debug_set(int key, int value) {
 // Debug view of the single-GPU workspace layout (byte offsets), used by tools/gpu_diag.py only.
 extern "C" int abt_debug_ws_offsets(int n_rows, int n_dims, int dtype, size_t* out8) {
     const WsLayout L = ws_layout(n_rows, n_dims, n_dims, dtype, false);
-    out8[0] = L.stats; out8[1] = L.c1; out8[2] = L.g1; out8[3] = L.g2; out8[4] = L.zb1; out8[5] = L.zb2; out8[6] = L.misc; out8[7] = L.total;
+    out8[0] = L.stats; out8[1] = L.c1; out8[2] = L.acc; out8[3] = L.zh1; out8[4] = L.zb1; out8[5] = L.zb2; out8[6] = L.misc; out8[7] = L.total;
     return 0;
 }
 

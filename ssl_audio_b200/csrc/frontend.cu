@@ -49,6 +49,7 @@ struct LogmelArgs {
     const float* wav;
     long long row_stride;
     const int* wav_offset;
+    const int* wav_origin;    // span input: row b holds the samples [wav_origin[b], wav_origin[b] + row_stride) of clip b; nullptr = whole clips
     int n_samples;
     int n_frames_total;    // 1 + n_samples / hop
     int hop;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // -1 in frame_start / wav_offset means "no crop was drawn" (clip not longer than the crop)
     const int f_first = (a.frame_start ? max(a.frame_start[clip], 0) : 0) + tile * kTileFrames;   // absolute frame index
-    const float* wav = a.wav + (long long)clip * a.row_stride + (a.wav_offset ? max(a.wav_offset[clip], 0) : 0);
+    const float* wav = a.wav + (long long)clip * a.row_stride + (a.wav_offset ? max(a.wav_offset[clip], 0) : 0) - (a.wav_origin ? a.wav_origin[clip] : 0);
 
     // ---- stage the sample span (reflect padding: padded index s -> original s - n_fft/2, mirrored)
     const long long s0 = (long long)f_first * a.hop;
@@ -335,6 +336,32 @@ __global__ void bank_push_kernel(const float* __restrict__ x, long long x_stride
 }
 
 // ------------------------------------------------------------------------------------------
+// crop-first input staging: copy only the samples the cropped frames need, (n_fft + (n_frames-1) hop) per clip,
+// from the waveforms -- which may live in MAPPED PINNED HOST memory (zero-copy reads over PCIe) -- into a compact
+// device buffer.  For 10 s clips and a 96-frame crop this moves 65 KB instead of 640 KB per clip across PCIe.
+// Small footprint on purpose (128 threads, no shared memory): it co-resides with the compute kernels of the
+// previous step.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) wav_span_gather_kernel(const float* __restrict__ wav, long long row_stride, int n_samples,
+                                                              const int* __restrict__ frame_start, int hop, int half_fft, int span_len,
+                                                              float* __restrict__ spans, int* __restrict__ origin) {
+    const int clip = blockIdx.y;
+    const int f0 = frame_start ? max(frame_start[clip], 0) : 0;
+    int o = f0 * hop - half_fft;                 // first padded-coordinate sample of the crop, in clip coordinates
+    o = min(o, n_samples - span_len);
+    o = max(o, 0);
+    o &= ~3;                                     // keep 16-byte alignment of the source (rows are 16-byte aligned)
+    if (blockIdx.x == 0 && threadIdx.x == 0) origin[clip] = o;
+    const int len = min(span_len, n_samples - o);
+    const float* src = wav + (long long)clip * row_stride + o;
+    float* dst = spans + (long long)clip * span_len;
+    const int n4 = len >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
+        reinterpret_cast<float4*>(dst)[i] = __ldcs(reinterpret_cast<const float4*>(src) + i);
+    if (blockIdx.x == 0 && threadIdx.x < (len & 3)) dst[(n4 << 2) + threadIdx.x] = src[(n4 << 2) + threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------
 // host: plan tables
 // ------------------------------------------------------------------------------------------
 static std::vector<float> linspace_f32(double start, double end, int steps) {
@@ -436,7 +463,7 @@ extern "C" int abt_logmel_plan_destroy(abt_logmel_plan* pl) {
     return 0;
 }
 
-static int launch_logmel(const abt_logmel_plan* pl, const float* wav, int64_t row_stride, const int32_t* wav_offset, int n_clips, int n_samples,
+static int launch_logmel(const abt_logmel_plan* pl, const float* wav, int64_t row_stride, const int32_t* wav_offset, const int32_t* wav_origin, int n_clips, int n_samples,
                          const int32_t* frame_start, int n_frames_out,
                          float* out_base, const int32_t* out_slot, int64_t out_slot_stride, cudaStream_t stream) {
     if (n_clips < 0 || n_frames_out < 0) return set_error(ABT_ERR_ARG, "negative size");
@@ -446,7 +473,7 @@ static int launch_logmel(const abt_logmel_plan* pl, const float* wav, int64_t ro
     if (n_clips > 65535) return set_error(ABT_ERR_ARG, "n_clips must be <= 65535 per call");
     if (int rc = check_device_sm100()) return rc;
     LogmelArgs a{};
-    a.wav = wav; a.row_stride = row_stride; a.wav_offset = wav_offset; a.n_samples = n_samples; a.hop = pl->cfg.hop_length;
+    a.wav = wav; a.row_stride = row_stride; a.wav_offset = wav_offset; a.wav_origin = wav_origin; a.n_samples = n_samples; a.hop = pl->cfg.hop_length;
     a.n_frames_total = 1 + n_samples / pl->cfg.hop_length;
     a.frame_start = frame_start; a.n_frames_out = n_frames_out;
     a.out_base = out_base; a.out_slot = out_slot; a.out_slot_stride = out_slot_stride;
@@ -473,7 +500,7 @@ static int launch_logmel(const abt_logmel_plan* pl, const float* wav, int64_t ro
 extern "C" int abt_logmel_fwd(const abt_logmel_plan* plan, const float* wav, int n_clips, int n_samples, float* out, abt_stream_t stream) {
     if (plan == nullptr) return set_error(ABT_ERR_ARG, "plan is null");
     const int n_frames = 1 + n_samples / plan->cfg.hop_length;
-    return launch_logmel(plan, wav, n_samples, nullptr, n_clips, n_samples, nullptr, n_frames, out, nullptr, (int64_t)kMels * n_frames,
+    return launch_logmel(plan, wav, n_samples, nullptr, nullptr, n_clips, n_samples, nullptr, n_frames, out, nullptr, (int64_t)kMels * n_frames,
                          reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -483,7 +510,50 @@ extern "C" int abt_logmel_crop_fwd(const abt_logmel_plan* plan, const float* wav
     if (plan == nullptr) return set_error(ABT_ERR_ARG, "plan is null");
     if (out_slot_stride < (int64_t)kMels * n_frames) return set_error(ABT_ERR_ARG, "out_slot_stride smaller than one clip");
     if (wav_row_stride < n_samples) return set_error(ABT_ERR_ARG, "wav_row_stride smaller than n_samples");
-    return launch_logmel(plan, wav, wav_row_stride, wav_offset, n_clips, n_samples, frame_start, n_frames, out_base, out_slot, out_slot_stride,
+    return launch_logmel(plan, wav, wav_row_stride, wav_offset, nullptr, n_clips, n_samples, frame_start, n_frames, out_base, out_slot, out_slot_stride,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int abt_wav_span_len(const abt_logmel_plan* plan, int n_frames, int* span_len) {
+    if (plan == nullptr || span_len == nullptr || n_frames < 1) return set_error(ABT_ERR_ARG, "bad argument");
+    *span_len = ((n_frames - 1) * plan->cfg.hop_length + kNfft + 4 + 3) & ~3;     // +4: the source start is rounded down to 16 bytes
+    return 0;
+}
+
+extern "C" int abt_wav_span_gather(const abt_logmel_plan* plan, const float* wav, int wav_on_host, int64_t wav_row_stride, int n_clips,
+                                   int n_samples, const int32_t* frame_start, int n_frames, float* spans, int32_t* span_origin,
+                                   abt_stream_t stream) {
+    if (n_clips == 0) return 0;
+    if (plan == nullptr || wav == nullptr || spans == nullptr || span_origin == nullptr) return set_error(ABT_ERR_ARG, "null argument");
+    if (n_clips < 0 || n_clips > 65535 || n_frames < 1) return set_error(ABT_ERR_ARG, "bad shape");
+    if ((wav_row_stride & 3) != 0 || (reinterpret_cast<uintptr_t>(wav) & 15) != 0) return set_error(ABT_ERR_ARG, "waveform rows must be 16-byte aligned");
+    if (int rc = check_device_sm100()) return rc;
+    int span_len = 0;
+    abt_wav_span_len(plan, n_frames, &span_len);
+    if (n_samples < span_len) return set_error(ABT_ERR_ARG, "clips of %d samples are shorter than the %d-sample span; use abt_logmel_crop_fwd", n_samples, span_len);
+    const float* src = wav;
+    if (wav_on_host) {
+        void* dptr = nullptr;
+        cudaError_t e = cudaHostGetDevicePointer(&dptr, const_cast<float*>(wav), 0);
+        if (e != cudaSuccess) return set_error(ABT_ERR_ARG, "host waveforms must be in mapped pinned memory (cudaHostAlloc / cudaHostRegister): %s", cudaGetErrorString(e));
+        src = static_cast<const float*>(dptr);
+    }
+    dim3 grid(4, n_clips);
+    wav_span_gather_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, wav_row_stride, n_samples, frame_start, plan->cfg.hop_length,
+                                                                                       kNfft / 2, span_len, spans, span_origin);
+    count_launch();
+    ABT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int abt_logmel_span_fwd(const abt_logmel_plan* plan, const float* spans, const int32_t* span_origin, int n_clips, int n_samples,
+                                   const int32_t* frame_start, int n_frames, float* out_base, const int32_t* out_slot, int64_t out_slot_stride,
+                                   abt_stream_t stream) {
+    if (plan == nullptr || span_origin == nullptr) return set_error(ABT_ERR_ARG, "null argument");
+    if (out_slot_stride < (int64_t)kMels * n_frames) return set_error(ABT_ERR_ARG, "out_slot_stride smaller than one clip");
+    int span_len = 0;
+    if (int rc = abt_wav_span_len(plan, n_frames, &span_len)) return rc;
+    return launch_logmel(plan, spans, span_len, nullptr, span_origin, n_clips, n_samples, frame_start, n_frames, out_base, out_slot, out_slot_stride,
                          reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -154,9 +154,11 @@ class BatchFrontend(nn.Module):
 
     # -- waveform input ---------------------------------------------------------------------------
     def forward(self, wav: torch.Tensor) -> List[torch.Tensor]:
-        """wav (B, L) CUDA fp32 -> list of views [(B,1,F,T), (B,1,F,T), local crops...]."""
-        if not wav.is_cuda or wav.dtype != torch.float32 or wav.dim() != 2:
-            raise ValueError("wav must be a CUDA float32 tensor (B, L)")
+        """wav (B, L) fp32, CUDA or PINNED host memory -> list of views [(B,1,F,T), (B,1,F,T), local crops...]."""
+        if wav.dtype != torch.float32 or wav.dim() != 2:
+            raise ValueError("wav must be a float32 tensor (B, L)")
+        if not wav.is_cuda:
+            return self.forward_host(wav)
         wav = wav.contiguous()
         B, L = int(wav.shape[0]), int(wav.shape[1])
         tf = self.transform
@@ -183,4 +185,46 @@ class BatchFrontend(nn.Module):
                 raise ValueError(f"unit_sec gives {n_frames} frames but crop_frames is {self.crop_frames}")
             self.logmel_norm.crop_into(wav, self.unit_length, plan.wav_starts_ptr, 0, n_frames, ring, plan.slots_ptr, stride)
         self.last_plan = plan
+        return tf.views_from_plan(ring, plan.slots_ptr, stride, plan)
+
+    # -- waveforms in pinned host memory (what a DataLoader with pin_memory=True hands over, main.py:308-309) ---------
+    def forward_host(self, wav: torch.Tensor, device: Optional[torch.device] = None) -> List[torch.Tensor]:
+        """wav (B, L) fp32 in PINNED host memory -> views on `device` (default: the current CUDA device).
+
+        Crop-first all the way to the host: the crop is planned first, then a small kernel reads ONLY the samples the
+        cropped frames need straight out of the pinned buffer over PCIe (abt_wav_span_gather), so a 10 s clip costs
+        65 KB of host->device traffic instead of 640 KB.  Results are bit-identical to `forward(wav.cuda())`.
+        Clips that are not longer than the crop (nothing to skip) are copied whole."""
+        if wav.is_cuda or wav.dtype != torch.float32 or wav.dim() != 2 or not wav.is_contiguous():
+            raise ValueError("wav must be a contiguous float32 host tensor (B, L)")
+        if not wav.is_pinned():
+            raise RuntimeError("host waveforms must be in pinned memory (DataLoader(pin_memory=True) or tensor.pin_memory()); "
+                               "ssl_audio_b200 has no pageable-memory / CPU path")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        B, L = int(wav.shape[0]), int(wav.shape[1])
+        lib = self._lib
+        span_len = C.c_int()
+        _lib.check(lib.abt_wav_span_len(self.logmel_norm.plan(dev), self.crop_frames, C.byref(span_len)))
+        T_full = self.logmel_raw.n_frames(L)
+        if self.path != "lms" or self.mode != "crop" or T_full <= self.crop_frames or L < span_len.value or B == 0:
+            return self.forward(wav.to(dev, non_blocking=True))
+        tf = self.transform
+        eng = tf.engine(B)
+        ring = eng.ensure_ring(dev)
+        stride = int(ring.shape[1])
+        key = (dev.index, B)
+        if getattr(self, "_span_key", None) != key:
+            self._spans = torch.empty((B, span_len.value), dtype=torch.float32, device=dev)
+            self._origin = torch.empty((B,), dtype=torch.int32, device=dev)
+            self._span_key = key
+        with torch.cuda.device(dev):
+            plan = eng.planner.plan(B, time_crop_range=T_full - self.crop_frames, device=dev)
+            st = _stream(dev)
+            lm = self.logmel_norm.plan(dev)
+            _lib.check(lib.abt_wav_span_gather(lm, wav.data_ptr(), 1, L, B, L, plan.starts_ptr, self.crop_frames, self._spans.data_ptr(),
+                                               self._origin.data_ptr(), st))
+            _lib.check(lib.abt_logmel_span_fwd(lm, self._spans.data_ptr(), self._origin.data_ptr(), B, L, plan.starts_ptr, self.crop_frames,
+                                               ring.data_ptr(), plan.slots_ptr, stride, st))
+        self.last_plan = plan
+        self.h2d_bytes = B * span_len.value * 4
         return tf.views_from_plan(ring, plan.slots_ptr, stride, plan)

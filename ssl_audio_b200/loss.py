@@ -121,8 +121,9 @@ class _BTLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         dz1, dz2 = ctx.saved_tensors
-        g1 = (dz1 * grad_out.to(dz1.dtype)) if ctx.has[0] else None
-        g2 = (dz2 * grad_out.to(dz2.dtype)) if ctx.has[1] else None
+        # the stored gradients are this call's own buffers (never exposed before): scale them in place
+        g1 = dz1.mul_(grad_out.to(dz1.dtype)) if ctx.has[0] else None
+        g2 = dz2.mul_(grad_out.to(dz2.dtype)) if ctx.has[1] else None
         return g1, g2, None
 
 

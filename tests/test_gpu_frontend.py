@@ -197,3 +197,46 @@ def test_short_clip_is_padded_before_normalisation():
     ref = O.normalise(ref, AS_STATS)
     assert np.abs(v[0].cpu().numpy() - ref).max() < TOL
     assert torch.equal(v[0], v[1])
+
+
+def test_pinned_host_waveforms_zero_copy_span_path_is_bit_identical():
+    """forward(pinned host wav) plans the crop first and reads only the cropped span over PCIe; the result must
+    equal forward(device wav) bit for bit (also when crops touch either end of the clip: reflect padding)."""
+    import ssl_audio_b200 as S
+    wav = O.synth_wave(48, 32000, seed=4)                   # 201 frames: 105 possible crop starts, many near the edges
+    outs = []
+    for host in (False, True):
+        np.random.seed(5); random.seed(5)
+        fe = S.BatchFrontend(_args(), norm_stats=AS_STATS, path="lms", mode="crop")
+        w = torch.from_numpy(wav).pin_memory() if host else torch.from_numpy(wav).cuda()
+        for _ in range(2):                                   # second call: Mixup partners come from the ring
+            v = fe(w)
+        outs.append((torch.stack(v, 1).cpu().numpy(), fe.last_plan.starts.copy()))
+    assert outs[0][1].min() <= 2 and outs[0][1].max() >= 102, "seed no longer exercises both clip edges"
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][0], outs[1][0])
+    # forced edge crops through the C ABI: first and last possible crop start
+    from ssl_audio_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    mel = S.LogMelSpectrogram(16000, 1024, 1024, 160, 64, 60, 7800, norm_stats=AS_STATS)
+    dev = torch.device("cuda", 0)
+    plan = mel.plan(dev)
+    wh = torch.from_numpy(wav[:4]).pin_memory()
+    wd = wh.cuda()
+    starts = torch.tensor([0, 105, 1, 104], dtype=torch.int32, device=dev)
+    ref = torch.empty((4, 64 * 96), device=dev)
+    got = torch.empty((4, 64 * 96), device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(lib.abt_logmel_crop_fwd(plan, wd.data_ptr(), 32000, None, 4, 32000, starts.data_ptr(), 96, ref.data_ptr(), None, 64 * 96, st))
+    n = C.c_int()
+    _lib.check(lib.abt_wav_span_len(plan, 96, C.byref(n)))
+    spans = torch.empty((4, n.value), device=dev)
+    origin = torch.empty((4,), dtype=torch.int32, device=dev)
+    _lib.check(lib.abt_wav_span_gather(plan, wh.data_ptr(), 1, 32000, 4, 32000, starts.data_ptr(), 96, spans.data_ptr(), origin.data_ptr(), st))
+    _lib.check(lib.abt_logmel_span_fwd(plan, spans.data_ptr(), origin.data_ptr(), 4, 32000, starts.data_ptr(), 96, got.data_ptr(), None, 64 * 96, st))
+    torch.cuda.synchronize()
+    assert torch.equal(ref, got)
+    assert origin.cpu().tolist()[0] == 0 and origin.cpu().tolist()[1] == 32000 - n.value
+    with pytest.raises(RuntimeError):
+        S.BatchFrontend(_args(), norm_stats=AS_STATS)(torch.from_numpy(wav))          # pageable host memory: refused
