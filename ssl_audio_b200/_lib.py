@@ -137,6 +137,9 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)          # AttributeError here = header / library mismatch
             fn.restype = res
             fn.argtypes = args
+        # debugging aid: ABT_CTA_GROUP=1 selects the single-CTA tensor-core kernel instead of the CTA-pair one
+        if os.environ.get("ABT_CTA_GROUP") in ("1", "2"):
+            lib.abt_debug_set(6, int(os.environ["ABT_CTA_GROUP"]))
         _lib = lib
     return _lib
 

@@ -229,14 +229,21 @@ __global__ void __launch_bounds__(256) bt_rowsum_kernel(const __nv_bfloat16* __r
 // ------------------------------------------------------------------------------------------
 constexpr int BM = 128;            // UMMA M (TMEM lanes)
 constexpr int BK = 64;             // K elements per pipeline stage (one 128-byte swizzle row)
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kABytes = BM * BK * 2;       // 16 KiB
 constexpr int kBBytesMax = 256 * BK * 2;   // 32 KiB
 constexpr int kStageBytes = kABytes + kBBytesMax;
+constexpr int kStages2 = 5;                       // CTA-pair kernel: half of B per CTA
+constexpr int kStageBytes2 = kABytes + kBBytesMax / 2;
 constexpr int kAccCols = 256;      // TMEM columns per accumulator stage
 constexpr int kNumThreads = 384;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 loss scalar, warps 4-11 epilogue
 constexpr int kEpiWarps = 8;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kColStatBytes = 2 * 2 * 256 * 4;   // CORR epilogue: column mean / scale of the tile's 256 columns, per accumulator stage
+constexpr int kStoreBytes = 8 * 4096;            // CORR epilogue: one 32-row x 64-column fp16 box per epilogue warp, staged for the TMA store
+constexpr int kPipeBytes = 5 * (kABytes + kBBytesMax / 2);   // = kStages2 * kStageBytes2 >= kStages * kStageBytes
+constexpr int kSmemBytes = kPipeBytes + kStoreBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kColStatBytes;
+static_assert(kPipeBytes >= kStages * kStageBytes, "pipeline area too small");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 // Shared-memory descriptor constants (bytes).  Overridable through abt_debug_set() so that a wrong
 // guess about the descriptor encoding can be diagnosed in one GPU session.
@@ -305,22 +312,6 @@ __global__ void bt_loss_scalar_kernel(const double* __restrict__ acc, float alph
     if (threadIdx.x == 0) *loss_out = loss_from_parts(acc, alpha, lambda, hsic, D);
 }
 
-// column sums over the 32 rows held by the lanes of a warp: on return lane l holds sum over lanes of v[l]
-// (butterfly reduce-scatter, 31 shuffles)
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        const bool up = (lane & s) != 0;
-#pragma unroll
-        for (int t = 0; t < s; ++t) {
-            const float send = up ? v[t] : v[t + s];
-            const float keep = up ? v[t + s] : v[t];
-            v[t] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-        }
-    }
-    return v[0];
-}
-
 template <typename T> __device__ __forceinline__ void store_out(T* p, float v);
 template <> __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ void store_out<__half>(__half* p, float v) { *p = __float2half_rn(v); }
@@ -366,101 +357,174 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&acc)[32], const Umma
     }
 }
 
+// CORR epilogue arithmetic for 32 columns of one row: c_t = (S_t + nmu * mu_t) * rho * r_t, diagonal zeroed, packed to fp16;
+// cs_mu / cs_r: shared-window addresses of the 32 column means / scales (broadcast reads)
+__device__ __forceinline__ void corr_chunk(const uint32_t (&r)[32], uint32_t cs_mu, uint32_t cs_r, float nmu, float rho, int diag_t, bool diag_here,
+                                           bool hsic, uint32_t (&packed)[16], float& l2, float& l1) {
+#pragma unroll
+    for (int t4 = 0; t4 < 8; ++t4) {
+        const float4 m4 = lds128(cs_mu + t4 * 16), b4 = lds128(cs_r + t4 * 16);
+        const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+        float cc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cc[u] = (fmaf(nmu, mm[u], __uint_as_float(r[t4 * 4 + u])) * rho) * bb[u];
+        if (diag_here) {       // warp-uniform: the diagonal is handled in fp32 (cdiag from the statistics pass)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cc[u] = (t4 * 4 + u == diag_t) ? 0.f : cc[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) l2 = fmaf(cc[u], cc[u], l2);
+        if (hsic) l1 += (cc[0] + cc[1]) + (cc[2] + cc[3]);
+        packed[t4 * 2] = pack_f16x2(cc[0], cc[1]);
+        packed[t4 * 2 + 1] = pack_f16x2(cc[2], cc[3]);
+    }
+}
+
+// CG = 1: one CTA per 128 x bn tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x bn tile -- each CTA stages
+// its own 128 rows of A and HALF of the B tile, so the operand bytes pulled through L2 per FLOP drop by a third (the single-CTA
+// kernel is L2-bandwidth-bound: 48 KB per 4.2 MFLOP k-block = 87 FLOP/B against ~12 TB/s of L2).  The leader CTA (rank 0) issues
+// the M = 256 MMAs; TMA completions of both CTAs land on the leader's `full` barriers, MMA commits are multicast to both CTAs.
+template <int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
-               const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1, const UmmaParams p) {
+               const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
+               const __grid_constant__ CUtensorMap mapC0, const __grid_constant__ CUtensorMap mapC1, const UmmaParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tfull_bar = empty_bar + kStages;
+    constexpr int kStg = CG == 1 ? kStages : kStages2;
+    constexpr int kStgBytes = CG == 1 ? kStageBytes : kStageBytes2;
+    static_assert(kStg * kStgBytes <= kPipeBytes, "pipeline stages exceed their area");
+    const uint32_t store_s = smem_u32(smem + kPipeBytes);                                // 1024-byte aligned staging boxes
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kPipeBytes + kStoreBytes);
+    uint64_t* empty_bar = full_bar + kStg;
+    uint64_t* tfull_bar = empty_bar + kStg;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    const uint32_t colstat_s = smem_u32(smem + kPipeBytes + kStoreBytes + 256);          // [acc][mu | r][256] floats
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_work = p.tiles_m * p.tiles_n * p.pass_count;
+    const int total_work = p.tiles_m * p.tiles_n * p.pass_count;      // tiles_m counts (128 * CG)-row tiles
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;          // 0 = leader of the pair
+    const int work0 = blockIdx.x / CG, work_stride = gridDim.x / CG;
+    const int bn_cta = p.bn / CG;                                     // B columns (or rows) staged by this CTA
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapB0);
         if (p.pass_count > 1) { tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapB1); }
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps); }
+        for (int s = 0; s < kStg; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps * CG); }
         mbar_fence_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
+        if (CG == 2) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     // Operand "major-ness": CORR reads both raw embeddings as MN-major tiles (B too); GRAD reads C K-major (rows of C) or
     // MN-major (the same C as C^T) and its B operand (standardised fp16 embeddings, one row per sample) K-major.
     const bool b_mn = (p.mode == 0);
-    if (warp == 0 && lane == 0) {
-        // ================= TMA producer =================
+    if (warp == 0) {
+        // ================= TMA producer (whole warp runs the loop so that the code stays warp-uniform; one elected lane issues) ==========
         int stage = 0; uint32_t phase = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        for (int w = work0; w < total_work; w += work_stride) {
             int pass, tm, tn;
             decode_work(p, w, pass, tm, tn);
+            tm = tm * CG + (int)rank;                 // this CTA's 128-row tile
             const PassCfg& pc = p.pass[pass];
             const CUtensorMap* mA = pass == 1 ? &mapA1 : &mapA0;
             const CUtensorMap* mB = pass == 1 ? &mapB1 : &mapB0;
-            const uint32_t tx = kABytes + (uint32_t)p.bn * BK * 2;
+            const uint32_t tx = (kABytes + (uint32_t)bn_cta * BK * 2) * CG;     // both CTAs' bytes land on the leader's barrier
+            const int bcol0 = tn * p.bn + (int)rank * bn_cta;
+            const int a_mn = pc.a_mn;
+            const int arow = a_mn ? pc.row0 + tm * BM : tm * BM;
             for (int kb = 0; kb < p.kblocks; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sA = smem + stage * kStageBytes;
-                uint8_t* sB = sA + kABytes;
-                mbar_expect_tx(&full_bar[stage], tx);
-                if (pc.a_mn) {
-                    // the tensor map spans global dimension indices (columns of z or of the full C)
-                    tma_load_2d(sA, mA, &full_bar[stage], pc.row0 + tm * BM, kb * BK);
-                    tma_load_2d(sA + 8192, mA, &full_bar[stage], pc.row0 + tm * BM + 64, kb * BK);
-                } else {
-                    // the tensor map spans the rows of the (possibly row-block compact) C matrix
-                    tma_load_2d(sA, mA, &full_bar[stage], kb * BK, tm * BM);
+                if (elect_one()) {
+                    uint8_t* sA = smem + stage * kStgBytes;
+                    uint8_t* sB = sA + kABytes;
+                    if (CG == 1) {
+                        mbar_expect_tx(&full_bar[stage], tx);
+                        if (a_mn) {
+                            // the tensor map spans global dimension indices (columns of z or of the full C)
+                            tma_load_2d(sA, mA, &full_bar[stage], arow, kb * BK);
+                            tma_load_2d(sA + 8192, mA, &full_bar[stage], arow + 64, kb * BK);
+                        } else {
+                            // the tensor map spans the rows of the (possibly row-block compact) C matrix
+                            tma_load_2d(sA, mA, &full_bar[stage], kb * BK, arow);
+                        }
+                        if (b_mn) {
+                            for (int c = 0; c < bn_cta / 64; ++c) tma_load_2d(sB + c * 8192, mB, &full_bar[stage], bcol0 + c * 64, kb * BK);
+                        } else {
+                            tma_load_2d(sB, mB, &full_bar[stage], kb * BK, bcol0);
+                        }
+                    } else {
+                        const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);       // the leader's barrier
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
+                        if (a_mn) {
+                            tma_load_2d_2sm(sA, mA, lbar, arow, kb * BK);
+                            tma_load_2d_2sm(sA + 8192, mA, lbar, arow + 64, kb * BK);
+                        } else {
+                            tma_load_2d_2sm(sA, mA, lbar, kb * BK, arow);
+                        }
+                        if (b_mn) {
+                            for (int c = 0; c < bn_cta / 64; ++c) tma_load_2d_2sm(sB + c * 8192, mB, lbar, bcol0 + c * 64, kb * BK);
+                        } else {
+                            tma_load_2d_2sm(sB, mB, lbar, kb * BK, bcol0);
+                        }
+                    }
                 }
-                if (b_mn) {
-                    for (int c = 0; c < p.bn / 64; ++c) tma_load_2d(sB + c * 8192, mB, &full_bar[stage], tn * p.bn + c * 64, kb * BK);
-                } else {
-                    tma_load_2d(sB, mB, &full_bar[stage], kb * BK, tn * p.bn);
-                }
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                __syncwarp();
+                if (++stage == kStg) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ================= MMA issuer (one thread) =================
+    } else if (warp == 1 && rank == 0) {
+        // ================= MMA issuer (leader CTA; warp-uniform loop, one elected lane issues) =================
+        // descriptor = constant high word (SBO, version, swizzle) + low word (address >> 4 | LBO << 16) that advances per UMMA_K
+        const uint32_t hi_mn = ((uint32_t)(p.dc.mn_sbo >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+        const uint32_t hi_k = ((uint32_t)(p.dc.k_sbo >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+        const uint32_t lo_mn = (((uint32_t)p.dc.mn_lbo >> 4) & 0x3FFF) << 16, lo_k = (((uint32_t)p.dc.k_lbo >> 4) & 0x3FFF) << 16;
+        const uint32_t b_hi = b_mn ? hi_mn : hi_k, b_lo = b_mn ? lo_mn : lo_k, b_step = (uint32_t)(b_mn ? p.dc.mn_kstep : p.dc.k_kstep) >> 4;
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        for (int w = work0; w < total_work; w += work_stride) {
             int pass, tm, tn;
             decode_work(p, w, pass, tm, tn);
             const bool a_mn = p.pass[pass].a_mn != 0;
-            const uint32_t idesc = make_idesc_f16(BM, p.bn, a_mn ? 1 : 0, b_mn ? 1 : 0, p.ab_format);
+            const uint32_t idesc = make_idesc_f16(BM * CG, p.bn, a_mn ? 1 : 0, b_mn ? 1 : 0, p.ab_format);
+            const uint32_t a_hi = a_mn ? hi_mn : hi_k, a_lo = a_mn ? lo_mn : lo_k, a_step = (uint32_t)(a_mn ? p.dc.mn_kstep : p.dc.k_kstep) >> 4;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * kAccCols;
             for (int kb = 0; kb < p.kblocks; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t sA = smem_u32(smem + stage * kStageBytes);
-                const uint32_t sB = sA + kABytes;
+                if (elect_one()) {
+                    const uint32_t sA = smem_u32(smem + stage * kStgBytes);
+                    const uint32_t sB = sA + kABytes;
+                    uint32_t da = a_lo | ((sA & 0x3FFFF) >> 4), db = b_lo | ((sB & 0x3FFFF) >> 4);
 #pragma unroll
-                for (int ks = 0; ks < BK / 16; ++ks) {
-                    const uint64_t da = a_mn ? make_smem_desc_sw128(sA + ks * p.dc.mn_kstep, p.dc.mn_lbo, p.dc.mn_sbo)
-                                             : make_smem_desc_sw128(sA + ks * p.dc.k_kstep, p.dc.k_lbo, p.dc.k_sbo);
-                    const uint64_t db = b_mn ? make_smem_desc_sw128(sB + ks * p.dc.mn_kstep, p.dc.mn_lbo, p.dc.mn_sbo)
-                                             : make_smem_desc_sw128(sB + ks * p.dc.k_kstep, p.dc.k_lbo, p.dc.k_sbo);
-                    umma_bf16_ss(d_tmem, da, db, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                    for (int ks = 0; ks < BK / 16; ++ks) {
+                        const uint64_t da64 = ((uint64_t)a_hi << 32) | da, db64 = ((uint64_t)b_hi << 32) | db;
+                        if (CG == 2) umma_bf16_ss_2sm(d_tmem, da64, db64, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                        else umma_bf16_ss(d_tmem, da64, db64, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                        da += a_step; db += b_step;
+                    }
+                    // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+                    if (CG == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+                    // accumulator complete -> epilogue (of both CTAs)
+                    if (kb == p.kblocks - 1) {
+                        if (CG == 2) umma_commit_2sm(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
+                    }
                 }
-                umma_commit(&empty_bar[stage]);   // frees the smem stage when these MMAs retire
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                __syncwarp();
+                if (++stage == kStg) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp == 3 && lane == 0) {
@@ -472,10 +536,20 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int hf = (warp - 4) >> 2;      // which half of the 32-column chunks
         int acc = 0; uint32_t acc_phase = 0;
         const int D = p.D;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        for (int w = work0; w < total_work; w += work_stride) {
             int pass, tm, tn;
             decode_work(p, w, pass, tm, tn);
+            tm = tm * CG + (int)rank;
             const PassCfg& pc = p.pass[pass];
+            const uint32_t cs_mu = colstat_s + acc * 2048, cs_r = cs_mu + 1024;
+            if (p.mode == 0) {
+                // stage the column statistics of this tile while its MMAs are still running (the previous use of this buffer, two
+                // tiles ago, ended before the named barrier of the previous tile; the barrier orders these writes before the reads)
+                const int e = threadIdx.x - 128, j = tn * p.bn + e;
+                sts32f(cs_mu + e * 4, j < D ? __ldg(pc.col_mu + j) : 0.f);
+                sts32f(cs_r + e * 4, j < D ? __ldg(pc.col_r + j) : 0.f);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
@@ -484,55 +558,65 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const bool row_ok = row < pc.row_end;
             if (p.mode == 0) {
                 // ---- CORR: v = S - N mu_i mu'_j;  c = v (r_i / N) r'_j   (batch-norm as a rank-1 correction)
+                // Warp (q, hf) owns rows 32q..32q+31 and columns 128 hf..128 hf+127 of the tile: 4 chunks of 32 columns = 2 boxes
+                // of 64 columns.  Each box is packed to fp16, staged in shared memory (128-byte swizzle) and written with ONE
+                // TMA store (row-major C with lane = row would otherwise need 32 scattered 16-byte stores per instruction);
+                // the column sums of C o C are taken from the staged box.  TMEM loads run one chunk ahead of the arithmetic.
                 const float nmu = row_ok ? pc.row_nmu[row] : 0.f;
                 const float rho = row_ok ? pc.row_rho[row] : 0.f;      // rows beyond the block give c = 0
                 float l2 = 0.f, l1 = 0.f;
-                const int nchunks = p.bn / 32;
-                for (int ch = hf; ch < nchunks; ch += 2) {
-                    const int j0 = tn * p.bn + ch * 32;
-                    if (j0 >= D) break;                                // warp-uniform
-                    uint32_t r[32];
-                    tmem_ld_32x32(t_addr + ch * 32, r);
-                    tmem_ld_wait();
+                const int row_base = pc.row0 + tm * BM + q * 32;       // global row of lane 0
+                const uint32_t stg = store_s + (uint32_t)(warp - 4) * 4096u, stg_row = stg + (uint32_t)lane * 128u;
+                const uint32_t sw = (uint32_t)(lane & 7);
+                const CUtensorMap* mC = pass == 1 ? &mapC1 : &mapC0;
+                const int c_first = hf * 4, j_tile = tn * p.bn;
+                int nvalid = (D - j_tile - c_first * 32) / 32;          // valid 32-column chunks of this warp (D % 64 == 0: 0, 2 or 4)
+                nvalid = nvalid < 0 ? 0 : (nvalid > 4 ? 4 : nvalid);
+                uint32_t ra[32], rb[32];
+                if (nvalid > 0) tmem_ld_32x32(t_addr + c_first * 32, ra);
+                for (int pp = 0; pp * 2 < nvalid; ++pp) {
+                    const int chA = c_first + pp * 2, jA = j_tile + chA * 32;
                     uint32_t packed[16];
-                    float csq[32];
+                    tmem_ld_wait();
+                    tmem_ld_32x32(t_addr + (chA + 1) * 32, rb);
+                    if (p.write_c) {                                   // the staging box is free once the previous store has read it
+                        if (lane == 0) tma_store_wait_read();
+                        __syncwarp();
+                    }
+                    corr_chunk(ra, cs_mu + chA * 128, cs_r + chA * 128, nmu, rho, row - jA, jA < row_base + 32 && jA + 32 > row_base, p.hsic != 0, packed, l2, l1);
+                    if (p.write_c) {
 #pragma unroll
-                    for (int t4 = 0; t4 < 8; ++t4) {
-                        const float4 m4 = __ldg(reinterpret_cast<const float4*>(pc.col_mu + j0) + t4);
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(pc.col_r + j0) + t4);
-                        const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
-                        float cc[4];
+                        for (int k = 0; k < 4; ++k) sts128(stg_row + (((uint32_t)k ^ sw) << 4), packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+                    }
+                    tmem_ld_wait();
+                    if (pp == 0 && nvalid > 2) tmem_ld_32x32(t_addr + (chA + 2) * 32, ra);
+                    corr_chunk(rb, cs_mu + (chA + 1) * 128, cs_r + (chA + 1) * 128, nmu, rho, row - jA - 32, jA + 32 < row_base + 32 && jA + 64 > row_base, p.hsic != 0, packed, l2, l1);
+                    if (p.write_c) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int t = t4 * 4 + u;
-                            const float v = fmaf(nmu, mm[u], __uint_as_float(r[t]));
-                            float c = (v * rho) * bb[u];
-                            c = (j0 + t == row) ? 0.f : c;      // the diagonal is handled in fp32 (cdiag from the statistics pass)
-                            csq[t] = c * c;
-                            l2 += csq[t];
-                            l1 += c;
-                            cc[u] = c;
+                        for (int k = 0; k < 4; ++k) sts128(stg_row + (((uint32_t)(k + 4) ^ sw) << 4), packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(mC, stg, jA, tm * BM + q * 32);       // rows / columns beyond the matrix are clipped by the tensor map
+                            tma_store_commit();
                         }
-                        packed[t4 * 2] = pack_f16x2(cc[0], cc[1]);
-                        packed[t4 * 2 + 1] = pack_f16x2(cc[2], cc[3]);
-                    }
-                    if (p.write_c && row_ok) {
-                        uint4* dst = reinterpret_cast<uint4*>(pc.c_out + (size_t)lrow * D + j0);
+                        if (pc.col_sq != nullptr) {
+                            // column sums over this warp's 32 rows from the staged (fp16) box: lane l owns columns jA + 2l, 2l + 1
+                            float sq0 = 0.f, sq1 = 0.f, sm0 = 0.f, sm1 = 0.f;
+                            const uint32_t woff = (uint32_t)(lane & 3) * 4u, kc = (uint32_t)(lane >> 2);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) dst[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
-                    }
-                    if (pc.col_sq != nullptr) {
-                        // column sums over this warp's 32 rows; lane l ends up with column j0 + l
-                        const float cs = warp_transpose_reduce(csq, lane);
-                        atomicAdd(pc.col_sq + j0 + lane, cs);
-                        if (p.hsic) {
-                            float cv[32];
-#pragma unroll
-                            for (int t = 0; t < 16; ++t) {
-                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&packed[t]));
-                                cv[2 * t] = f.x; cv[2 * t + 1] = f.y;
+                            for (int r = 0; r < 32; ++r) {
+                                const uint32_t w = lds32(stg + (uint32_t)r * 128u + ((kc ^ (uint32_t)(r & 7)) << 4) + woff);
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                                sq0 = fmaf(f.x, f.x, sq0); sq1 = fmaf(f.y, f.y, sq1);
+                                sm0 += f.x; sm1 += f.y;
                             }
-                            atomicAdd(pc.col_sum + j0 + lane, warp_transpose_reduce(cv, lane));
+                            atomicAdd(pc.col_sq + jA + 2 * lane, sq0);
+                            atomicAdd(pc.col_sq + jA + 2 * lane + 1, sq1);
+                            if (p.hsic) {
+                                atomicAdd(pc.col_sum + jA + 2 * lane, sm0);
+                                atomicAdd(pc.col_sum + jA + 2 * lane + 1, sm1);
+                            }
                         }
                     }
                 }
@@ -576,13 +660,20 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                // the MMA issuer (leader CTA) may overwrite this accumulator stage once every epilogue warp of the pair is done
+                if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+                else mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
+    if (warp >= 4 && lane == 0) tma_store_wait_all();     // bulk stores of the CORR epilogue
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) {
+        if (CG == 2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -670,22 +761,39 @@ static int num_sms() {
     return g_num_sms;
 }
 
+static int g_cta_group = 2;     // 2 = CTA-pair kernel (default), 1 = single-CTA kernel (abt_debug_set key 6)
+
 static int ensure_umma_attr() {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(bt_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(bt_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
     return 0;
 }
 
-static void launch_umma(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1, const UmmaParams& p,
-                        cudaStream_t stream) {
+// p.tiles_m counts (128 * cg)-row tiles
+static int launch_umma(int cg, const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1, const CUtensorMap& c0,
+                       const CUtensorMap& c1, const UmmaParams& p, cudaStream_t stream) {
     const int total = p.tiles_m * p.tiles_n * p.pass_count;
-    const int grid = total < num_sms() ? total : num_sms();
-    bt_umma_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(a0, b0, a1, b1, p);
+    const int slots = num_sms() / cg;
+    const int grid = (total < slots ? total : slots) * cg;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cg == 2 ? cudaLaunchKernelEx(&cfg, bt_umma_kernel<2>, a0, b0, a1, b1, c0, c1, p) : cudaLaunchKernelEx(&cfg, bt_umma_kernel<1>, a0, b0, a1, b1, c0, c1, p);
     count_launch();
+    if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "bt_umma_kernel launch: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 // Everything one loss evaluation needs, for both the single-GPU and the row-block entry points.
@@ -746,7 +854,8 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         count_launch(2);
     }
 
-    const int row_tiles = (RC + BM - 1) / BM;
+    const int cg = g_cta_group == 1 ? 1 : 2;
+    const int row_tiles = (RC + BM * cg - 1) / (BM * cg);
     // ---- CORR: C[rows, :] (and, in row-block mode, C^T[rows, :] with the views swapped)
     if (timed) cudaEventRecord(tev[1], stream);
     {
@@ -774,15 +883,20 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         c1.row_sq = accs + A_SQ2 * D; c1.row_sum = accs + A_SUM2 * D; c1.col_sq = nullptr; c1.col_sum = nullptr;
         p.pass[0] = c0; p.pass[1] = c1;
         p.pass_count = second ? 2 : 1;
-        launch_umma(m1, m2, m2, m1, p, stream);
+        // C is written by TMA stores of 32-row x 64-column boxes (row-block compact: RC rows)
+        CUtensorMap mc1, mc2;
+        if (int rc = make_map_16(&mc1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C1, RC, D, 64, 32)) return rc;
+        if (int rc = make_map_16(&mc2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, second ? C2 : C1, RC, D, 64, 32)) return rc;
+        if (int rc = launch_umma(cg, m1, m2, m2, m1, mc1, mc2, p, stream)) return rc;
     }
     if (timed) cudaEventRecord(tev[2], stream);
     // ---- GRAD (+ batch-norm backward epilogue)
     if (need != 0) {
         const int passes = (need == 3) ? 2 : 1;
-        int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
+        const int q = 16 * cg;                                  // UMMA N granularity (M = 128: 16, M = 256: 32 so that each CTA stages a multiple of 16)
+        int bn = N >= 256 ? 256 : ((N + q - 1) / q) * q;
         // small problems: narrower sample tiles instead of split-K, so that the epilogue always sees complete sums
-        while (bn > 32 && row_tiles * ((N + bn - 1) / bn) * passes < num_sms()) bn = ((bn / 2 + 15) / 16) * 16;
+        while (bn > 32 && row_tiles * ((N + bn - 1) / bn) * passes < num_sms() / cg) bn = ((bn / 2 + q - 1) / q) * q;
         CUtensorMap mCk, mCt, mZ2, mZ1;
         if (int rc = make_map_16(&mCk, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C1, RC, D, 64, 128)) return rc;
         if (a.rows_mode) {
@@ -790,8 +904,8 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         } else {
             if (int rc = make_map_16(&mCt, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C1, RC, D, 64, 64)) return rc;     // the same C read MN-major
         }
-        if (int rc = make_map_16(&mZ2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh2, N, D, 64, bn)) return rc;
-        if (int rc = make_map_16(&mZ1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh1, N, D, 64, bn)) return rc;
+        if (int rc = make_map_16(&mZ2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh2, N, D, 64, bn / cg)) return rc;     // each CTA of a pair stages bn / 2 samples
+        if (int rc = make_map_16(&mZ1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh1, N, D, 64, bn / cg)) return rc;
         UmmaParams p{};
         p.dc = g_desc;
         p.mode = 1; p.D = D; p.N = N; p.bn = bn; p.ab_format = 0;
@@ -811,7 +925,7 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         const CUtensorMap *a0, *b0, *a1, *b1;
         if (need & 1) { p.pass[0] = d1; a0 = &mCk; b0 = &mZ2; p.pass[1] = d2; a1 = &mCt; b1 = &mZ1; }
         else { p.pass[0] = d2; a0 = &mCt; b0 = &mZ1; p.pass[1] = d2; a1 = &mCt; b1 = &mZ1; }
-        launch_umma(*a0, *b0, *a1, *b1, p, stream);
+        if (int rc = launch_umma(cg, *a0, *b0, *a1, *b1, *a0, *a0, p, stream)) return rc;
     } else if (a.loss_out != nullptr) {
         bt_loss_scalar_kernel<<<1, 32, 0, stream>>>(loss_acc, a.alpha, a.lambda, a.hsic, D, a.loss_out);
         count_launch();
@@ -877,6 +991,7 @@ extern "C" int abt_debug_timing_read(float* stats_ms, float* corr_ms, float* gra
 
 extern "C" int abt_debug_set(int key, int value) {
     int* f[6] = {&g_desc.mn_lbo, &g_desc.mn_sbo, &g_desc.mn_kstep, &g_desc.k_lbo, &g_desc.k_sbo, &g_desc.k_kstep};
+    if (key == 6) { g_cta_group = value == 1 ? 1 : 2; return 0; }
     if (key < 0 || key >= 6) return set_error(ABT_ERR_ARG, "unknown debug key %d", key);
     *f[key] = value;
     return 0;
