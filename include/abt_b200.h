@@ -187,6 +187,12 @@ int abt_planner_packed_bytes(const abt_planner* p, int n_clips, size_t* total, s
                              size_t* off_slots);
 int abt_planner_plan_batch_packed(abt_planner* p, int n_clips, int time_crop_range, int wav_crop_range, void* out, size_t out_bytes);
 
+/* Same, against the interpreter's GLOBAL generators in place (one call per batch): np_state -> numpy's legacy
+ * `struct { uint32_t key[624]; int pos; }` (np.random.mtrand._rand._bit_generator.ctypes.state_address), py_index / py_key -> the
+ * index and the 624 state words inside CPython's `random._inst` object.  Either may be NULL when that generator cannot be drawn from. */
+int abt_planner_plan_batch_global(abt_planner* p, int n_clips, int time_crop_range, int wav_crop_range, void* np_state, int32_t* py_index,
+                                  uint32_t* py_key, void* out, size_t out_bytes);
+
 /* ===================================================================================== *
  *  Barlow Twins objective forward + backward
  *  replaces BarlowTwinsLoss.forward_loss (utils/loss.py:15-30: BatchNorm1d(affine=False) on

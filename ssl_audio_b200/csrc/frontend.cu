@@ -71,13 +71,14 @@ struct LogmelArgs {
 };
 
 __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs a) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int span = (kTileFrames - 1) * a.hop + kNfft;
     float* s_x = smem;                                  // span samples (padded coordinates)
     float* s_scratch = s_x + ((span + 31) & ~31);       // kWarps * kScratchFloats
     float* s_out = s_scratch + kWarps * kScratchFloats; // kMels * (kTileFrames + 1)
     float* s_melw = s_out + kMels * (kTileFrames + 1);  // nnz
     int* s_mel_start = reinterpret_cast<int*>(s_melw + a.nnz);   // 64 start, 64 len, 64 off
+    __shared__ __align__(8) unsigned long long s_bar;
 
     const int clip = blockIdx.y;
     const int tile = blockIdx.x;
@@ -87,14 +88,39 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
     const float* wav = a.wav + (long long)clip * a.row_stride + (a.wav_offset ? max(a.wav_offset[clip], 0) : 0) - (a.wav_origin ? a.wav_origin[clip] : 0);
 
     // ---- stage the sample span (reflect padding: padded index s -> original s - n_fft/2, mirrored)
-    const long long s0 = (long long)f_first * a.hop;
-    for (int s = tid; s < span; s += blockDim.x) {
-        long long o = s0 + s - kNfft / 2;
-        if (o < 0) o = -o;
-        if (o >= a.n_samples) o = 2LL * (a.n_samples - 1) - o;
-        float v = 0.f;
-        if (o >= 0 && o < a.n_samples) v = __ldg(wav + o);
-        s_x[s] = v;
+    const long long o_first = (long long)f_first * a.hop - kNfft / 2;      // original index of padded sample 0 of this tile
+    const bool interior = o_first >= 0 && o_first + span <= a.n_samples && (span & 3) == 0 &&
+                          (reinterpret_cast<uintptr_t>(wav + o_first) & 15) == 0;
+    if (interior) {
+        // one bulk async copy (TMA, 1-D) of the whole span, issued by a single thread
+        const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&s_bar));
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(span * 4) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             static_cast<unsigned>(__cvta_generic_to_shared(s_x))),
+                         "l"(wav + o_first), "r"(span * 4), "r"(bar)
+                         : "memory");
+        }
+    } else {
+        // clip edges / unaligned rows: mirrored scalar loads, eight independent requests in flight per thread
+        for (int base = 0; base < span; base += 8 * kWarps * 32) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int sidx = base + u * kWarps * 32 + tid;
+                long long o = o_first + sidx;
+                if (o < 0) o = -o;
+                if (o >= a.n_samples) o = 2LL * (a.n_samples - 1) - o;
+                v[u] = (sidx < span && o >= 0 && o < a.n_samples) ? __ldg(wav + o) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int sidx = base + u * kWarps * 32 + tid;
+                if (sidx < span) s_x[sidx] = v[u];
+            }
+        }
     }
     for (int i = tid; i < a.nnz; i += blockDim.x) s_melw[i] = a.mel_w[i];
     if (tid < kMels) {
@@ -102,10 +128,22 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
         s_mel_start[kMels + tid] = a.mel_len[tid];
         s_mel_start[2 * kMels + tid] = a.mel_off[tid];
     }
-    __syncthreads();
+    __syncthreads();      // also orders the mbarrier init before the waits below
+    if (interior) {
+        const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&s_bar));
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                "selp.b32 %0, 1, 0, p;\n\t}\n"
+                : "=r"(done)
+                : "r"(bar)
+                : "memory");
+        }
+    }
 
-    float* sre = s_scratch + warp * kScratchFloats;
-    float* sim = sre + 32 * 33;
+    float2* sc = reinterpret_cast<float2*>(s_scratch + warp * kScratchFloats);     // 32 x 33 complex, later 513 x (Pa, Pb)
 
     for (int round = 0; round < kTileFrames / (2 * kWarps); ++round) {
         const int fa = round * 2 * kWarps + 2 * warp;     // local frame indices of this warp's pair
@@ -124,78 +162,61 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
                 im[n2] = xb[n] * w;
             }
             fft32(re, im);   // register p: Y[n1 = lane][k2 = bitrev(p)]
-            // twiddle W1024^(n1 k2) and transpose through shared memory
+            // twiddle W1024^(n1 k2) and transpose through shared memory (64-bit accesses, conflict-free with the 33-stride)
+            __syncwarp();    // the previous round's mel reads of this scratch are complete
 #pragma unroll
             for (int p = 0; p < 32; ++p) {
                 const int k2 = bitrev5(p);
                 const float2 w = __ldg(a.twiddle + k2 * 32 + lane);
-                const float yr = re[p] * w.x - im[p] * w.y;
-                const float yi = re[p] * w.y + im[p] * w.x;
-                sre[lane * 33 + k2] = yr;
-                sim[lane * 33 + k2] = yi;
+                sc[lane * 33 + k2] = make_float2(re[p] * w.x - im[p] * w.y, re[p] * w.y + im[p] * w.x);
             }
             __syncwarp();
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1) {     // lane = k2, register = n1
-                re[n1] = sre[n1 * 33 + lane];
-                im[n1] = sim[n1 * 33 + lane];
+                const float2 v = sc[n1 * 33 + lane];
+                re[n1] = v.x;
+                im[n1] = v.y;
             }
-            fft32(re, im);   // register p: X[32 k1 + k2], k1 = bitrev(p), k2 = lane
-            __syncwarp();
-#pragma unroll
-            for (int p = 0; p < 32; ++p) {
-                const int k1 = bitrev5(p);
-                sre[k1 * 33 + lane] = re[p];
-                sim[k1 * 33 + lane] = im[p];
-            }
-            __syncwarp();
-            // power spectra of the two real frames for bins k = 32 k1 + lane, k1 < 16 (and k = 512 on lane 0)
-            float pa[17], pb[17];
+            fft32(re, im);   // register p: Z[32 k1 + k2], k1 = bitrev(p), k2 = lane
+            __syncwarp();    // all lanes have read the transposed tile: the scratch can hold the power spectra now
+            // Z = A + i B with A, B the (Hermitian) spectra of the two real frames: the partner bin Z[1024 - k] lives in lane
+            // (32 - lane) & 31, register k1' = 31 - k1 (lane 0: its own register (32 - k1) & 31) -> one shuffle per value
             const int lp = (32 - lane) & 31;
 #pragma unroll
-            for (int p = 0; p < 32; ++p) {
-                const int k1 = bitrev5(p);
-                if (k1 < 16) {
-                    const int k1p = (lane == 0) ? ((32 - k1) & 31) : (31 - k1);
-                    const float qr = sre[k1p * 33 + lp], qi = sim[k1p * 33 + lp];   // X[1024 - k]
-                    const float ar = re[p] + qr, ai = im[p] - qi;     // 2 A[k]
-                    const float br = im[p] + qi, bi = qr - re[p];     // 2 B[k]
-                    pa[k1] = 0.25f * (ar * ar + ai * ai);
-                    pb[k1] = 0.25f * (br * br + bi * bi);
-                }
-                if (k1 == 16) {   // k = 512 lives on lane 0; X[512] pairs with itself
-                    pa[16] = re[p] * re[p];
-                    pb[16] = im[p] * im[p];
-                }
-            }
-            __syncwarp();
-            float* spa = sre;            // 520 floats per frame
-            float* spb = sre + 520;
-#pragma unroll
             for (int k1 = 0; k1 < 16; ++k1) {
-                spa[32 * k1 + lane] = pa[k1];
-                spb[32 * k1 + lane] = pb[k1];
+                constexpr int dummy = 0; (void)dummy;
+                const int p = bitrev5(k1), pq = bitrev5(31 - k1), pq0 = bitrev5((32 - k1) & 31);
+                float qr = __shfl_sync(0xffffffffu, re[pq], lp), qi = __shfl_sync(0xffffffffu, im[pq], lp);
+                if (lane == 0) { qr = re[pq0]; qi = im[pq0]; }
+                const float ar = re[p] + qr, ai = im[p] - qi;     // 2 A[k]
+                const float br = im[p] + qi, bi = qr - re[p];     // 2 B[k]
+                sc[32 * k1 + lane] = make_float2(0.25f * (ar * ar + ai * ai), 0.25f * (br * br + bi * bi));
             }
-            if (lane == 0) { spa[512] = pa[16]; spb[512] = pb[16]; }
+            if (lane == 0) {   // k = 512 pairs with itself
+                const int p16 = bitrev5(16);
+                sc[512] = make_float2(re[p16] * re[p16], im[p16] * im[p16]);
+            }
             __syncwarp();
-            // sparse mel projection: this lane owns bands `lane` and `63 - lane`
+            // sparse mel projection: this lane owns bands `lane` and `63 - lane` of both frames
 #pragma unroll
             for (int hm = 0; hm < 2; ++hm) {
                 const int m = hm == 0 ? lane : (kMels - 1 - lane);
                 const int ks = s_mel_start[m], kl = s_mel_start[kMels + m];
                 const float* w = s_melw + s_mel_start[2 * kMels + m];
+                const float2* pp = sc + ks;
                 float ma = 0.f, mb = 0.f;
+#pragma unroll 4
                 for (int t = 0; t < kl; ++t) {
                     const float wt = w[t];
-                    ma = fmaf(wt, spa[ks + t], ma);
-                    mb = fmaf(wt, spb[ks + t], mb);
+                    const float2 pv = pp[t];
+                    ma = fmaf(wt, pv.x, ma);
+                    mb = fmaf(wt, pv.y, mb);
                 }
                 float la = logf(ma + kF32Eps), lb = logf(mb + kF32Eps);
                 if (a.apply_norm) { la = (la - a.norm_mean) * a.inv_std; lb = (lb - a.norm_mean) * a.inv_std; }
                 s_out[m * (kTileFrames + 1) + fa] = la;
                 s_out[m * (kTileFrames + 1) + fb] = lb;
             }
-            __syncwarp();
         }
     }
     __syncthreads();
@@ -243,11 +264,22 @@ __device__ __forceinline__ float cubic2(float x) {   // 1 < |x| < 2
     return ((-0.75f * x - 5.0f * -0.75f) * x + 8.0f * -0.75f) * x - 4.0f * -0.75f;
 }
 
-__global__ void __launch_bounds__(256) views_kernel(const abt_views_args a) {
-    extern __shared__ float smem[];
-    float* canvas = smem;                                     // canvas_h * canvas_w
-    float* coef = canvas + a.canvas_h * a.canvas_w;           // (out_w + out_h) * 4 coefficients
-    int* tap = reinterpret_cast<int*>(coef + (a.out_w + a.out_h) * 4);   // (out_w + out_h) * 4 clamped taps
+constexpr int kViewThreads = 384;
+
+// One CTA per (clip, view).  Three phases over shared memory:
+//   1. the crop rows of the virtual canvas: log-mixup-exp of x with its partner inside the pasted region, zeros outside
+//      (every canvas element the taps can touch is written exactly once; float4 global loads);
+//   2. horizontal cubic pass  H[y][ox] = sum_c canvas[y][tx_c(ox)] cx_c(ox)   for the crop rows only;
+//   3. vertical cubic pass + fader, coalesced stores.
+// ATen's upsample_bicubic2d interpolates along x inside each of the 4 tap rows and then along y, so the separable form
+// performs the same arithmetic in the same order with 8 instead of 16 taps per output.  A thread keeps its output column:
+// the x taps / coefficients live in registers.
+__global__ void __launch_bounds__(kViewThreads) views_kernel(const abt_views_args a) {
+    extern __shared__ __align__(16) float smem[];
+    float* canvas = smem;                                               // canvas_h * canvas_w
+    float* hbuf = canvas + a.canvas_h * a.canvas_w;                     // canvas_h * out_w (rows of the crop)
+    float4* coef = reinterpret_cast<float4*>(hbuf + a.canvas_h * a.out_w);   // out_w + out_h
+    int4* tap = reinterpret_cast<int4*>(coef + (a.out_w + a.out_h));    // out_w + out_h (clamped taps, canvas coordinates)
     const int clip = blockIdx.x, view = blockIdx.y;
     const int tid = threadIdx.x;
     const int pstride = a.param_stride > 0 ? a.param_stride : a.n_views;
@@ -259,29 +291,42 @@ __global__ void __launch_bounds__(256) views_kernel(const abt_views_args a) {
     if ((p.flags & 1) && p.z_kind == 2) z = a.x + (long long)(a.x_slot ? a.x_slot[p.z_index] : p.z_index) * a.x_slot_stride;
 
     const int y0 = (a.canvas_h - a.in_h) / 2, x0 = (a.canvas_w - a.in_w) / 2;
-    for (int idx = tid; idx < a.canvas_h * a.canvas_w; idx += blockDim.x) canvas[idx] = 0.f;
-    __syncthreads();
-    // log-mixup-exp into the centre of the virtual canvas (augmentations.py:43-48, :81-85)
-    const int n_in = a.in_h * a.in_w;
-    for (int idx = tid * 4; idx < n_in; idx += blockDim.x * 4) {
-        float4 xv = *reinterpret_cast<const float4*>(x + idx);
-        float v[4] = {xv.x, xv.y, xv.z, xv.w};
-        if (z != nullptr) {
-            const float4 zv = *reinterpret_cast<const float4*>(z + idx);
-            const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
-#pragma unroll
-            // fast exp2/log2 (MUFU): relative error ~1e-6, far inside the 1e-3 tolerance of the views
-            for (int k = 0; k < 4; ++k) v[k] = __logf(p.w_x * __expf(v[k]) + p.w_z * __expf(zz[k]) + kF32Eps);
+    const bool rrc = (p.flags & 2) != 0;
+    const int ci = rrc ? p.i : y0, cj = rrc ? p.j : x0, chh = rrc ? p.h : a.in_h, cww = rrc ? p.w : a.in_w;
+
+    // ---- phase 1: canvas rows [ci, ci + chh)   (augmentations.py:43-48, :81-85)
+    if (((a.canvas_w | x0 | a.in_w) & 3) == 0) {
+        const int g_per_row = a.canvas_w >> 2;
+        for (int g = tid; g < chh * g_per_row; g += kViewThreads) {
+            const int r = ci + g / g_per_row, col = (g % g_per_row) << 2;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r >= y0 && r < y0 + a.in_h && col >= x0 && col < x0 + a.in_w) {
+                const int e = (r - y0) * a.in_w + (col - x0);
+                v = __ldg(reinterpret_cast<const float4*>(x + e));
+                if (z != nullptr) {
+                    const float4 zv = __ldg(reinterpret_cast<const float4*>(z + e));
+                    // fast exp2/log2 (MUFU): relative error ~1e-6, far inside the 1e-3 tolerance of the views
+                    v.x = __logf(p.w_x * __expf(v.x) + p.w_z * __expf(zv.x) + kF32Eps);
+                    v.y = __logf(p.w_x * __expf(v.y) + p.w_z * __expf(zv.y) + kF32Eps);
+                    v.z = __logf(p.w_x * __expf(v.z) + p.w_z * __expf(zv.z) + kF32Eps);
+                    v.w = __logf(p.w_x * __expf(v.w) + p.w_z * __expf(zv.w) + kF32Eps);
+                }
+            }
+            *reinterpret_cast<float4*>(canvas + r * a.canvas_w + col) = v;
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int e = idx + k, r = e / a.in_w, c = e % a.in_w;
-            canvas[(y0 + r) * a.canvas_w + x0 + c] = v[k];
+    } else {
+        for (int g = tid; g < chh * a.canvas_w; g += kViewThreads) {
+            const int r = ci + g / a.canvas_w, col = g % a.canvas_w;
+            float v = 0.f;
+            if (r >= y0 && r < y0 + a.in_h && col >= x0 && col < x0 + a.in_w) {
+                const int e = (r - y0) * a.in_w + (col - x0);
+                v = __ldg(x + e);
+                if (z != nullptr) v = __logf(p.w_x * __expf(v) + p.w_z * __expf(__ldg(z + e)) + kF32Eps);
+            }
+            canvas[r * a.canvas_w + col] = v;
         }
     }
     // bicubic tables (ATen upsample_bicubic2d, align_corners=True): src = dst * (in-1)/(out-1)
-    const bool rrc = (p.flags & 2) != 0;
-    const int ci = rrc ? p.i : y0, cj = rrc ? p.j : x0, chh = rrc ? p.h : a.in_h, cww = rrc ? p.w : a.in_w;
     if (tid < a.out_w + a.out_h) {
         const bool is_x = tid < a.out_w;
         const int o = is_x ? tid : tid - a.out_w;
@@ -291,39 +336,46 @@ __global__ void __launch_bounds__(256) views_kernel(const abt_views_args a) {
         const float fl = floorf(pos);
         const float t = pos - fl;
         const int base = (int)fl;
-        const float c4[4] = {cubic2(t + 1.0f), cubic1(t), cubic1(1.0f - t), cubic2(2.0f - t)};
+        int sidx[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            int s = base - 1 + k;
-            s = s < 0 ? 0 : (s > n_in_ax - 1 ? n_in_ax - 1 : s);
-            tap[tid * 4 + k] = s + (is_x ? cj : ci);
-            coef[tid * 4 + k] = c4[k];
+            int sk = base - 1 + k;
+            sk = sk < 0 ? 0 : (sk > n_in_ax - 1 ? n_in_ax - 1 : sk);
+            sidx[k] = sk + (is_x ? cj : 0);          // x taps in canvas columns, y taps relative to the crop's first row
+        }
+        tap[tid] = make_int4(sidx[0], sidx[1], sidx[2], sidx[3]);
+        coef[tid] = make_float4(cubic2(t + 1.0f), cubic1(t), cubic1(1.0f - t), cubic2(2.0f - t));
+    }
+    __syncthreads();
+    // ---- phase 2: horizontal pass over the crop rows; thread = (output column, row group)
+    const int n_groups = kViewThreads / a.out_w;
+    const int ox = tid % a.out_w, grp = tid / a.out_w;
+    const bool active = grp < n_groups;
+    if (active) {
+        const int4 tx = tap[ox];
+        const float4 cx = coef[ox];
+        for (int yy = grp; yy < chh; yy += n_groups) {
+            const float* row = canvas + (ci + yy) * a.canvas_w;
+            hbuf[yy * a.out_w + ox] = row[tx.x] * cx.x + row[tx.y] * cx.y + row[tx.z] * cx.z + row[tx.w] * cx.w;
         }
     }
     __syncthreads();
-    // fader: torch.linspace(head, tail, T) evaluated from both ends with one rounding (fma)
-    const bool fade = (p.flags & 4) != 0;
-    const float step = a.out_w > 1 ? (p.tail - p.head) / (float)(a.out_w - 1) : 0.f;
-    float* out = a.outs[view] + (size_t)clip * a.out_h * a.out_w;
-    const int n_out = a.out_h * a.out_w;
-    for (int idx = tid; idx < n_out; idx += blockDim.x) {
-        const int oy = idx / a.out_w, ox = idx % a.out_w;
-        const int* tx = tap + ox * 4;
-        const float* cx = coef + ox * 4;
-        const int* ty = tap + (a.out_w + oy) * 4;
-        const float* cy = coef + (a.out_w + oy) * 4;
-        float acc = 0.f;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const float* row = canvas + ty[r] * a.canvas_w;
-            const float hsum = row[tx[0]] * cx[0] + row[tx[1]] * cx[1] + row[tx[2]] * cx[2] + row[tx[3]] * cx[3];
-            acc += hsum * cy[r];
+    // ---- phase 3: vertical pass + fader (torch.linspace(head, tail, T) evaluated from both ends with one rounding)
+    if (active) {
+        const bool fade = (p.flags & 4) != 0;
+        const float step = a.out_w > 1 ? (p.tail - p.head) / (float)(a.out_w - 1) : 0.f;
+        const float fv = !fade ? 0.f : ((ox < a.out_w / 2) ? fmaf(step, (float)ox, p.head) : fmaf(-step, (float)(a.out_w - 1 - ox), p.tail));
+        float* out = a.outs[view] + (size_t)clip * a.out_h * a.out_w;
+        for (int oy = grp; oy < a.out_h; oy += n_groups) {
+            const int4 ty = tap[a.out_w + oy];
+            const float4 cy = coef[a.out_w + oy];
+            float acc = 0.f;
+            acc += hbuf[ty.x * a.out_w + ox] * cy.x;
+            acc += hbuf[ty.y * a.out_w + ox] * cy.y;
+            acc += hbuf[ty.z * a.out_w + ox] * cy.z;
+            acc += hbuf[ty.w * a.out_w + ox] * cy.w;
+            out[oy * a.out_w + ox] = fade ? acc + fv : acc;
         }
-        if (fade) {
-            const float s = (ox < a.out_w / 2) ? fmaf(step, (float)ox, p.head) : fmaf(-step, (float)(a.out_w - 1 - ox), p.tail);
-            acc += s;
-        }
-        out[idx] = acc;
     }
 }
 
@@ -585,7 +637,8 @@ extern "C" int abt_views_fwd(const abt_views_args* a, abt_stream_t stream) {
     if (a->out_h < 1 || a->out_w < 1 || a->out_h + a->out_w > 256) return set_error(ABT_ERR_ARG, "out_h + out_w must be in [2, 256]");
     if ((a->x_slot_stride % 4) != 0 || (a->bank_slot_stride % 4) != 0) return set_error(ABT_ERR_ARG, "slot strides must be multiples of 4 floats");
     if (int rc = check_device_sm100()) return rc;
-    const size_t smem = sizeof(float) * ((size_t)a->canvas_h * a->canvas_w + (size_t)(a->out_w + a->out_h) * 4) + sizeof(int) * (size_t)(a->out_w + a->out_h) * 4;
+    if (a->out_w > kViewThreads) return set_error(ABT_ERR_ARG, "out_w must be <= %d", kViewThreads);
+    const size_t smem = sizeof(float) * ((size_t)a->canvas_h * a->canvas_w + (size_t)a->canvas_h * a->out_w) + 32 * (size_t)(a->out_w + a->out_h);
     if (smem > 200 * 1024) return set_error(ABT_ERR_ARG, "canvas too large for shared memory");
     static size_t smem_set = 48 * 1024;
     if (smem > smem_set) {
@@ -593,7 +646,7 @@ extern "C" int abt_views_fwd(const abt_views_args* a, abt_stream_t stream) {
         smem_set = smem;
     }
     dim3 grid(a->n_clips, a->n_views);
-    views_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    views_kernel<<<grid, kViewThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
     count_launch();
     ABT_CUDA_OK(cudaGetLastError());
     return 0;

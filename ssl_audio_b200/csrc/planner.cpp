@@ -251,3 +251,34 @@ extern "C" int abt_planner_plan_batch_packed(abt_planner* p, int n_clips, int ti
     return abt_planner_plan_batch(p, n_clips, time_crop_range, wav_crop_range, reinterpret_cast<int32_t*>(b + o1),
                                   reinterpret_cast<int32_t*>(b + o2), reinterpret_cast<abt_view_params*>(b), reinterpret_cast<int32_t*>(b + o3));
 }
+
+// Plan one batch against the INTERPRETER's global generators in place: np_state points at numpy's legacy
+// `struct { uint32_t key[624]; int pos; }` (may be NULL if no numpy draw can happen), py_index / py_key at the index and the
+// 624 state words of CPython's `random` instance (may be NULL likewise).  One call instead of set-state / plan / get-state.
+extern "C" int abt_planner_plan_batch_global(abt_planner* p, int n_clips, int time_crop_range, int wav_crop_range, void* np_state,
+                                             int32_t* py_index, uint32_t* py_key, void* out, size_t out_bytes) {
+    if (p == nullptr) return abt::set_error(ABT_ERR_ARG, "planner is null");
+    struct NpState { uint32_t key[624]; int pos; };
+    NpState* ns = static_cast<NpState*>(np_state);
+    if (ns != nullptr) {
+        if (ns->pos < 0 || ns->pos > 624) return abt::set_error(ABT_ERR_ARG, "bad numpy MT19937 position %d", ns->pos);
+        std::memcpy(p->np_rng.key, ns->key, sizeof(ns->key));
+        p->np_rng.pos = ns->pos;
+    }
+    if (py_index != nullptr && py_key != nullptr) {
+        if (*py_index < 0 || *py_index > 624) return abt::set_error(ABT_ERR_ARG, "bad CPython MT19937 index %d", *py_index);
+        std::memcpy(p->py_rng.key, py_key, sizeof(p->py_rng.key));
+        p->py_rng.pos = *py_index;
+    }
+    const int rc = abt_planner_plan_batch_packed(p, n_clips, time_crop_range, wav_crop_range, out, out_bytes);
+    if (rc != 0) return rc;
+    if (ns != nullptr) {
+        std::memcpy(ns->key, p->np_rng.key, sizeof(ns->key));
+        ns->pos = p->np_rng.pos;
+    }
+    if (py_index != nullptr && py_key != nullptr) {
+        std::memcpy(py_key, p->py_rng.key, sizeof(p->py_rng.key));
+        *py_index = p->py_rng.pos;
+    }
+    return 0;
+}

@@ -112,7 +112,7 @@ class _BTLossFn(torch.autograd.Function):
                                              momentum=bn.momentum if bn.momentum is not None else 0.1,
                                              running_mean=rm, running_var=rv, need_dz1=need1, need_dz2=need2)
         if track:
-            bn.num_batches_tracked += 2     # BatchNorm is applied to z1 and then to z2 (utils/loss.py:17)
+            module._pending_batches += 2    # BatchNorm is applied to z1 and then to z2 (utils/loss.py:17); flushed lazily
         ctx.save_for_backward(dz1 if dz1 is not None else torch.empty(0, device=z1.device),
                               dz2 if dz2 is not None else torch.empty(0, device=z1.device))
         ctx.has = (dz1 is not None, dz2 is not None)
@@ -138,6 +138,15 @@ class BarlowTwinsLoss(nn.Module):
         # multi-GPU only: local gradients are multiplied by this; None = world_size, which cancels DDP's gradient
         # averaging so that R-rank and single-process runs give the same parameter update
         self.grad_scale = None
+        # `bn.num_batches_tracked` is bookkeeping only (momentum is fixed): count on the host and fold the count into the
+        # buffer when somebody looks at it (state_dict / explicit flush) instead of launching a kernel every step
+        self._pending_batches = 0
+        self.register_state_dict_pre_hook(lambda module, prefix, keep_vars: module.flush_counters())
+
+    def flush_counters(self) -> None:
+        if self._pending_batches:
+            self.bn.num_batches_tracked += self._pending_batches
+            self._pending_batches = 0
 
     def forward_loss(self, z1, z2):
         if z1.shape[-1] != self.cfg.projector_out_dim:
@@ -151,13 +160,15 @@ class BarlowTwinsLoss(nn.Module):
         # pairing loop of the reference (utils/loss.py:32-48)
         student_out = student_output.chunk(self.ncrops - (2 - ngcrops_each))
         teacher_out = teacher_output.chunk(ngcrops_each)
-        total_loss = 0
+        total_loss = None
         n_loss_terms = 0
         for q in range(len(teacher_out)):
             for v in range(len(student_out)):
                 if len(teacher_out) > 1 and q == v:
                     continue
-                total_loss = total_loss + self.forward_loss(teacher_out[q], student_out[v])
+                term = self.forward_loss(teacher_out[q], student_out[v])
+                total_loss = term if total_loss is None else total_loss + term
                 n_loss_terms += 1
-        total_loss = total_loss / n_loss_terms
+        if n_loss_terms > 1:                      # (0 + x) / 1 == x: no arithmetic (and no launches) for the single-term case
+            total_loss = total_loss / n_loss_terms
         return total_loss

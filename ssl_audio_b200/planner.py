@@ -35,6 +35,30 @@ def _numpy_global_state_address() -> int:
     return int(bitgen.ctypes.state_address)
 
 
+_PYRANDOM_ADDR = None   # (address of `int index`, address of `uint32_t state[624]`) inside random._inst, or False
+
+
+def _pyrandom_state_address():
+    """CPython keeps the Mersenne Twister of the `random` module inside the `random._inst` object as
+    `struct { PyObject_HEAD; int index; uint32_t state[624]; }` (Modules/_randommodule.c).  Reading and writing it in place
+    saves two 625-element tuple conversions per batch.  The layout is VERIFIED against random.getstate() before it is
+    trusted; on any mismatch (other interpreter, other layout) the slow getstate()/setstate() path is used."""
+    global _PYRANDOM_ADDR
+    if _PYRANDOM_ADDR is None:
+        _PYRANDOM_ADDR = False
+        try:
+            inst = _pyrandom._inst
+            base = id(inst) + C.sizeof(C.c_ssize_t) + C.sizeof(C.c_void_p)
+            st = inst.getstate()[1]
+            idx = C.c_int.from_address(base).value
+            key = (C.c_uint32 * 624).from_address(base + 4)
+            if idx == st[624] and tuple(key) == tuple(st[:624]):
+                _PYRANDOM_ADDR = (base, base + 4)
+        except Exception:
+            _PYRANDOM_ADDR = False
+    return _PYRANDOM_ADDR
+
+
 @dataclass
 class BatchPlan:
     starts: np.ndarray       # (B,) int32 time-crop start per clip, -1 if none was drawn
@@ -145,24 +169,20 @@ class ViewPlanner:
             buf = st.host_np[slot]
         else:
             buf = np.empty(max(nbytes, 16), dtype=np.uint8)
-        if use_np:
-            # numpy's global legacy generator, accessed in place: its bit generator exposes the address of
-            # `struct { uint32_t key[624]; int pos; }` (numpy/random/src/mt19937/mt19937.h)
-            np_addr = _numpy_global_state_address()
-            np_pos = C.c_int.from_address(np_addr + 624 * 4)
-            _lib.check(lib.abt_planner_set_numpy_state(h, np_addr, int(np_pos.value)))
-        if use_py:
+        np_addr = _numpy_global_state_address() if use_np else None
+        py_addr = _pyrandom_state_address() if use_py else None
+        if use_py and not py_addr:
+            # unknown interpreter layout: go through random.getstate() / setstate()
             pst = _pyrandom.getstate()
             pkey = np.array(pst[1][:624], dtype=np.uint32)
-            _lib.check(lib.abt_planner_set_pyrandom_state(h, pkey.ctypes.data, int(pst[1][624])))
-        _lib.check(lib.abt_planner_plan_batch_packed(h, n_clips, int(time_crop_range), int(wav_crop_range), buf.ctypes.data, buf.nbytes))
-        pos = C.c_int()
-        if use_np:
-            _lib.check(lib.abt_planner_get_numpy_state(h, np_addr, C.byref(pos)))
-            np_pos.value = pos.value
-        if use_py:
-            _lib.check(lib.abt_planner_get_pyrandom_state(h, self._key.ctypes.data, C.byref(pos)))
-            _pyrandom.setstate((pst[0], tuple(self._key.tolist()) + (pos.value,), pst[2]))
+            pidx = C.c_int32(int(pst[1][624]))
+            _lib.check(lib.abt_planner_plan_batch_global(h, n_clips, int(time_crop_range), int(wav_crop_range), np_addr, C.addressof(pidx),
+                                                         pkey.ctypes.data, buf.ctypes.data, buf.nbytes))
+            _pyrandom.setstate((pst[0], tuple(pkey.tolist()) + (int(pidx.value),), pst[2]))
+        else:
+            _lib.check(lib.abt_planner_plan_batch_global(h, n_clips, int(time_crop_range), int(wav_crop_range), np_addr,
+                                                         py_addr[0] if py_addr else None, py_addr[1] if py_addr else None,
+                                                         buf.ctypes.data, buf.nbytes))
         nv = self.n_views
         params = buf[:48 * nv * n_clips].view(VIEW_DTYPE).reshape(n_clips, nv)
         starts = buf[o1.value:o1.value + 4 * n_clips].view(np.int32)
