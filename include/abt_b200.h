@@ -223,6 +223,10 @@ typedef struct {
 int abt_bt_workspace_bytes(int n_rows, int n_dims, int dtype, size_t* bytes);
 int abt_bt_loss_fwd_bwd(const abt_bt_args* args, abt_stream_t stream);
 
+/* backward of the loss scalar: the gradients were produced by the forward call; autograd's `grad_output` (a device scalar,
+ * e.g. the GradScaler factor) multiplies them in place.  a, b: (n_elems) of `dtype`, either may be NULL. */
+int abt_scale_inplace(void* a, void* b, size_t n_elems, int dtype, const float* scale_dev, abt_stream_t stream);
+
 /* Row-block form for the multi-GPU objective (replaces the D x D `torch.distributed.all_reduce(c)` of
  * utils/loss.py:20-21 with: all-gather of the embeddings -> this call -> all-to-all of the gradients -> 3-double
  * all-reduce).  zg1 / zg2 are the rank-ordered GLOBAL batches (n_rows = N_g); this rank owns dimensions
@@ -249,6 +253,49 @@ typedef struct {
 
 int abt_bt_rows_workspace_bytes(int n_rows, int n_dims, int row_count, int dtype, size_t* bytes);
 int abt_bt_loss_rows_fwd_bwd(const abt_bt_rows_args* args, abt_stream_t stream);
+
+/* Multi-GPU objective as BASELINE.json:north_star words it (one process per GPU; the collectives themselves are NCCL calls made by
+ * the host between these entry points, ssl_audio_b200/dist.py):
+ *   1. abt_bt_dist_stats_local   local rows -> 7 numbers per column (shifted sums + shifts) at workspace + layout.pack_local
+ *      [all-gather of the packs (7 D floats per rank) into workspace + layout.pack_all]
+ *   2. abt_bt_dist_normalize     global statistics (combined in double), BatchNorm running-stat update, on-diagonal loss, and the
+ *                                fp16 STANDARDISED local rows written into this rank's slot of the gather buffers (layout.zh1 / zh2)
+ *      [in-place all-gather of the standardised embeddings: (world * n_local, n_dims) fp16 per view]
+ *   3. abt_bt_dist_rows_fwd_bwd  rows [row_begin, row_begin + row_count) of C and C^T on the tensor cores from the gathered
+ *                                standardised embeddings, their loss terms, and d loss / d z of ALL samples for those dimensions
+ *      [all-to-all of the gradient slices, 2-double all-reduce of the loss]
+ * The three calls of one step share ONE workspace (abt_bt_dist_layout_query gives its size and the offsets the host needs). */
+typedef struct {
+    size_t total_bytes;
+    size_t zh1, zh2;          /* (world * n_local, n_dims) fp16 gather buffers; rank r owns rows [r * n_local, (r + 1) * n_local) */
+    size_t pack_local;        /* pack_floats floats */
+    size_t pack_all;          /* world * pack_floats floats */
+    size_t pack_floats;       /* 7 * n_dims */
+} abt_bt_dist_layout;
+
+typedef struct {
+    int32_t dtype;            /* dtype of dzr1 / dzr2 (the embeddings' dtype) */
+    int32_t n_local, world, n_dims;
+    int32_t row_begin, row_count;
+    float alpha, lambda;
+    int32_t hsic;
+    float grad_scale;
+    int32_t need_grad_mask;   /* gradients wanted from the whole step */
+    int32_t phase;            /* 0: everything in one call.  1: statistics hand-over, CORR and the dz1 gradient pass; 2: only the dz2
+                               * gradient pass (after a phase-1 call) -- lets the host overlap the all-to-all of dz1 with the dz2 GEMM */
+    double* loss_parts;       /* device, 3 doubles as in abt_bt_rows_args (written by phases 0 and 1) */
+    void* dzr1;               /* (world * n_local, row_count) compact */
+    void* dzr2;
+    void* workspace;
+    size_t workspace_bytes;
+} abt_bt_dist_args;
+
+int abt_bt_dist_layout_query(int n_local, int world, int n_dims, int row_count, abt_bt_dist_layout* out);
+int abt_bt_dist_stats_local(const void* z1, const void* z2, int dtype, int n_local, int world, int n_dims, int row_count, void* workspace,
+                            abt_stream_t stream);
+int abt_bt_dist_normalize(const void* z1, const void* z2, int dtype, int n_local, int world, int rank, int n_dims, int row_count, float eps,
+                          float momentum, float* running_mean, float* running_var, void* workspace, abt_stream_t stream);
+int abt_bt_dist_rows_fwd_bwd(const abt_bt_dist_args* args, abt_stream_t stream);
 
 /* ===================================================================================== *
  *  Debug hooks (not part of the drop-in surface; used by tools/gpu_diag.py)

@@ -75,6 +75,20 @@ class BtRowsArgs(C.Structure):
     ]
 
 
+class BtDistLayout(C.Structure):
+    _fields_ = [("total_bytes", C.c_size_t), ("zh1", C.c_size_t), ("zh2", C.c_size_t), ("pack_local", C.c_size_t),
+                ("pack_all", C.c_size_t), ("pack_floats", C.c_size_t)]
+
+
+class BtDistArgs(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("n_local", C.c_int32), ("world", C.c_int32), ("n_dims", C.c_int32), ("row_begin", C.c_int32),
+        ("row_count", C.c_int32), ("alpha", C.c_float), ("lambda_", C.c_float), ("hsic", C.c_int32), ("grad_scale", C.c_float),
+        ("need_grad_mask", C.c_int32), ("phase", C.c_int32), ("loss_parts", C.c_void_p), ("dzr1", C.c_void_p), ("dzr2", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol of include/abt_b200.h
 SIGNATURES = {
     "abt_version": (C.c_int, []),
@@ -109,8 +123,14 @@ SIGNATURES = {
     "abt_planner_plan_batch_global": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "abt_bt_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "abt_bt_loss_fwd_bwd": (C.c_int, [C.POINTER(BtArgs), C.c_void_p]),
+    "abt_scale_inplace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "abt_bt_rows_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "abt_bt_loss_rows_fwd_bwd": (C.c_int, [C.POINTER(BtRowsArgs), C.c_void_p]),
+    "abt_bt_dist_layout_query": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(BtDistLayout)]),
+    "abt_bt_dist_stats_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "abt_bt_dist_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "abt_bt_dist_rows_fwd_bwd": (C.c_int, [C.POINTER(BtDistArgs), C.c_void_p]),
     "abt_debug_set": (C.c_int, [C.c_int, C.c_int]),
     "abt_debug_launch_count": (C.c_longlong, [C.c_int]),
     "abt_debug_timing": (C.c_int, [C.c_int]),

@@ -46,6 +46,7 @@ enum StatSlot {
     S_MU1 = 0, S_R1, S_MU2, S_R2, S_CDIAG,
     S_NMU1, S_RHO1,   // -N * mu1, r1 / N : row constants of the rank-1 batch-norm correction (rows = view-1 dims)
     S_NMU2, S_RHO2,   // same with the views swapped (row-block mode, C^T pass)
+    S_ZERO, S_ONE, S_INVN,   // constants 0, 1, 1/N: the CORR epilogue on already standardised operands (multi-GPU) is c = S / N
     S_COUNT
 };
 // accumulators zeroed at the start of every call (float arrays of length D each, after the 256-byte misc block)
@@ -224,6 +225,137 @@ __global__ void __launch_bounds__(256) bt_rowsum_kernel(const __nv_bfloat16* __r
     }
 }
 
+// in-place gradient scaling for autograd's backward: dz *= *scale (both views in one launch, 16-byte accesses)
+template <typename T>
+__global__ void __launch_bounds__(256) bt_scale_kernel(T* __restrict__ a, T* __restrict__ b, size_t n_vec, const float* __restrict__ scale) {
+    const float s = __ldg(scale);
+    constexpr int E = 16 / sizeof(T);
+    T* base = blockIdx.y == 0 ? a : b;
+    if (base == nullptr) return;
+    uint4* p4 = reinterpret_cast<uint4*>(base);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 v = p4[i];
+        T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+        for (int k = 0; k < E; k += 2) {
+            const float2 f = Ld2<T>::ld(e + k);
+            Ld2<T>::st(e + k, f.x * s, f.y * s);
+        }
+        p4[i] = v;
+    }
+}
+
+// same for already standardised fp16 embeddings
+__global__ void __launch_bounds__(256) bt_rowsum_zh_kernel(const __half* __restrict__ zh, int N, int D, float* __restrict__ out) {
+    __shared__ float red[8];
+    const int n = blockIdx.x;
+    float acc = 0.f;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) acc += __half2float(zh[(size_t)n * D + c]);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        out[n] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU statistics: every rank reduces its LOCAL rows to 7 numbers per column (5 shifted sums + the two shifts),
+// the ranks all-gather those (7 D floats each), and every rank combines them into the GLOBAL batch statistics
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bt_stat_pack_kernel(const T* __restrict__ z1, const T* __restrict__ z2, int D, int n_splits,
+                                                           const float* __restrict__ partials, float* __restrict__ pack) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= D) return;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        float t = 0.f;
+        for (int sp = 0; sp < n_splits; ++sp) t += partials[((size_t)sp * 5 + k) * D + c];
+        pack[(size_t)k * D + c] = t;
+    }
+    const float2 a = Ld2<T>::ld(z1 + (c & ~1)), b = Ld2<T>::ld(z2 + (c & ~1));
+    pack[(size_t)5 * D + c] = bf16_round((c & 1) ? a.y : a.x);
+    pack[(size_t)6 * D + c] = bf16_round((c & 1) ? b.y : b.x);
+}
+
+// packs: [world][7][D].  Combines the per-rank shifted sums in double (exact re-centring), writes the statistics arrays, the
+// BatchNorm running-stat update, the on-diagonal loss, and the fp16 standardised LOCAL rows (into this rank's slot of the
+// all-gather buffers).
+template <typename T>
+__global__ void __launch_bounds__(kColThreads) bt_normalize_global_kernel(const T* __restrict__ z1, const T* __restrict__ z2, int n_local, int world,
+                                                                          int D, int chunk, float eps, float momentum,
+                                                                          const float* __restrict__ packs, float* __restrict__ stats,
+                                                                          __half* __restrict__ zh1, __half* __restrict__ zh2,
+                                                                          float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                                          double* __restrict__ ondiag) {
+    __shared__ float colstat[4][kColsPerBlock];
+    __shared__ float on_red[2];
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int col = blockIdx.x * kColsPerBlock + lane * 2;
+    float on = 0.f;
+    if (threadIdx.x < kColsPerBlock) {
+        const int c = threadIdx.x, gc = blockIdx.x * kColsPerBlock + c;
+        if (gc < D) {
+            const double n = (double)n_local, Ng = (double)n_local * world;
+            double s1 = 0, s2 = 0;
+            for (int r = 0; r < world; ++r) {
+                const float* pk = packs + (size_t)r * 7 * D;
+                s1 += (double)pk[0 * D + gc] + n * (double)pk[5 * D + gc];
+                s2 += (double)pk[2 * D + gc] + n * (double)pk[6 * D + gc];
+            }
+            const double m1 = s1 / Ng, m2 = s2 / Ng;
+            double v1 = 0, v2 = 0, cv = 0;
+            for (int r = 0; r < world; ++r) {
+                const float* pk = packs + (size_t)r * 7 * D;
+                const double a1 = pk[0 * D + gc], q1 = pk[1 * D + gc], a2 = pk[2 * D + gc], q2 = pk[3 * D + gc], x12 = pk[4 * D + gc];
+                const double d1 = (double)pk[5 * D + gc] - m1, d2 = (double)pk[6 * D + gc] - m2;
+                v1 += q1 + 2.0 * d1 * a1 + n * d1 * d1;
+                v2 += q2 + 2.0 * d2 * a2 + n * d2 * d2;
+                cv += x12 + d2 * a1 + d1 * a2 + n * d1 * d2;
+            }
+            const float var1 = (float)fmax(v1 / Ng, 0.0), var2 = (float)fmax(v2 / Ng, 0.0);
+            const float mu1 = (float)m1, mu2 = (float)m2;
+            const float r1n = (float)(1.0 / sqrt((double)var1 + (double)eps)), r2n = (float)(1.0 / sqrt((double)var2 + (double)eps));
+            const float cd = (float)(cv / Ng) * r1n * r2n;
+            colstat[0][c] = mu1; colstat[1][c] = r1n; colstat[2][c] = mu2; colstat[3][c] = r2n;
+            if (blockIdx.y == 0) {
+                const float invN = (float)(1.0 / Ng);
+                stats[S_MU1 * D + gc] = mu1; stats[S_R1 * D + gc] = r1n;
+                stats[S_MU2 * D + gc] = mu2; stats[S_R2 * D + gc] = r2n;
+                stats[S_CDIAG * D + gc] = cd;
+                stats[S_ZERO * D + gc] = 0.f; stats[S_ONE * D + gc] = 1.f; stats[S_INVN * D + gc] = invN;
+                on = (cd - 1.0f) * (cd - 1.0f);
+                if (running_mean != nullptr) {
+                    const float unb = (Ng > 1.0) ? (float)(Ng / (Ng - 1.0)) : 1.0f;
+                    float rm = running_mean[gc], rv = running_var[gc];
+                    rm = (1.f - momentum) * rm + momentum * mu1; rv = (1.f - momentum) * rv + momentum * var1 * unb;
+                    rm = (1.f - momentum) * rm + momentum * mu2; rv = (1.f - momentum) * rv + momentum * var2 * unb;
+                    running_mean[gc] = rm; running_var[gc] = rv;
+                }
+            }
+        }
+        on = warp_sum(on);
+        if (lane == 0) on_red[threadIdx.x >> 5] = on;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.y == 0) atomicAdd(ondiag, (double)(on_red[0] + on_red[1]));
+    if (col < D) {
+        const float m1[2] = {colstat[0][lane * 2], colstat[0][lane * 2 + 1]}, q1r[2] = {colstat[1][lane * 2], colstat[1][lane * 2 + 1]};
+        const float m2[2] = {colstat[2][lane * 2], colstat[2][lane * 2 + 1]}, q2r[2] = {colstat[3][lane * 2], colstat[3][lane * 2 + 1]};
+        const int n0 = blockIdx.y * chunk, n1 = min(n_local, n0 + chunk);
+#pragma unroll 4
+        for (int n = n0 + rg; n < n1; n += kRowGroups) {
+            const size_t o = (size_t)n * D + col;
+            const float2 a2 = Ld2<T>::ld(z1 + o), b2 = Ld2<T>::ld(z2 + o);
+            Ld2<__half>::st(zh1 + o, (bf16_round(a2.x) - m1[0]) * q1r[0], (bf16_round(a2.y) - m1[1]) * q1r[1]);
+            Ld2<__half>::st(zh2 + o, (bf16_round(b2.x) - m2[0]) * q2r[0], (bf16_round(b2.y) - m2[1]) * q2r[1]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // 3./4. tcgen05 GEMM kernel (persistent, warp specialised)
 // ------------------------------------------------------------------------------------------
@@ -286,8 +418,9 @@ struct UmmaParams {
     double* loss_acc;
     // GRAD
     int io_dtype;                      // abt_dtype of dz
-    const __nv_bfloat16* zq1;          // (N, D) bf16 embeddings (the inputs, or their bf16 copies)
-    const __nv_bfloat16* zq2;
+    const void* zq1;                   // (N, D) 16-bit embeddings read by the epilogue: raw bf16 (zfmt 0) or standardised fp16 (zfmt 1)
+    const void* zq2;
+    int zfmt;
     const float* stats;                // StatSlot arrays
     const float* rs1; const float* rs2;   // HSIC: row sums of zh1 / zh2 over all dimensions
     float alpha, lambda, grad_scale;
@@ -323,8 +456,8 @@ template <> __device__ __forceinline__ void store_out<float>(float* p, float v) 
 template <typename T>
 __device__ __forceinline__ void grad_chunk(const uint32_t (&acc)[32], const UmmaParams& p, const PassCfg& pc, int row, int lrow, int n_base, int n_valid,
                                            float mu_s, float r_s, float mu_o, float r_o, float hs, float gd, float b) {
-    const __nv_bfloat16* zs = (pc.side == 0 ? p.zq1 : p.zq2) + row;
-    const __nv_bfloat16* zo = (pc.side == 0 ? p.zq2 : p.zq1) + row;
+    const unsigned short* zs = static_cast<const unsigned short*>(pc.side == 0 ? p.zq1 : p.zq2) + row;
+    const unsigned short* zo = static_cast<const unsigned short*>(pc.side == 0 ? p.zq2 : p.zq1) + row;
     const float* rso = pc.side == 0 ? p.rs2 : p.rs1;
     T* dz = static_cast<T*>(pc.dz) + lrow;
     const float rg = r_s * p.grad_scale;
@@ -338,8 +471,8 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&acc)[32], const Umma
         for (int u = 0; u < 16; ++u) {
             const int t = h * 16 + u;
             const size_t n = (size_t)(n_base + (t < n_valid ? t : 0));
-            zs_raw[u] = __ldg(reinterpret_cast<const unsigned short*>(zs + n * p.D));
-            zo_raw[u] = __ldg(reinterpret_cast<const unsigned short*>(zo + n * p.D));
+            zs_raw[u] = __ldg(zs + n * p.D);
+            zo_raw[u] = __ldg(zo + n * p.D);
             rsv[u] = p.hsic ? __ldg(rso + n) : 0.f;
         }
 #pragma unroll
@@ -347,8 +480,8 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&acc)[32], const Umma
             const int t = h * 16 + u;
             if (t < n_valid) {
                 const size_t n = (size_t)(n_base + t);
-                const float zhs = (__uint_as_float((uint32_t)zs_raw[u] << 16) - mu_s) * r_s;
-                const float zho = (__uint_as_float((uint32_t)zo_raw[u] << 16) - mu_o) * r_o;
+                const float zhs = p.zfmt ? __half2float(__ushort_as_half(zs_raw[u])) : (__uint_as_float((uint32_t)zs_raw[u] << 16) - mu_s) * r_s;
+                const float zho = p.zfmt ? __half2float(__ushort_as_half(zo_raw[u])) : (__uint_as_float((uint32_t)zo_raw[u] << 16) - mu_o) * r_o;
                 float g = fmaf(hs, __uint_as_float(acc[t]), gd * zho);
                 if (p.hsic) g = fmaf(hs, rsv[u] - zho, g);
                 store_out<T>(dz + n * pc.ld_dz, (g - zhs * b) * rg);
@@ -726,11 +859,11 @@ static TimingState g_timing;
 // Workspace layout.  `rows` = number of C rows this call materialises (D single-GPU, row_count in row-block mode);
 // `two_c` = a second C block for the transposed pass (row-block mode).
 struct WsLayout {
-    size_t misc, acc, stats, partials, rs1, rs2, zb1, zb2, zh1, zh2, c1, c2, total;
+    size_t misc, acc, stats, partials, keep, pack_local, pack_all, rs1, rs2, zb1, zb2, zh1, zh2, c1, c2, total;
     size_t zero_bytes;   // misc + acc: cleared at the start of every call
 };
 
-static WsLayout ws_layout(int N, int D, int rows, int dtype, bool two_c) {
+static WsLayout ws_layout(int N, int D, int rows, int dtype, bool two_c, int world = 0) {
     WsLayout L{};
     size_t off = 0;
     L.misc = off; off += 256;
@@ -738,6 +871,9 @@ static WsLayout ws_layout(int N, int D, int rows, int dtype, bool two_c) {
     L.zero_bytes = off;
     L.stats = off; off = align_up(off + sizeof(float) * S_COUNT * (size_t)D, 256);
     L.partials = off; off = align_up(off + sizeof(float) * 5 * kMaxRowSplits * (size_t)D, 256);
+    L.keep = off; off += 256;                                   // multi-GPU: on-diagonal loss sum kept between the calls of one step
+    L.pack_local = off; if (world > 0) off = align_up(off + sizeof(float) * 7 * (size_t)D, 256);
+    L.pack_all = off; if (world > 0) off = align_up(off + sizeof(float) * 7 * (size_t)D * world, 256);
     L.rs1 = off; off = align_up(off + sizeof(float) * (size_t)N, 256);
     L.rs2 = off; off = align_up(off + sizeof(float) * (size_t)N, 256);
     L.zb1 = off; if (dtype != ABT_DTYPE_BF16) off = align_up(off + 2 * (size_t)N * D, 256);
@@ -802,6 +938,8 @@ struct LossCall {
     int N, D;
     int row_begin, row_count;   // dimensions owned by this call (0, D single-GPU)
     bool rows_mode;             // compute the C^T row block with a second CORR pass instead of reading C transposed
+    bool zh_mode;               // z1 / z2 are standardised fp16 embeddings and the statistics are already in the workspace (multi-GPU)
+    int phase;                  // 0 = whole evaluation; 1 = everything except the dz2 GRAD pass; 2 = only the dz2 GRAD pass (after a phase-1 call)
     float alpha, lambda; int hsic; float eps, momentum, grad_scale; int need;
     float* loss_out;            // single-GPU only
     double* loss_parts_out;     // row-block mode: 3 doubles copied out (off-diag sum c^2, off-diag sum c, on-diag sum)
@@ -836,36 +974,49 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
     const bool timed = g_timing.enabled && g_timing.count < kTimingRing;
     cudaEvent_t* tev = timed ? g_timing.ev[g_timing.count] : nullptr;
     if (timed) cudaEventRecord(tev[0], stream);
-    cudaMemsetAsync(ws + L.misc, 0, L.zero_bytes, stream);     // loss partial sums + row / column accumulators
+    const bool front = a.phase != 2;      // statistics + CORR belong to phases 0 and 1
+    if (front) cudaMemsetAsync(ws + L.misc, 0, L.zero_bytes, stream);     // loss partial sums + row / column accumulators
     // ---- statistics
-    int splits = (N + 127) / 128;
-    if (splits > kMaxRowSplits) splits = kMaxRowSplits;
-    const int chunk = (N + splits - 1) / splits;
-    splits = (N + chunk - 1) / chunk;
-    const dim3 sgrid(col_blocks, splits);
-    bt_colstat_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, chunk, partials, zb1, zb2);
-    bt_normalize_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, chunk, splits, a.eps,
-                                                              a.momentum, partials, stats, need != 0 ? zh1 : nullptr, need != 0 ? zh2 : nullptr,
-                                                              a.running_mean, a.running_var, loss_acc);
-    count_launch(2);
-    if (a.hsic && need != 0) {
-        bt_rowsum_kernel<<<N, 256, 0, stream>>>(zq1, N, D, stats + S_MU1 * D, stats + S_R1 * D, rs1);
-        bt_rowsum_kernel<<<N, 256, 0, stream>>>(zq2, N, D, stats + S_MU2 * D, stats + S_R2 * D, rs2);
+    if (!front) {
+    } else if (!a.zh_mode) {
+        int splits = (N + 127) / 128;
+        if (splits > kMaxRowSplits) splits = kMaxRowSplits;
+        const int chunk = (N + splits - 1) / splits;
+        splits = (N + chunk - 1) / chunk;
+        const dim3 sgrid(col_blocks, splits);
+        bt_colstat_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, chunk, partials, zb1, zb2);
+        bt_normalize_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, chunk, splits, a.eps,
+                                                                  a.momentum, partials, stats, need != 0 ? zh1 : nullptr, need != 0 ? zh2 : nullptr,
+                                                                  a.running_mean, a.running_var, loss_acc);
         count_launch(2);
+        if (a.hsic && need != 0) {
+            bt_rowsum_kernel<<<N, 256, 0, stream>>>(zq1, N, D, stats + S_MU1 * D, stats + S_R1 * D, rs1);
+            bt_rowsum_kernel<<<N, 256, 0, stream>>>(zq2, N, D, stats + S_MU2 * D, stats + S_R2 * D, rs2);
+            count_launch(2);
+        }
+    } else {
+        // the statistics (and the on-diagonal loss sum) were produced by abt_bt_dist_normalize into this workspace
+        cudaMemcpyAsync(loss_acc + 2, ws + L.keep, sizeof(double), cudaMemcpyDeviceToDevice, stream);
+        if (a.hsic && need != 0) {
+            bt_rowsum_zh_kernel<<<N, 256, 0, stream>>>(static_cast<const __half*>(a.z1), N, D, rs1);
+            bt_rowsum_zh_kernel<<<N, 256, 0, stream>>>(static_cast<const __half*>(a.z2), N, D, rs2);
+            count_launch(2);
+        }
     }
 
     const int cg = g_cta_group == 1 ? 1 : 2;
     const int row_tiles = (RC + BM * cg - 1) / (BM * cg);
     // ---- CORR: C[rows, :] (and, in row-block mode, C^T[rows, :] with the views swapped)
     if (timed) cudaEventRecord(tev[1], stream);
-    {
+    if (front) {
         CUtensorMap m1, m2;
-        if (int rc = make_map_16(&m1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, zq1, N, D, 64, 64)) return rc;
-        if (int rc = make_map_16(&m2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, zq2, N, D, 64, 64)) return rc;
+        const CUtensorMapDataType odt = a.zh_mode ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        if (int rc = make_map_16(&m1, odt, a.zh_mode ? a.z1 : zq1, N, D, 64, 64)) return rc;
+        if (int rc = make_map_16(&m2, odt, a.zh_mode ? a.z2 : zq2, N, D, 64, 64)) return rc;
         UmmaParams p{};
         p.dc = g_desc;
         p.mode = 0; p.D = D; p.N = N;
-        p.bn = 256; p.ab_format = 1;
+        p.bn = 256; p.ab_format = a.zh_mode ? 0 : 1;
         p.tiles_m = row_tiles; p.tiles_n = (D + p.bn - 1) / p.bn;
         p.kblocks = (N + BK - 1) / BK;
         p.hsic = a.hsic; p.write_c = need != 0;
@@ -874,11 +1025,13 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         PassCfg c0{}, c1{};
         c0.a_mn = 1; c0.row0 = R0; c0.row_end = R0 + RC;
         c0.row_nmu = stats + S_NMU1 * D; c0.row_rho = stats + S_RHO1 * D; c0.col_mu = stats + S_MU2 * D; c0.col_r = stats + S_R2 * D;
+        if (a.zh_mode) { c0.row_nmu = stats + S_ZERO * D; c0.row_rho = stats + S_INVN * D; c0.col_mu = stats + S_ZERO * D; c0.col_r = stats + S_ONE * D; }
         c0.accumulate_loss = 1; c0.c_out = C1;
         c0.row_sq = (need & 1) ? accs + A_SQ1 * D : nullptr; c0.row_sum = accs + A_SUM1 * D;
         c0.col_sq = (!a.rows_mode && (need & 2)) ? accs + A_SQ2 * D : nullptr; c0.col_sum = accs + A_SUM2 * D;
         c1 = c0;
         c1.row_nmu = stats + S_NMU2 * D; c1.row_rho = stats + S_RHO2 * D; c1.col_mu = stats + S_MU1 * D; c1.col_r = stats + S_R1 * D;
+        if (a.zh_mode) { c1.row_nmu = c0.row_nmu; c1.row_rho = c0.row_rho; c1.col_mu = c0.col_mu; c1.col_r = c0.col_r; }
         c1.accumulate_loss = 0; c1.c_out = C2;
         c1.row_sq = accs + A_SQ2 * D; c1.row_sum = accs + A_SUM2 * D; c1.col_sq = nullptr; c1.col_sum = nullptr;
         p.pass[0] = c0; p.pass[1] = c1;
@@ -891,8 +1044,9 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
     }
     if (timed) cudaEventRecord(tev[2], stream);
     // ---- GRAD (+ batch-norm backward epilogue)
-    if (need != 0) {
-        const int passes = (need == 3) ? 2 : 1;
+    const int gneed = a.phase == 1 ? (need & 1) : (a.phase == 2 ? (need & 2) : need);     // gradient passes of THIS call
+    if (gneed != 0) {
+        const int passes = (gneed == 3) ? 2 : 1;
         const int q = 16 * cg;                                  // UMMA N granularity (M = 128: 16, M = 256: 32 so that each CTA stages a multiple of 16)
         int bn = N >= 256 ? 256 : ((N + q - 1) / q) * q;
         // small problems: narrower sample tiles instead of split-K, so that the epilogue always sees complete sums
@@ -904,8 +1058,10 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         } else {
             if (int rc = make_map_16(&mCt, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C1, RC, D, 64, 64)) return rc;     // the same C read MN-major
         }
-        if (int rc = make_map_16(&mZ2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh2, N, D, 64, bn / cg)) return rc;     // each CTA of a pair stages bn / 2 samples
-        if (int rc = make_map_16(&mZ1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh1, N, D, 64, bn / cg)) return rc;
+        const void* zB1 = a.zh_mode ? a.z1 : static_cast<const void*>(zh1);
+        const void* zB2 = a.zh_mode ? a.z2 : static_cast<const void*>(zh2);
+        if (int rc = make_map_16(&mZ2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zB2, N, D, 64, bn / cg)) return rc;     // each CTA of a pair stages bn / 2 samples
+        if (int rc = make_map_16(&mZ1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zB1, N, D, 64, bn / cg)) return rc;
         UmmaParams p{};
         p.dc = g_desc;
         p.mode = 1; p.D = D; p.N = N; p.bn = bn; p.ab_format = 0;
@@ -913,7 +1069,8 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         p.kblocks = (D + BK - 1) / BK;
         p.hsic = a.hsic; p.write_c = 0;
         p.loss_acc = loss_acc;
-        p.io_dtype = a.dtype; p.zq1 = zq1; p.zq2 = zq2; p.stats = stats; p.rs1 = rs1; p.rs2 = rs2;
+        p.io_dtype = a.dtype; p.stats = stats; p.rs1 = rs1; p.rs2 = rs2;
+        p.zq1 = a.zh_mode ? a.z1 : static_cast<const void*>(zq1); p.zq2 = a.zh_mode ? a.z2 : static_cast<const void*>(zq2); p.zfmt = a.zh_mode ? 1 : 0;
         p.alpha = a.alpha; p.lambda = a.lambda; p.grad_scale = a.grad_scale; p.loss_out = a.loss_out;
         PassCfg d1{}, d2{};
         d1.a_mn = 0; d1.row0 = R0; d1.row_end = R0 + RC; d1.side = 0; d1.dz = a.dz1; d1.ld_dz = a.ld_dz;
@@ -923,15 +1080,15 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         d2.sq = accs + A_SQ2 * D; d2.sm = accs + A_SUM2 * D;
         p.pass_count = passes;
         const CUtensorMap *a0, *b0, *a1, *b1;
-        if (need & 1) { p.pass[0] = d1; a0 = &mCk; b0 = &mZ2; p.pass[1] = d2; a1 = &mCt; b1 = &mZ1; }
+        if (gneed & 1) { p.pass[0] = d1; a0 = &mCk; b0 = &mZ2; p.pass[1] = d2; a1 = &mCt; b1 = &mZ1; }
         else { p.pass[0] = d2; a0 = &mCt; b0 = &mZ1; p.pass[1] = d2; a1 = &mCt; b1 = &mZ1; }
         if (int rc = launch_umma(cg, *a0, *b0, *a1, *b1, *a0, *a0, p, stream)) return rc;
-    } else if (a.loss_out != nullptr) {
+    } else if (a.loss_out != nullptr && need == 0) {
         bt_loss_scalar_kernel<<<1, 32, 0, stream>>>(loss_acc, a.alpha, a.lambda, a.hsic, D, a.loss_out);
         count_launch();
     }
     if (timed) { cudaEventRecord(tev[3], stream); ++g_timing.count; }
-    if (a.loss_parts_out != nullptr) cudaMemcpyAsync(a.loss_parts_out, loss_acc, 3 * sizeof(double), cudaMemcpyDeviceToDevice, stream);
+    if (a.loss_parts_out != nullptr && front) cudaMemcpyAsync(a.loss_parts_out, loss_acc, 3 * sizeof(double), cudaMemcpyDeviceToDevice, stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "bt loss launch: %s", cudaGetErrorString(e));
     return 0;
@@ -1059,4 +1216,137 @@ extern "C" int abt_bt_loss_rows_fwd_bwd(const abt_bt_rows_args* a, abt_stream_t 
     c.dz1 = a->dzr1; c.dz2 = a->dzr2; c.ld_dz = a->row_count;
     c.running_mean = a->running_mean; c.running_var = a->running_var; c.workspace = a->workspace;
     return dispatch(c, L, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int abt_scale_inplace(void* a, void* b, size_t n_elems, int dtype, const float* scale_dev, abt_stream_t stream) {
+    if (n_elems == 0 || (a == nullptr && b == nullptr)) return 0;
+    if (scale_dev == nullptr) return set_error(ABT_ERR_ARG, "scale is null");
+    if (dtype < 0 || dtype > 2) return set_error(ABT_ERR_ARG, "unknown dtype %d", dtype);
+    const size_t esz = dtype == ABT_DTYPE_F32 ? 4 : 2;
+    if ((n_elems * esz) % 16 != 0 || (reinterpret_cast<uintptr_t>(a) & 15) != 0 || (reinterpret_cast<uintptr_t>(b) & 15) != 0)
+        return set_error(ABT_ERR_ARG, "buffers must be 16-byte aligned and a multiple of 16 bytes long");
+    if (int rc = check_device_sm100()) return rc;
+    const size_t n_vec = n_elems * esz / 16;
+    const unsigned bx = (unsigned)((n_vec + 255) / 256 < 148u * 8u ? (n_vec + 255) / 256 : 148u * 8u);
+    const dim3 grid(bx, 2);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == ABT_DTYPE_BF16) bt_scale_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a), static_cast<__nv_bfloat16*>(b), n_vec, scale_dev);
+    else if (dtype == ABT_DTYPE_F16) bt_scale_kernel<__half><<<grid, 256, 0, st>>>(static_cast<__half*>(a), static_cast<__half*>(b), n_vec, scale_dev);
+    else bt_scale_kernel<float><<<grid, 256, 0, st>>>(static_cast<float*>(a), static_cast<float*>(b), n_vec, scale_dev);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "bt_scale_kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU objective (one process per GPU): statistics exchange + standardised-embedding gather + row block
+// ------------------------------------------------------------------------------------------
+static int check_dist(int n_local, int world, int n_dims, int row_count) {
+    if (world < 1 || n_local < 1) return set_error(ABT_ERR_ARG, "bad world size / local batch");
+    if (int rc = check_shape(n_local * world, n_dims, ABT_DTYPE_BF16)) return rc;
+    if (row_count < 8 || row_count > n_dims || (row_count % 8) != 0) return set_error(ABT_ERR_ARG, "row_count must be a multiple of 8 in [8, n_dims]");
+    return 0;
+}
+
+extern "C" int abt_bt_dist_layout_query(int n_local, int world, int n_dims, int row_count, abt_bt_dist_layout* out) {
+    if (out == nullptr) return set_error(ABT_ERR_ARG, "layout is null");
+    if (int rc = check_dist(n_local, world, n_dims, row_count)) return rc;
+    const WsLayout L = ws_layout(n_local * world, n_dims, row_count, ABT_DTYPE_BF16, true, world);
+    out->total_bytes = L.total; out->zh1 = L.zh1; out->zh2 = L.zh2; out->pack_local = L.pack_local; out->pack_all = L.pack_all;
+    out->pack_floats = 7 * (size_t)n_dims;
+    return 0;
+}
+
+template <typename T>
+static int dist_stats_local(const void* z1, const void* z2, int N, int D, uint8_t* ws, const WsLayout& L, cudaStream_t stream) {
+    float* partials = reinterpret_cast<float*>(ws + L.partials);
+    int splits = (N + 127) / 128;
+    if (splits > kMaxRowSplits) splits = kMaxRowSplits;
+    const int chunk = (N + splits - 1) / splits;
+    splits = (N + chunk - 1) / chunk;
+    const dim3 sgrid((D + kColsPerBlock - 1) / kColsPerBlock, splits);
+    cudaMemsetAsync(ws + L.keep, 0, 256, stream);
+    bt_colstat_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(z1), static_cast<const T*>(z2), N, D, chunk, partials, nullptr, nullptr);
+    bt_stat_pack_kernel<T><<<(D + 255) / 256, 256, 0, stream>>>(static_cast<const T*>(z1), static_cast<const T*>(z2), D, splits, partials,
+                                                                reinterpret_cast<float*>(ws + L.pack_local));
+    count_launch(2);
+    return 0;
+}
+
+extern "C" int abt_bt_dist_stats_local(const void* z1, const void* z2, int dtype, int n_local, int world, int n_dims, int row_count, void* workspace,
+                                       abt_stream_t stream) {
+    if (z1 == nullptr || z2 == nullptr || workspace == nullptr) return set_error(ABT_ERR_ARG, "null pointer argument");
+    if (dtype < 0 || dtype > 2) return set_error(ABT_ERR_ARG, "unknown dtype %d", dtype);
+    if (int rc = check_dist(n_local, world, n_dims, row_count)) return rc;
+    if (int rc = check_device_sm100()) return rc;
+    const WsLayout L = ws_layout(n_local * world, n_dims, row_count, ABT_DTYPE_BF16, true, world);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == ABT_DTYPE_BF16) dist_stats_local<__nv_bfloat16>(z1, z2, n_local, n_dims, ws, L, st);
+    else if (dtype == ABT_DTYPE_F16) dist_stats_local<__half>(z1, z2, n_local, n_dims, ws, L, st);
+    else dist_stats_local<float>(z1, z2, n_local, n_dims, ws, L, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "dist statistics launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+template <typename T>
+static void dist_normalize(const void* z1, const void* z2, int N, int world, int rank, int D, float eps, float momentum, float* rm, float* rv,
+                           uint8_t* ws, const WsLayout& L, cudaStream_t stream) {
+    int splits = (N + 127) / 128;
+    if (splits > kMaxRowSplits) splits = kMaxRowSplits;
+    const int chunk = (N + splits - 1) / splits;
+    splits = (N + chunk - 1) / chunk;
+    const dim3 sgrid((D + kColsPerBlock - 1) / kColsPerBlock, splits);
+    __half* zh1 = reinterpret_cast<__half*>(ws + L.zh1) + (size_t)rank * N * D;     // this rank's slot of the gather buffers
+    __half* zh2 = reinterpret_cast<__half*>(ws + L.zh2) + (size_t)rank * N * D;
+    bt_normalize_global_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(z1), static_cast<const T*>(z2), N, world, D, chunk, eps, momentum,
+                                                                     reinterpret_cast<const float*>(ws + L.pack_all), reinterpret_cast<float*>(ws + L.stats),
+                                                                     zh1, zh2, rm, rv, reinterpret_cast<double*>(ws + L.keep));
+    count_launch();
+}
+
+extern "C" int abt_bt_dist_normalize(const void* z1, const void* z2, int dtype, int n_local, int world, int rank, int n_dims, int row_count, float eps,
+                                     float momentum, float* running_mean, float* running_var, void* workspace, abt_stream_t stream) {
+    if (z1 == nullptr || z2 == nullptr || workspace == nullptr) return set_error(ABT_ERR_ARG, "null pointer argument");
+    if (dtype < 0 || dtype > 2) return set_error(ABT_ERR_ARG, "unknown dtype %d", dtype);
+    if (rank < 0 || rank >= world) return set_error(ABT_ERR_ARG, "rank %d outside [0, %d)", rank, world);
+    if (int rc = check_dist(n_local, world, n_dims, row_count)) return rc;
+    if (int rc = check_device_sm100()) return rc;
+    const WsLayout L = ws_layout(n_local * world, n_dims, row_count, ABT_DTYPE_BF16, true, world);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == ABT_DTYPE_BF16) dist_normalize<__nv_bfloat16>(z1, z2, n_local, world, rank, n_dims, eps, momentum, running_mean, running_var, ws, L, st);
+    else if (dtype == ABT_DTYPE_F16) dist_normalize<__half>(z1, z2, n_local, world, rank, n_dims, eps, momentum, running_mean, running_var, ws, L, st);
+    else dist_normalize<float>(z1, z2, n_local, world, rank, n_dims, eps, momentum, running_mean, running_var, ws, L, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "dist normalize launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int abt_bt_dist_rows_fwd_bwd(const abt_bt_dist_args* a, abt_stream_t stream) {
+    if (a == nullptr) return set_error(ABT_ERR_ARG, "args is null");
+    if (int rc = check_dist(a->n_local, a->world, a->n_dims, a->row_count)) return rc;
+    if (a->dtype < 0 || a->dtype > 2) return set_error(ABT_ERR_ARG, "unknown dtype %d", a->dtype);
+    if (a->row_begin < 0 || (a->row_begin % 8) != 0 || a->row_begin + a->row_count > a->n_dims)
+        return set_error(ABT_ERR_ARG, "row block [%d, %d) must be 8-aligned and inside [0, %d)", a->row_begin, a->row_begin + a->row_count, a->n_dims);
+    if (a->loss_parts == nullptr || a->workspace == nullptr) return set_error(ABT_ERR_ARG, "null pointer argument");
+    if (a->phase < 0 || a->phase > 2) return set_error(ABT_ERR_ARG, "phase must be 0, 1 or 2");
+    if ((a->need_grad_mask & 1) && a->phase != 2 && a->dzr1 == nullptr) return set_error(ABT_ERR_ARG, "dzr1 is null but requested");
+    if ((a->need_grad_mask & 2) && a->phase != 1 && a->dzr2 == nullptr) return set_error(ABT_ERR_ARG, "dzr2 is null but requested");
+    const int ng = a->n_local * a->world;
+    const WsLayout L = ws_layout(ng, a->n_dims, a->row_count, ABT_DTYPE_BF16, true, a->world);
+    if (a->workspace_bytes < L.total) return set_error(ABT_ERR_ARG, "workspace too small: %zu < %zu", a->workspace_bytes, L.total);
+    if ((reinterpret_cast<uintptr_t>(a->workspace) & 255) != 0) return set_error(ABT_ERR_ARG, "workspace must be 256-byte aligned");
+    if (int rc = check_device_sm100()) return rc;
+    uint8_t* ws = static_cast<uint8_t*>(a->workspace);
+    LossCall c{};
+    c.z1 = ws + L.zh1; c.z2 = ws + L.zh2; c.dtype = a->dtype; c.N = ng; c.D = a->n_dims;
+    c.row_begin = a->row_begin; c.row_count = a->row_count; c.rows_mode = true; c.zh_mode = true; c.phase = a->phase;
+    c.alpha = a->alpha; c.lambda = a->lambda; c.hsic = a->hsic; c.eps = 0.f; c.momentum = 0.f; c.grad_scale = a->grad_scale;
+    c.need = a->need_grad_mask; c.loss_out = nullptr; c.loss_parts_out = a->loss_parts;
+    c.dz1 = a->dzr1; c.dz2 = a->dzr2; c.ld_dz = a->row_count;
+    c.running_mean = nullptr; c.running_var = nullptr; c.workspace = a->workspace;
+    return run_loss<__nv_bfloat16>(c, L, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -7,20 +7,23 @@ section 3.3, quirk 1).  North-star semantics implemented here: ONE objective ove
 N_g = sum of local batches, identical (up to rounding) to the single-process reference run on the
 rank-ordered concatenation of the batches:
 
-    1. all-gather the raw bf16 embeddings of both views                       (NCCL, 2 x N_g x D x 2 B)
-    2. every rank derives the global column statistics from the gathered data   (redundant, bandwidth-trivial)
+    1. per-dimension statistics of the LOCAL rows (7 numbers per column)            abt_bt_dist_stats_local
+       all-gather of those packs (7 D floats per rank)                              NCCL, 229 KB per rank at D = 8192
+    2. every rank combines them into the global BatchNorm statistics and writes its
+       fp16 STANDARDISED rows into its slot of the gather buffers                   abt_bt_dist_normalize
+       all-gather of the standardised embeddings, in place                          NCCL, 2 x N_g x D x 2 B
     3. rank r computes rows [r D/R, (r+1) D/R) of C and of C^T on the tensor cores, its share of the
        off-diagonal loss, and d loss / d z for ALL samples restricted to its dimensions
-       (abt_bt_loss_rows_fwd_bwd; batch-norm backward is per column, so no partial sums cross ranks)
+       (batch-norm backward is per column, so no partial sums cross ranks)          abt_bt_dist_rows_fwd_bwd
     4. all-to-all returns each sample's gradient slice to the rank that owns the sample (NCCL)
     5. a 2-double all-reduce completes the loss
 
 `grad_scale`: DDP averages parameter gradients over ranks, so the local d loss / d z is multiplied by
 `world_size` by default; single-process and R-rank runs then produce the same parameter update.
 
-The collective choreography is separated from the row-block compute (`rows_fn`) so that it can be exercised
-with the gloo backend on CPUs (tests/test_dist_gloo.py passes an oracle-backed `rows_fn`); the product default
-is the CUDA entry point and nothing else.
+The collective choreography is separated from the compute (`backend`) so that it can be exercised with the gloo
+backend on CPUs (tests/test_dist_gloo.py injects a numpy-backed object); the product default is the CUDA
+library and nothing else.
 """
 from __future__ import annotations
 
@@ -87,15 +90,87 @@ def row_block(d: int, world: int, rank: int) -> Tuple[int, int]:
     return begin, max(0, min(per, d - begin))
 
 
+class CudaBackend:
+    """The three compute stages of one step on this rank's GPU, sharing one workspace per (N, R, D) shape."""
+
+    def __init__(self):
+        self._ws = {}
+
+    def workspace(self, device, n_local: int, world: int, d: int, row_count: int):
+        key = (device.index, n_local, world, d, row_count)
+        if key not in self._ws:
+            lay = _lib.BtDistLayout()
+            _lib.check(_lib.load().abt_bt_dist_layout_query(n_local, world, d, row_count, C.byref(lay)))
+            buf = torch.empty(lay.total_bytes + 256, dtype=torch.uint8, device=device)
+            base = (buf.data_ptr() + 255) // 256 * 256
+            off0 = base - buf.data_ptr()
+            ng, pf = n_local * world, int(lay.pack_floats)
+
+            def view(off, numel, dtype, shape):
+                nbytes = numel * torch.empty((), dtype=dtype).element_size()
+                return buf[off0 + off: off0 + off + nbytes].view(dtype).view(*shape)
+            self._ws[key] = dict(buf=buf, base=base, nbytes=int(lay.total_bytes),
+                                 zh1=view(lay.zh1, ng * d, torch.float16, (ng, d)), zh2=view(lay.zh2, ng * d, torch.float16, (ng, d)),
+                                 pack_local=view(lay.pack_local, pf, torch.float32, (pf,)),
+                                 pack_all=view(lay.pack_all, world * pf, torch.float32, (world * pf,)))
+        return self._ws[key]
+
+    @staticmethod
+    def _stream(dev):
+        return torch.cuda.current_stream(dev).cuda_stream
+
+    def stats_local(self, w, z1, z2, world, row_count):
+        n, d = int(z1.shape[0]), int(z1.shape[1])
+        with torch.cuda.device(z1.device):
+            _lib.check(_lib.load().abt_bt_dist_stats_local(z1.data_ptr(), z2.data_ptr(), _DTYPES[z1.dtype], n, world, d, row_count, w["base"],
+                                                           self._stream(z1.device)))
+
+    def normalize(self, w, z1, z2, world, rank, row_count, eps, momentum, running_mean, running_var):
+        n, d = int(z1.shape[0]), int(z1.shape[1])
+        with torch.cuda.device(z1.device):
+            _lib.check(_lib.load().abt_bt_dist_normalize(z1.data_ptr(), z2.data_ptr(), _DTYPES[z1.dtype], n, world, rank, d, row_count, float(eps),
+                                                         float(momentum), running_mean.data_ptr() if running_mean is not None else None,
+                                                         running_var.data_ptr() if running_var is not None else None, w["base"],
+                                                         self._stream(z1.device)))
+
+    def rows(self, w, dtype, device, n_local, world, d, row_begin, row_count, alpha, lmbda, hsic, grad_scale, need_mask, phase=0):
+        """phase 0: everything; 1: CORR + the dz1 pass (returns parts, dzr1, None); 2: the dz2 pass only (returns None, None, dzr2)."""
+        ng = n_local * world
+        parts = torch.empty(3, dtype=torch.float64, device=device) if phase != 2 else None
+        dzr1 = torch.empty((ng, row_count), dtype=dtype, device=device) if (need_mask & 1) and phase != 2 else None
+        dzr2 = torch.empty((ng, row_count), dtype=dtype, device=device) if (need_mask & 2) and phase != 1 else None
+        a = _lib.BtDistArgs()
+        a.dtype, a.n_local, a.world, a.n_dims = _DTYPES[dtype], n_local, world, d
+        a.row_begin, a.row_count = int(row_begin), int(row_count)
+        a.alpha, a.lambda_, a.hsic, a.grad_scale = float(alpha), float(lmbda), int(bool(hsic)), float(grad_scale)
+        a.need_grad_mask, a.phase = int(need_mask), int(phase)
+        a.loss_parts = parts.data_ptr() if parts is not None else w["base"]      # unused in phase 2
+        a.dzr1 = dzr1.data_ptr() if dzr1 is not None else None
+        a.dzr2 = dzr2.data_ptr() if dzr2 is not None else None
+        a.workspace, a.workspace_bytes = w["base"], w["nbytes"]
+        with torch.cuda.device(device):
+            _lib.check(_lib.load().abt_bt_dist_rows_fwd_bwd(C.byref(a), self._stream(device)))
+        return parts, dzr1, dzr2
+
+
+_CUDA_BACKEND = CudaBackend()
+
+
 def bt_loss_fwd_bwd_global(z1: torch.Tensor, z2: torch.Tensor, alpha: float, lmbda: float, hsic: bool, *, eps: float = 1e-5,
                            momentum: float = 0.1, running_mean: Optional[torch.Tensor] = None,
                            running_var: Optional[torch.Tensor] = None, need_dz1: bool = True, need_dz2: bool = True,
-                           grad_scale: Optional[float] = None, group=None, rows_fn: Optional[Callable] = None):
+                           grad_scale: Optional[float] = None, group=None, backend=None, overlap_hook: Optional[Callable[[], None]] = None):
     """Global-batch Barlow Twins loss + local gradients.  z1, z2: this rank's (N, D) embeddings (same N on every rank).
-    Returns (loss 0-dim fp32, identical on every rank; dz1 (N, D) or None; dz2 (N, D) or None)."""
+    Returns (loss 0-dim fp32, identical on every rank; dz1 (N, D) or None; dz2 (N, D) or None).
+
+    `overlap_hook`, if given, is called once the all-gather of the standardised embeddings is in flight: whatever it enqueues on the
+    current stream (typically the frontend of the NEXT batch) runs while the embeddings cross NVLink."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    rows_fn = rows_fn or _rows_cuda
+    if backend is None:
+        if not z1.is_cuda:
+            raise RuntimeError("embeddings must be CUDA tensors: ssl_audio_b200 has no CPU path")
+        backend = _CUDA_BACKEND
     if grad_scale is None:
         grad_scale = float(world)
     z1 = z1.contiguous()
@@ -107,24 +182,45 @@ def bt_loss_fwd_bwd_global(z1: torch.Tensor, z2: torch.Tensor, alpha: float, lmb
     per = row_block(d, world, 0)[1]
     if count != per:
         raise ValueError(f"D = {d} does not split into equal 8-aligned blocks over {world} ranks")
-    # 1. all-gather the raw embeddings (rank-ordered concatenation = the single-process global batch)
-    zg1 = torch.empty((world * n, d), dtype=z1.dtype, device=z1.device)
-    zg2 = torch.empty((world * n, d), dtype=z2.dtype, device=z2.device)
-    dist.all_gather_into_tensor(zg1, z1, group=group)
-    dist.all_gather_into_tensor(zg2, z2, group=group)
-    # 2.+3. statistics, row block of C / C^T, gradients of all samples for the dimensions of this rank
+    w = backend.workspace(z1.device, n, world, d, count)
+    # 1. local statistics -> all-gather of the 7 D-float packs
+    backend.stats_local(w, z1, z2, world, count)
+    dist.all_gather_into_tensor(w["pack_all"], w["pack_local"], group=group)
+    # 2. global statistics; standardised local rows into this rank's slot -> in-place all-gather (rank-ordered concatenation =
+    #    the single-process global batch)
+    backend.normalize(w, z1, z2, world, rank, count, eps, momentum, running_mean, running_var)
+    g1 = dist.all_gather_into_tensor(w["zh1"], w["zh1"][rank * n:(rank + 1) * n], group=group, async_op=True)
+    g2 = dist.all_gather_into_tensor(w["zh2"], w["zh2"][rank * n:(rank + 1) * n], group=group, async_op=True)
+    if overlap_hook is not None:
+        overlap_hook()
+    g1.wait()
+    g2.wait()
+    # 3. row block of C / C^T and the gradients of all samples for the dimensions of this rank, in two launches so that
+    # 4. the all-to-all returning the dz1 slices to the sample owners ((R, N, D/R) blocks) overlaps the dz2 GEMM
     need_mask = (1 if need_dz1 else 0) | (2 if need_dz2 else 0)
-    parts, dzr1, dzr2 = rows_fn(zg1, zg2, begin, count, alpha, lmbda, hsic, eps, momentum, grad_scale, need_mask, running_mean,
-                                running_var)
-    # 4. all-to-all: (R, N, D/R) blocks of my dimensions go to the ranks owning the samples
-    def exchange(dzr):
-        if dzr is None:
-            return None
+
+    def exchange_begin(dzr):
         recv = torch.empty((world, n, count), dtype=dzr.dtype, device=dzr.device)
-        dist.all_to_all_single(recv, dzr.view(world, n, count), group=group)
+        return recv, dist.all_to_all_single(recv, dzr.view(world, n, count), group=group, async_op=True), dzr
+
+    def exchange_end(pending):
+        if pending is None:
+            return None
+        recv, work, _keep = pending
+        work.wait()
         return recv.permute(1, 0, 2).reshape(n, d)        # [src rank = dimension block][n] -> (n, D)
-    dz1 = exchange(dzr1)
-    dz2 = exchange(dzr2)
+
+    if need_mask == 3:
+        parts, dzr1, _ = backend.rows(w, z1.dtype, z1.device, n, world, d, begin, count, alpha, lmbda, hsic, grad_scale, need_mask, 1)
+        p1 = exchange_begin(dzr1)
+        _, _, dzr2 = backend.rows(w, z1.dtype, z1.device, n, world, d, begin, count, alpha, lmbda, hsic, grad_scale, need_mask, 2)
+        p2 = exchange_begin(dzr2)
+    else:
+        parts, dzr1, dzr2 = backend.rows(w, z1.dtype, z1.device, n, world, d, begin, count, alpha, lmbda, hsic, grad_scale, need_mask, 0)
+        p1 = exchange_begin(dzr1) if dzr1 is not None else None
+        p2 = exchange_begin(dzr2) if dzr2 is not None else None
+    dz1 = exchange_end(p1)
+    dz2 = exchange_end(p2)
     # 5. loss: the off-diagonal partial sums are per row block, the on-diagonal sum is already global
     off = parts[:2].clone()
     dist.all_reduce(off, group=group)

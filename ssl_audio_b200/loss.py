@@ -106,7 +106,7 @@ class _BTLossFn(torch.autograd.Function):
             loss, dz1, dz2 = _dist.bt_loss_fwd_bwd_global(z1.detach(), z2.detach(), cfg.alpha, cfg.lmbda, cfg.HSIC, eps=bn.eps,
                                                           momentum=bn.momentum if bn.momentum is not None else 0.1,
                                                           running_mean=rm, running_var=rv, need_dz1=need1, need_dz2=need2,
-                                                          grad_scale=module.grad_scale)
+                                                          grad_scale=module.grad_scale, overlap_hook=module.comm_overlap_hook)
         else:
             loss, dz1, dz2 = bt_loss_fwd_bwd(z1.detach(), z2.detach(), cfg.alpha, cfg.lmbda, cfg.HSIC, eps=bn.eps,
                                              momentum=bn.momentum if bn.momentum is not None else 0.1,
@@ -121,9 +121,16 @@ class _BTLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         dz1, dz2 = ctx.saved_tensors
-        # the stored gradients are this call's own buffers (never exposed before): scale them in place
-        g1 = dz1.mul_(grad_out.to(dz1.dtype)) if ctx.has[0] else None
-        g2 = dz2.mul_(grad_out.to(dz2.dtype)) if ctx.has[1] else None
+        # the stored gradients are this call's own buffers (never exposed before): scale both in place with one launch
+        g1 = dz1 if ctx.has[0] else None
+        g2 = dz2 if ctx.has[1] else None
+        ref = g1 if g1 is not None else g2
+        if ref is not None:
+            scale = grad_out.detach().to(torch.float32).contiguous()
+            with torch.cuda.device(ref.device):
+                _lib.check(_lib.load().abt_scale_inplace(g1.data_ptr() if g1 is not None else None, g2.data_ptr() if g2 is not None else None,
+                                                         ref.numel(), _DTYPES[ref.dtype], scale.data_ptr(),
+                                                         torch.cuda.current_stream(ref.device).cuda_stream))
         return g1, g2, None
 
 
@@ -138,6 +145,8 @@ class BarlowTwinsLoss(nn.Module):
         # multi-GPU only: local gradients are multiplied by this; None = world_size, which cancels DDP's gradient
         # averaging so that R-rank and single-process runs give the same parameter update
         self.grad_scale = None
+        # multi-GPU only: optional callable invoked while the embedding all-gather is in flight (e.g. the next batch's frontend)
+        self.comm_overlap_hook = None
         # `bn.num_batches_tracked` is bookkeeping only (momentum is fixed): count on the host and fold the count into the
         # buffer when somebody looks at it (state_dict / explicit flush) instead of launching a kernel every step
         self._pending_batches = 0

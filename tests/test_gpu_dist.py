@@ -67,3 +67,63 @@ def test_row_block_one_sided_and_errors():
         D._rows_cuda(zg1, zg2, 4, 64, 1.0, 0.005, False, 1e-5, 0.1, 1.0, 3, None, None)     # unaligned block
     with pytest.raises(ValueError):
         D._rows_cuda(zg1, zg2, 224, 64, 1.0, 0.005, False, 1e-5, 0.1, 1.0, 3, None, None)   # outside D
+
+
+@pytest.mark.parametrize("world,n_local,d,hsic,dtype", [
+    (2, 64, 256, False, "f32"), (4, 32, 512, True, "f32"), (8, 128, 2048, False, "bf16"), (2, 100, 320, False, "f32"),
+])
+def test_three_stage_pipeline_emulated_on_one_gpu(world, n_local, d, hsic, dtype):
+    """abt_bt_dist_stats_local -> [all-gather] -> abt_bt_dist_normalize -> [all-gather] -> abt_bt_dist_rows_fwd_bwd with the R ranks
+    emulated one after the other (one workspace per rank, the collectives done by hand)."""
+    from ssl_audio_b200 import dist as D
+    if d % (8 * world) != 0:
+        pytest.skip("D must split into 8-aligned blocks")
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    ng = world * n_local
+    z1, z2 = O.synth_embeddings(ng, d, seed=3 * world + d)
+    z1 = O.round_bf16(z1 + 0.5)                      # shifted means: exercises the re-centring of the combined sums
+    zg1, zg2 = torch.from_numpy(z1).cuda().to(tdt), torch.from_numpy(z2).cuda().to(tdt)
+    count = D.row_block(d, world, 0)[1]
+    bes = [D.CudaBackend() for _ in range(world)]
+    wss = [bes[r].workspace(zg1.device, n_local, world, d, count) for r in range(world)]
+    loc = [(zg1[r * n_local:(r + 1) * n_local].contiguous(), zg2[r * n_local:(r + 1) * n_local].contiguous()) for r in range(world)]
+    for r in range(world):
+        bes[r].stats_local(wss[r], loc[r][0], loc[r][1], world, count)
+    packs = torch.cat([wss[r]["pack_local"] for r in range(world)])
+    rm = [torch.zeros(d, device="cuda") for _ in range(world)]
+    rv = [torch.ones(d, device="cuda") for _ in range(world)]
+    for r in range(world):
+        wss[r]["pack_all"].copy_(packs)
+        bes[r].normalize(wss[r], loc[r][0], loc[r][1], world, r, count, 1e-5, 0.1, rm[r], rv[r])
+    for r in range(world):                            # the all-gather of the standardised rows
+        for q in range(world):
+            if q != r:
+                wss[r]["zh1"][q * n_local:(q + 1) * n_local].copy_(wss[q]["zh1"][q * n_local:(q + 1) * n_local])
+                wss[r]["zh2"][q * n_local:(q + 1) * n_local].copy_(wss[q]["zh2"][q * n_local:(q + 1) * n_local])
+    off = np.zeros(2)
+    on = None
+    dz1 = np.zeros((ng, d), np.float32)
+    dz2 = np.zeros((ng, d), np.float32)
+    for r in range(world):
+        begin, cnt = D.row_block(d, world, r)
+        if r % 2 == 0:                                  # one launch ...
+            parts, a, b = bes[r].rows(wss[r], tdt, zg1.device, n_local, world, d, begin, cnt, 1.0, 0.005, hsic, 1.0, 3)
+        else:                                           # ... or the two-phase form the host uses to overlap the gradient all-to-all
+            parts, a, _ = bes[r].rows(wss[r], tdt, zg1.device, n_local, world, d, begin, cnt, 1.0, 0.005, hsic, 1.0, 3, 1)
+            _, _, b = bes[r].rows(wss[r], tdt, zg1.device, n_local, world, d, begin, cnt, 1.0, 0.005, hsic, 1.0, 3, 2)
+        p = parts.cpu().numpy()
+        off += p[:2]
+        on = p[2] if on is None else on
+        assert abs(p[2] - on) <= 1e-9 * max(1.0, abs(on))
+        dz1[:, begin:begin + cnt] = a.float().cpu().numpy()
+        dz2[:, begin:begin + cnt] = b.float().cpu().numpy()
+    loss = on + 0.005 * (off[0] + (2 * off[1] + d * (d - 1) if hsic else 0.0))
+    rl, r1, r2, _ = O.bt_loss_forward_backward(z1, z2, 1.0, 0.005, hsic)
+    assert abs(loss - rl) <= TOL * abs(rl), (loss, rl)
+    slack = 0.0 if dtype == "f32" else 4e-3                           # bf16 output quantum
+    assert _rel(dz1, r1) < TOL + slack and _rel(dz2, r2) < TOL + slack, (_rel(dz1, r1), _rel(dz2, r2))
+    m, v = O.bn_running_update(np.zeros(d), np.ones(d), z1)
+    m, v = O.bn_running_update(m, v, z2)
+    for r in range(world):
+        np.testing.assert_allclose(rm[r].cpu().numpy(), m, rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(rv[r].cpu().numpy(), v, rtol=1e-4, atol=1e-5)
