@@ -221,10 +221,18 @@ def bt_loss_fwd_bwd_global(z1: torch.Tensor, z2: torch.Tensor, alpha: float, lmb
         p2 = exchange_begin(dzr2) if dzr2 is not None else None
     dz1 = exchange_end(p1)
     dz2 = exchange_end(p2)
-    # 5. loss: the off-diagonal partial sums are per row block, the on-diagonal sum is already global
-    off = parts[:2].clone()
-    dist.all_reduce(off, group=group)
-    on = parts[2]
-    off_total = off[0] + (2.0 * off[1] + float(d) * float(d - 1) if hsic else 0.0)
-    loss = (alpha * on + lmbda * off_total).to(torch.float32)
-    return loss, dz1, dz2
+    # 5. loss: the off-diagonal partial sums are per row block; the on-diagonal sum is already global and identical on every
+    #    rank, so one SUM all-reduce of the three doubles followed by a dot product with constant coefficients finishes the scalar
+    dist.all_reduce(parts, group=group)
+    key = (parts.device, float(alpha), float(lmbda), bool(hsic), world)
+    coef = _COEF.get(key)
+    if coef is None:
+        coef = torch.tensor([lmbda, 2.0 * lmbda if hsic else 0.0, alpha / world], dtype=torch.float64, device=parts.device)
+        _COEF[key] = coef
+    loss = torch.dot(parts, coef)
+    if hsic:
+        loss = loss + lmbda * float(d) * float(d - 1)
+    return loss.to(torch.float32), dz1, dz2
+
+
+_COEF = {}
