@@ -297,6 +297,40 @@ int abt_bt_dist_normalize(const void* z1, const void* z2, int dtype, int n_local
                           float momentum, float* running_mean, float* running_var, void* workspace, abt_stream_t stream);
 int abt_bt_dist_rows_fwd_bwd(const abt_bt_dist_args* args, abt_stream_t stream);
 
+/* The same step issued natively: ONE host call per training step.  The collectives run on NCCL -- the libnccl.so.2 the process has
+ * already loaded (PyTorch's), resolved with dlopen at run time -- over a private communicator and a private high-priority
+ * communication stream; the all-to-all of the dz1 slices overlaps the dz2 GEMM, and `overlap_cb` (optional) is invoked right after
+ * the embedding all-gather has been launched so that the caller can enqueue independent work (the next batch's frontend) that runs
+ * while the embeddings cross NVLink.  Create the communicator once per process group:
+ *     rank 0: abt_comm_unique_id(id) -> broadcast the 128 bytes -> every rank: abt_comm_create(world, rank, id, &comm). */
+typedef struct abt_comm abt_comm;
+int abt_comm_unique_id(void* id128);
+int abt_comm_create(int world, int rank, const void* id128, abt_comm** comm);
+int abt_comm_destroy(abt_comm* comm);
+
+typedef void (*abt_overlap_cb)(void* user);
+typedef struct {
+    const void* z1;           /* this rank's (n_local, n_dims) embeddings */
+    const void* z2;
+    int32_t dtype, n_local, n_dims;   /* n_dims divisible by the world size, n_dims / world a multiple of 8 */
+    float alpha, lambda;
+    int32_t hsic;
+    float eps, momentum, grad_scale;
+    int32_t need_grad_mask;
+    float* loss_out;          /* device scalar: the GLOBAL-batch loss (identical on every rank) */
+    void* dz1;                /* (n_local, n_dims), dtype of the inputs, or NULL */
+    void* dz2;
+    float* running_mean;      /* BatchNorm buffers (n_dims), updated with the global-batch statistics, or NULL */
+    float* running_var;
+    void* workspace;          /* abt_bt_dist_step_workspace_bytes() bytes, 256-byte aligned */
+    size_t workspace_bytes;
+    abt_overlap_cb overlap_cb;
+    void* overlap_user;
+} abt_bt_dist_step_args;
+
+int abt_bt_dist_step_workspace_bytes(int n_local, int world, int n_dims, size_t* bytes);
+int abt_bt_dist_step(const abt_bt_dist_step_args* args, abt_comm* comm, abt_stream_t stream);
+
 /* ===================================================================================== *
  *  Debug hooks (not part of the drop-in surface; used by tools/gpu_diag.py)
  * ===================================================================================== */

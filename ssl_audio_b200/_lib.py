@@ -89,6 +89,19 @@ class BtDistArgs(C.Structure):
     ]
 
 
+OVERLAP_CB = C.CFUNCTYPE(None, C.c_void_p)
+
+
+class BtDistStepArgs(C.Structure):
+    _fields_ = [
+        ("z1", C.c_void_p), ("z2", C.c_void_p), ("dtype", C.c_int32), ("n_local", C.c_int32), ("n_dims", C.c_int32),
+        ("alpha", C.c_float), ("lambda_", C.c_float), ("hsic", C.c_int32), ("eps", C.c_float), ("momentum", C.c_float),
+        ("grad_scale", C.c_float), ("need_grad_mask", C.c_int32), ("loss_out", C.c_void_p), ("dz1", C.c_void_p), ("dz2", C.c_void_p),
+        ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("overlap_cb", OVERLAP_CB), ("overlap_user", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol of include/abt_b200.h
 SIGNATURES = {
     "abt_version": (C.c_int, []),
@@ -131,6 +144,11 @@ SIGNATURES = {
     "abt_bt_dist_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "abt_bt_dist_rows_fwd_bwd": (C.c_int, [C.POINTER(BtDistArgs), C.c_void_p]),
+    "abt_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "abt_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "abt_comm_destroy": (C.c_int, [C.c_void_p]),
+    "abt_bt_dist_step_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "abt_bt_dist_step": (C.c_int, [C.POINTER(BtDistStepArgs), C.c_void_p, C.c_void_p]),
     "abt_debug_set": (C.c_int, [C.c_int, C.c_int]),
     "abt_debug_launch_count": (C.c_longlong, [C.c_int]),
     "abt_debug_timing": (C.c_int, [C.c_int]),

@@ -37,6 +37,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstring>
+
 namespace abt {
 
 // ------------------------------------------------------------------------------------------
@@ -1325,6 +1327,21 @@ extern "C" int abt_bt_dist_normalize(const void* z1, const void* z2, int dtype, 
     return 0;
 }
 
+static int dist_rows_call(int dtype, int n_local, int world, int n_dims, int row_begin, int row_count, float alpha, float lambda, int hsic,
+                          float grad_scale, int need, int phase, double* loss_parts, void* dzr1, void* dzr2, void* workspace, cudaStream_t stream) {
+    const int ng = n_local * world;
+    const WsLayout L = ws_layout(ng, n_dims, row_count, ABT_DTYPE_BF16, true, world);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    LossCall c{};
+    c.z1 = ws + L.zh1; c.z2 = ws + L.zh2; c.dtype = dtype; c.N = ng; c.D = n_dims;
+    c.row_begin = row_begin; c.row_count = row_count; c.rows_mode = true; c.zh_mode = true; c.phase = phase;
+    c.alpha = alpha; c.lambda = lambda; c.hsic = hsic; c.eps = 0.f; c.momentum = 0.f; c.grad_scale = grad_scale;
+    c.need = need; c.loss_out = nullptr; c.loss_parts_out = loss_parts;
+    c.dz1 = dzr1; c.dz2 = dzr2; c.ld_dz = row_count;
+    c.running_mean = nullptr; c.running_var = nullptr; c.workspace = workspace;
+    return run_loss<__nv_bfloat16>(c, L, stream);
+}
+
 extern "C" int abt_bt_dist_rows_fwd_bwd(const abt_bt_dist_args* a, abt_stream_t stream) {
     if (a == nullptr) return set_error(ABT_ERR_ARG, "args is null");
     if (int rc = check_dist(a->n_local, a->world, a->n_dims, a->row_count)) return rc;
@@ -1335,18 +1352,248 @@ extern "C" int abt_bt_dist_rows_fwd_bwd(const abt_bt_dist_args* a, abt_stream_t 
     if (a->phase < 0 || a->phase > 2) return set_error(ABT_ERR_ARG, "phase must be 0, 1 or 2");
     if ((a->need_grad_mask & 1) && a->phase != 2 && a->dzr1 == nullptr) return set_error(ABT_ERR_ARG, "dzr1 is null but requested");
     if ((a->need_grad_mask & 2) && a->phase != 1 && a->dzr2 == nullptr) return set_error(ABT_ERR_ARG, "dzr2 is null but requested");
-    const int ng = a->n_local * a->world;
-    const WsLayout L = ws_layout(ng, a->n_dims, a->row_count, ABT_DTYPE_BF16, true, a->world);
+    const WsLayout L = ws_layout(a->n_local * a->world, a->n_dims, a->row_count, ABT_DTYPE_BF16, true, a->world);
     if (a->workspace_bytes < L.total) return set_error(ABT_ERR_ARG, "workspace too small: %zu < %zu", a->workspace_bytes, L.total);
     if ((reinterpret_cast<uintptr_t>(a->workspace) & 255) != 0) return set_error(ABT_ERR_ARG, "workspace must be 256-byte aligned");
     if (int rc = check_device_sm100()) return rc;
+    return dist_rows_call(a->dtype, a->n_local, a->world, a->n_dims, a->row_begin, a->row_count, a->alpha, a->lambda, a->hsic, a->grad_scale,
+                          a->need_grad_mask, a->phase, a->loss_parts, a->dzr1, a->dzr2, a->workspace, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------
+// native multi-GPU step: the whole choreography (statistics exchange, embedding all-gather, row block, gradient
+// all-to-all, loss all-reduce) issued from ONE call, with the collectives on NCCL (the library PyTorch already loaded,
+// resolved at run time) and a private communication stream, so that a training step costs one host call instead of
+// a dozen framework-level collectives
+// ------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace abt {
+
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    const char* (*GetErrorString)(ncclResult_t);
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    bool ok = false;
+};
+
+static NcclApi g_nccl;
+
+static int load_nccl() {
+    if (g_nccl.ok) return 0;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);     // the copy PyTorch loaded, if any: same soname
+    if (h == nullptr) return set_error(ABT_ERR_STATE, "libnccl.so.2 not found: %s", dlerror());
+#define ABT_NCCL_SYM(field, name)                                                        \
+    *reinterpret_cast<void**>(&g_nccl.field) = dlsym(h, name);                            \
+    if (g_nccl.field == nullptr) return set_error(ABT_ERR_STATE, "libnccl.so.2 lacks %s", name)
+    ABT_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+    ABT_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+    ABT_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    ABT_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+    ABT_NCCL_SYM(AllGather, "ncclAllGather");
+    ABT_NCCL_SYM(AllReduce, "ncclAllReduce");
+    ABT_NCCL_SYM(Send, "ncclSend");
+    ABT_NCCL_SYM(Recv, "ncclRecv");
+    ABT_NCCL_SYM(GroupStart, "ncclGroupStart");
+    ABT_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+#undef ABT_NCCL_SYM
+    g_nccl.ok = true;
+    return 0;
+}
+
+#define ABT_NCCL_OK(expr)                                                                                              \
+    do {                                                                                                               \
+        ncclResult_t r__ = (expr);                                                                                     \
+        if (r__ != ncclSuccess) return set_error(ABT_ERR_CUDA, "%s: %s", #expr, g_nccl.GetErrorString(r__));           \
+    } while (0)
+
+// recv [src rank][n][count] -> dz [n][src * count + j]: the slices a rank received from every dimension owner, in sample-major order
+template <int VEC_BYTES>
+__global__ void __launch_bounds__(256) bt_unpermute_kernel(const uint4* __restrict__ recv, uint4* __restrict__ dz, int world, int n, int vec_per_slice) {
+    const size_t total = (size_t)world * n * vec_per_slice;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vec_per_slice);
+        const size_t t = i / vec_per_slice;
+        const int row = (int)(t % n), src = (int)(t / n);
+        dz[((size_t)row * world + src) * vec_per_slice + v] = recv[i];
+    }
+}
+
+__global__ void bt_dist_loss_kernel(const double* __restrict__ parts, float alpha, float lambda, int hsic, int D, int world, float* __restrict__ loss_out) {
+    if (threadIdx.x == 0) {
+        double off = parts[0];
+        if (hsic) off = parts[0] + 2.0 * parts[1] + (double)D * (double)(D - 1);
+        *loss_out = (float)((double)alpha * parts[2] / (double)world + (double)lambda * off);   // the on-diagonal sum is global on every rank
+    }
+}
+
+struct DistLayout {
+    WsLayout L;
+    size_t dzr1, dzr2, recv1, recv2, parts, total;
+};
+
+static DistLayout dist_layout(int n_local, int world, int D, int row_count) {
+    DistLayout d{};
+    d.L = ws_layout(n_local * world, D, row_count, ABT_DTYPE_BF16, true, world);
+    size_t off = d.L.total;
+    const size_t slab = align_up((size_t)n_local * world * row_count * 4, 256);     // sized for fp32 gradients
+    d.dzr1 = off; off += slab;
+    d.dzr2 = off; off += slab;
+    d.recv1 = off; off += slab;
+    d.recv2 = off; off += slab;
+    d.parts = off; off += 256;
+    d.total = off;
+    return d;
+}
+
+}  // namespace abt
+
+struct abt_comm {
+    ncclComm_t comm;
+    int world, rank;
+    cudaStream_t cs;          // communication stream
+    cudaEvent_t ev[6];
+};
+
+extern "C" int abt_comm_unique_id(void* id128) {
+    if (id128 == nullptr) return set_error(ABT_ERR_ARG, "id buffer is null");
+    if (int rc = load_nccl()) return rc;
+    ncclUniqueId id;
+    ABT_NCCL_OK(g_nccl.GetUniqueId(&id));
+    std::memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+
+extern "C" int abt_comm_create(int world, int rank, const void* id128, abt_comm** out) {
+    if (id128 == nullptr || out == nullptr || world < 1 || rank < 0 || rank >= world) return set_error(ABT_ERR_ARG, "bad communicator arguments");
+    if (int rc = load_nccl()) return rc;
+    if (int rc = check_device_sm100()) return rc;
+    abt_comm* c = new abt_comm();
+    c->world = world; c->rank = rank;
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) { delete c; return set_error(ABT_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&c->cs, cudaStreamNonBlocking, hi) != cudaSuccess) { g_nccl.CommDestroy(c->comm); delete c; return set_error(ABT_ERR_CUDA, "cudaStreamCreate failed"); }
+    for (auto& e : c->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    *out = c;
+    return 0;
+}
+
+extern "C" int abt_comm_destroy(abt_comm* c) {
+    if (c == nullptr) return 0;
+    cudaStreamSynchronize(c->cs);
+    for (auto& e : c->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->cs);
+    if (g_nccl.ok) g_nccl.CommDestroy(c->comm);
+    delete c;
+    return 0;
+}
+
+extern "C" int abt_bt_dist_step_workspace_bytes(int n_local, int world, int n_dims, size_t* bytes) {
+    if (bytes == nullptr) return set_error(ABT_ERR_ARG, "bytes is null");
+    if (world < 1 || n_dims % world != 0) return set_error(ABT_ERR_ARG, "n_dims must be divisible by the world size");
+    if (int rc = check_dist(n_local, world, n_dims, n_dims / world)) return rc;
+    *bytes = dist_layout(n_local, world, n_dims, n_dims / world).total;
+    return 0;
+}
+
+static ncclDataType_t nccl_dtype(int dtype) { return dtype == ABT_DTYPE_BF16 ? ncclBfloat16 : (dtype == ABT_DTYPE_F16 ? ncclFloat16 : ncclFloat32); }
+
+// all-to-all of (world) equal slices: slice q of `send` goes to rank q, slice q of `recv` comes from rank q
+static int all_to_all(abt_comm* c, const void* send, void* recv, size_t slice_elems, int dtype, cudaStream_t st) {
+    const size_t esz = dtype == ABT_DTYPE_F32 ? 4 : 2;
+    ABT_NCCL_OK(g_nccl.GroupStart());
+    for (int q = 0; q < c->world; ++q) {
+        ABT_NCCL_OK(g_nccl.Send(static_cast<const uint8_t*>(send) + (size_t)q * slice_elems * esz, slice_elems, nccl_dtype(dtype), q, c->comm, st));
+        ABT_NCCL_OK(g_nccl.Recv(static_cast<uint8_t*>(recv) + (size_t)q * slice_elems * esz, slice_elems, nccl_dtype(dtype), q, c->comm, st));
+    }
+    ABT_NCCL_OK(g_nccl.GroupEnd());
+    return 0;
+}
+
+extern "C" int abt_bt_dist_step(const abt_bt_dist_step_args* a, abt_comm* c, abt_stream_t stream_) {
+    if (a == nullptr || c == nullptr) return set_error(ABT_ERR_ARG, "null argument");
+    const int world = c->world, rank = c->rank, N = a->n_local, D = a->n_dims;
+    if (world < 1 || D % world != 0) return set_error(ABT_ERR_ARG, "n_dims must be divisible by the world size");
+    const int Dr = D / world, R0 = rank * Dr;
+    if (int rc = check_dist(N, world, D, Dr)) return rc;
+    if (a->dtype < 0 || a->dtype > 2) return set_error(ABT_ERR_ARG, "unknown dtype %d", a->dtype);
+    if (a->z1 == nullptr || a->z2 == nullptr || a->loss_out == nullptr || a->workspace == nullptr) return set_error(ABT_ERR_ARG, "null pointer argument");
+    const int need = a->need_grad_mask & 3;
+    if ((need & 1) && a->dz1 == nullptr) return set_error(ABT_ERR_ARG, "dz1 is null but requested");
+    if ((need & 2) && a->dz2 == nullptr) return set_error(ABT_ERR_ARG, "dz2 is null but requested");
+    const DistLayout dl = dist_layout(N, world, D, Dr);
+    if (a->workspace_bytes < dl.total) return set_error(ABT_ERR_ARG, "workspace too small: %zu < %zu", a->workspace_bytes, dl.total);
+    if ((reinterpret_cast<uintptr_t>(a->workspace) & 255) != 0) return set_error(ABT_ERR_ARG, "workspace must be 256-byte aligned");
+    if (int rc = check_device_sm100()) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
     uint8_t* ws = static_cast<uint8_t*>(a->workspace);
-    LossCall c{};
-    c.z1 = ws + L.zh1; c.z2 = ws + L.zh2; c.dtype = a->dtype; c.N = ng; c.D = a->n_dims;
-    c.row_begin = a->row_begin; c.row_count = a->row_count; c.rows_mode = true; c.zh_mode = true; c.phase = a->phase;
-    c.alpha = a->alpha; c.lambda = a->lambda; c.hsic = a->hsic; c.eps = 0.f; c.momentum = 0.f; c.grad_scale = a->grad_scale;
-    c.need = a->need_grad_mask; c.loss_out = nullptr; c.loss_parts_out = a->loss_parts;
-    c.dz1 = a->dzr1; c.dz2 = a->dzr2; c.ld_dz = a->row_count;
-    c.running_mean = nullptr; c.running_var = nullptr; c.workspace = a->workspace;
-    return run_loss<__nv_bfloat16>(c, L, reinterpret_cast<cudaStream_t>(stream));
+    const WsLayout& L = dl.L;
+    const size_t esz = a->dtype == ABT_DTYPE_F32 ? 4 : 2;
+    const size_t slice = (size_t)N * Dr;                       // elements of one (source rank) slice of a gradient slab
+
+    // 1. local statistics -> all-gather of the 7 D-float packs (tiny: same stream)
+    if (int rc = abt_bt_dist_stats_local(a->z1, a->z2, a->dtype, N, world, D, Dr, a->workspace, stream_)) return rc;
+    ABT_NCCL_OK(g_nccl.AllGather(ws + L.pack_local, ws + L.pack_all, 7 * (size_t)D, ncclFloat32, c->comm, st));
+    // 2. global statistics + standardised local rows -> in-place all-gather of both views on the communication stream
+    if (int rc = abt_bt_dist_normalize(a->z1, a->z2, a->dtype, N, world, rank, D, Dr, a->eps, a->momentum, a->running_mean, a->running_var,
+                                       a->workspace, stream_)) return rc;
+    cudaEventRecord(c->ev[0], st);
+    cudaStreamWaitEvent(c->cs, c->ev[0], 0);
+    __half* zh1 = reinterpret_cast<__half*>(ws + L.zh1);
+    __half* zh2 = reinterpret_cast<__half*>(ws + L.zh2);
+    ABT_NCCL_OK(g_nccl.GroupStart());
+    ABT_NCCL_OK(g_nccl.AllGather(zh1 + (size_t)rank * N * D, zh1, (size_t)N * D, ncclFloat16, c->comm, c->cs));
+    ABT_NCCL_OK(g_nccl.AllGather(zh2 + (size_t)rank * N * D, zh2, (size_t)N * D, ncclFloat16, c->comm, c->cs));
+    ABT_NCCL_OK(g_nccl.GroupEnd());
+    cudaEventRecord(c->ev[1], c->cs);
+    // whatever the caller enqueues here (the next batch's frontend) runs while the embeddings cross NVLink
+    if (a->overlap_cb != nullptr) a->overlap_cb(a->overlap_user);
+    cudaStreamWaitEvent(st, c->ev[1], 0);
+    // 3. row block of C and C^T; gradient slabs (N_g, D/R); the all-to-all of dz1 overlaps the dz2 GEMM
+    double* parts = reinterpret_cast<double*>(ws + dl.parts);
+    const int phase_a = need == 3 ? 1 : 0;
+    if (int rc = dist_rows_call(a->dtype, N, world, D, R0, Dr, a->alpha, a->lambda, a->hsic, a->grad_scale, need, phase_a, parts, ws + dl.dzr1,
+                                ws + dl.dzr2, a->workspace, st)) return rc;
+    cudaEventRecord(c->ev[2], st);
+    cudaStreamWaitEvent(c->cs, c->ev[2], 0);
+    if (need & 1) { if (int rc = all_to_all(c, ws + dl.dzr1, ws + dl.recv1, slice, a->dtype, c->cs)) return rc; }
+    if (need == 2) { if (int rc = all_to_all(c, ws + dl.dzr2, ws + dl.recv2, slice, a->dtype, c->cs)) return rc; }
+    ABT_NCCL_OK(g_nccl.AllReduce(parts, parts, 3, ncclFloat64, ncclSum, c->comm, c->cs));
+    cudaEventRecord(c->ev[3], c->cs);
+    if (need == 3) {
+        if (int rc = dist_rows_call(a->dtype, N, world, D, R0, Dr, a->alpha, a->lambda, a->hsic, a->grad_scale, need, 2, parts, ws + dl.dzr1,
+                                    ws + dl.dzr2, a->workspace, st)) return rc;
+        cudaEventRecord(c->ev[4], st);
+        cudaStreamWaitEvent(c->cs, c->ev[4], 0);
+        if (int rc = all_to_all(c, ws + dl.dzr2, ws + dl.recv2, slice, a->dtype, c->cs)) return rc;
+        cudaEventRecord(c->ev[5], c->cs);
+    }
+    // 4. received slices -> (N, D) gradients of the local samples; loss scalar
+    cudaStreamWaitEvent(st, c->ev[3], 0);
+    const int vec_per_slice = (int)((size_t)Dr * esz / 16);
+    const size_t nvec = (size_t)world * N * vec_per_slice;
+    const unsigned blocks = (unsigned)((nvec + 255) / 256 < 148u * 8u ? (nvec + 255) / 256 : 148u * 8u);
+    if (need & 1) bt_unpermute_kernel<16><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(ws + dl.recv1), static_cast<uint4*>(a->dz1), world, N, vec_per_slice);
+    if (need == 2) bt_unpermute_kernel<16><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(ws + dl.recv2), static_cast<uint4*>(a->dz2), world, N, vec_per_slice);
+    bt_dist_loss_kernel<<<1, 32, 0, st>>>(parts, a->alpha, a->lambda, a->hsic, D, world, a->loss_out);
+    if (need == 3) {
+        cudaStreamWaitEvent(st, c->ev[5], 0);
+        bt_unpermute_kernel<16><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(ws + dl.recv2), static_cast<uint4*>(a->dz2), world, N, vec_per_slice);
+    }
+    count_launch(need == 3 ? 3 : (need ? 2 : 1));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "dist step launch: %s", cudaGetErrorString(e));
+    return 0;
 }

@@ -28,6 +28,7 @@ library and nothing else.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -156,6 +157,72 @@ class CudaBackend:
 _CUDA_BACKEND = CudaBackend()
 
 
+class NativeStep:
+    """ONE library call per step (abt_bt_dist_step): private NCCL communicator + communication stream owned by the library.
+    The communicator is created once per (process group, device); its 128-byte NCCL id travels over torch.distributed."""
+
+    _comms = {}
+    _ws = {}
+
+    @classmethod
+    def comm(cls, group, device):
+        key = (id(group) if group is not None else 0, device.index)
+        if key not in cls._comms:
+            lib = _lib.load()
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            ident = C.create_string_buffer(128)
+            if rank == 0:
+                _lib.check(lib.abt_comm_unique_id(ident))
+            box = [bytes(ident.raw)]
+            src = dist.get_global_rank(group, 0) if group is not None else 0
+            dist.broadcast_object_list(box, src=src, group=group)
+            h = C.c_void_p()
+            with torch.cuda.device(device):
+                _lib.check(lib.abt_comm_create(world, rank, C.create_string_buffer(box[0], 128), C.byref(h)))
+            cls._comms[key] = h
+        return cls._comms[key]
+
+    @classmethod
+    def workspace(cls, device, n, world, d):
+        key = (device.index, n, world, d)
+        if key not in cls._ws:
+            nbytes = C.c_size_t()
+            _lib.check(_lib.load().abt_bt_dist_step_workspace_bytes(n, world, d, C.byref(nbytes)))
+            cls._ws[key] = (torch.empty(nbytes.value + 256, dtype=torch.uint8, device=device), int(nbytes.value))
+        return cls._ws[key]
+
+    @classmethod
+    def run(cls, z1, z2, alpha, lmbda, hsic, eps, momentum, running_mean, running_var, need_dz1, need_dz2, grad_scale, group, overlap_hook):
+        lib = _lib.load()
+        dev = z1.device
+        world = dist.get_world_size(group)
+        n, d = int(z1.shape[0]), int(z1.shape[1])
+        comm = cls.comm(group, dev)
+        buf, nbytes = cls.workspace(dev, n, world, d)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        dz1 = torch.empty_like(z1) if need_dz1 else None
+        dz2 = torch.empty_like(z2) if need_dz2 else None
+        a = _lib.BtDistStepArgs()
+        a.z1, a.z2 = z1.data_ptr(), z2.data_ptr()
+        a.dtype, a.n_local, a.n_dims = _DTYPES[z1.dtype], n, d
+        a.alpha, a.lambda_, a.hsic = float(alpha), float(lmbda), int(bool(hsic))
+        a.eps, a.momentum, a.grad_scale = float(eps), float(momentum), float(grad_scale)
+        a.need_grad_mask = (1 if need_dz1 else 0) | (2 if need_dz2 else 0)
+        a.loss_out = loss.data_ptr()
+        a.dz1 = dz1.data_ptr() if dz1 is not None else None
+        a.dz2 = dz2.data_ptr() if dz2 is not None else None
+        a.running_mean = running_mean.data_ptr() if running_mean is not None else None
+        a.running_var = running_var.data_ptr() if running_var is not None else None
+        a.workspace = (buf.data_ptr() + 255) // 256 * 256
+        a.workspace_bytes = nbytes
+        cb = _lib.OVERLAP_CB(lambda _user: overlap_hook()) if overlap_hook is not None else _lib.OVERLAP_CB()
+        a.overlap_cb = cb
+        with torch.cuda.device(dev):
+            _lib.check(lib.abt_bt_dist_step(C.byref(a), comm, torch.cuda.current_stream(dev).cuda_stream))
+        del cb
+        return loss, dz1, dz2
+
+
 def bt_loss_fwd_bwd_global(z1: torch.Tensor, z2: torch.Tensor, alpha: float, lmbda: float, hsic: bool, *, eps: float = 1e-5,
                            momentum: float = 0.1, running_mean: Optional[torch.Tensor] = None,
                            running_var: Optional[torch.Tensor] = None, need_dz1: bool = True, need_dz2: bool = True,
@@ -167,10 +234,6 @@ def bt_loss_fwd_bwd_global(z1: torch.Tensor, z2: torch.Tensor, alpha: float, lmb
     current stream (typically the frontend of the NEXT batch) runs while the embeddings cross NVLink."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    if backend is None:
-        if not z1.is_cuda:
-            raise RuntimeError("embeddings must be CUDA tensors: ssl_audio_b200 has no CPU path")
-        backend = _CUDA_BACKEND
     if grad_scale is None:
         grad_scale = float(world)
     z1 = z1.contiguous()
@@ -182,6 +245,14 @@ def bt_loss_fwd_bwd_global(z1: torch.Tensor, z2: torch.Tensor, alpha: float, lmb
     per = row_block(d, world, 0)[1]
     if count != per:
         raise ValueError(f"D = {d} does not split into equal 8-aligned blocks over {world} ranks")
+    if backend is None:
+        if not z1.is_cuda:
+            raise RuntimeError("embeddings must be CUDA tensors: ssl_audio_b200 has no CPU path")
+        if os.environ.get("ABT_DIST_C10D") != "1" and d % world == 0:
+            # product default: the whole choreography below as one native call
+            return NativeStep.run(z1, z2, alpha, lmbda, hsic, eps, momentum, running_mean, running_var, need_dz1, need_dz2, grad_scale,
+                                  group, overlap_hook)
+        backend = _CUDA_BACKEND
     w = backend.workspace(z1.device, n, world, d, count)
     # 1. local statistics -> all-gather of the 7 D-float packs
     backend.stats_local(w, z1, z2, world, count)

@@ -127,3 +127,17 @@ def test_three_stage_pipeline_emulated_on_one_gpu(world, n_local, d, hsic, dtype
     for r in range(world):
         np.testing.assert_allclose(rm[r].cpu().numpy(), m, rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(rv[r].cpu().numpy(), v, rtol=1e-4, atol=1e-5)
+
+
+def test_native_multi_gpu_step_under_torchrun():
+    """Two real ranks over NCCL (skipped on a single-GPU box): the native one-call step and the torch.distributed choreography
+    against the global-batch oracle (tools/dist_check.py)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(root, "tools", "dist_check.py")], capture_output=True, text=True, timeout=600)
+    assert "DIST_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
