@@ -302,10 +302,14 @@ int abt_bt_dist_rows_fwd_bwd(const abt_bt_dist_args* args, abt_stream_t stream);
  * communication stream; the all-to-all of the dz1 slices overlaps the dz2 GEMM, and `overlap_cb` (optional) is invoked right after
  * the embedding all-gather has been launched so that the caller can enqueue independent work (the next batch's frontend) that runs
  * while the embeddings cross NVLink.  Create the communicator once per process group:
- *     rank 0: abt_comm_unique_id(id) -> broadcast the 128 bytes -> every rank: abt_comm_create(world, rank, id, &comm). */
+ *     rank 0: abt_comm_unique_id(id) -> broadcast the 256 bytes (two NCCL ids: large gathers / small exchanges) -> every rank:
+ *     abt_comm_create(world, rank, id, &comm).
+ * Default schedule ("exchange"): view 2 is gathered first; CORR (whose A operand, the view-1 columns of this rank's dimensions, arrives
+ * by a small all-to-all) and the dz1 GEMM run while view 1 is still in flight; the transposed block C[:, rows] arrives by an
+ * all-to-all of C blocks instead of a second CORR pass, so every rank executes 6 N D^2 FLOP as on one GPU. */
 typedef struct abt_comm abt_comm;
-int abt_comm_unique_id(void* id128);
-int abt_comm_create(int world, int rank, const void* id128, abt_comm** comm);
+int abt_comm_unique_id(void* id256);
+int abt_comm_create(int world, int rank, const void* id256, abt_comm** comm);
 int abt_comm_destroy(abt_comm* comm);
 
 typedef void (*abt_overlap_cb)(void* user);

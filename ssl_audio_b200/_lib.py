@@ -179,6 +179,8 @@ def load() -> C.CDLL:
         # debugging aid: ABT_CTA_GROUP=1 selects the single-CTA tensor-core kernel instead of the CTA-pair one
         if os.environ.get("ABT_CTA_GROUP") in ("1", "2"):
             lib.abt_debug_set(6, int(os.environ["ABT_CTA_GROUP"]))
+        if os.environ.get("ABT_DIST_XCHG") in ("0", "1"):       # 0: multi-GPU step without the exchange schedule
+            lib.abt_debug_set(7, int(os.environ["ABT_DIST_XCHG"]))
         _lib = lib
     return _lib
 

@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(kColThreads) bt_normalize_global_kernel(const 
                                                                           int D, int chunk, float eps, float momentum,
                                                                           const float* __restrict__ packs, float* __restrict__ stats,
                                                                           __half* __restrict__ zh1, __half* __restrict__ zh2,
+                                                                          __half* __restrict__ zh1_blk, int dr,
                                                                           float* __restrict__ running_mean, float* __restrict__ running_var,
                                                                           double* __restrict__ ondiag) {
     __shared__ float colstat[4][kColsPerBlock];
@@ -352,10 +353,31 @@ __global__ void __launch_bounds__(kColThreads) bt_normalize_global_kernel(const 
         for (int n = n0 + rg; n < n1; n += kRowGroups) {
             const size_t o = (size_t)n * D + col;
             const float2 a2 = Ld2<T>::ld(z1 + o), b2 = Ld2<T>::ld(z2 + o);
-            Ld2<__half>::st(zh1 + o, (bf16_round(a2.x) - m1[0]) * q1r[0], (bf16_round(a2.y) - m1[1]) * q1r[1]);
+            const float h0 = (bf16_round(a2.x) - m1[0]) * q1r[0], h1 = (bf16_round(a2.y) - m1[1]) * q1r[1];
+            Ld2<__half>::st(zh1 + o, h0, h1);
             Ld2<__half>::st(zh2 + o, (bf16_round(b2.x) - m2[0]) * q2r[0], (bf16_round(b2.y) - m2[1]) * q2r[1]);
+            // [dimension owner q][local row][Dr]: the slice every other rank needs as the A operand of its CORR tiles, contiguous
+            if (zh1_blk != nullptr) Ld2<__half>::st(zh1_blk + ((size_t)(col / dr) * n_local + n) * dr + (col % dr), h0, h1);
         }
     }
+}
+
+// column sums of C o C (and of C) over all rows of a (rows x cols) fp16 block: the batch-norm backward constants of the
+// view-2 gradients when the transposed block arrives by all-to-all (multi-GPU)
+__global__ void __launch_bounds__(256) bt_colsq_kernel(const __half* __restrict__ c, int rows, int cols, int rows_per_block,
+                                                       float* __restrict__ col_sq, float* __restrict__ col_sum, int hsic) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (j >= cols) return;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    float q0 = 0.f, q1 = 0.f, s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+    for (int r = r0; r < r1; ++r) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(c + (size_t)r * cols + j));
+        q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+        s0 += f.x; s1 += f.y;
+    }
+    atomicAdd(col_sq + j, q0); atomicAdd(col_sq + j + 1, q1);
+    if (hsic) { atomicAdd(col_sum + j, s0); atomicAdd(col_sum + j + 1, s1); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -399,8 +421,14 @@ struct PassCfg {
     float* row_sum;           // HSIC only: += sum_j c_ij
     float* col_sq;            // += sum_i c_ij^2 (i != j), indexed by the global column; null when a second pass provides it
     float* col_sum;           // HSIC only
+    int a_col0;               // MN-major A: first column of the A matrix that belongs to tile row 0 (row0 for full matrices, 0 for compact ones)
+    int blocked_dr;           // > 0: C is stored column-blocked, element (i, j) at ((j / Dr) * Dr + i) * Dr + j % Dr, so that the block
+                              // C[rows, q Dr : (q + 1) Dr] is contiguous (multi-GPU: the blocks are exchanged by an all-to-all)
     // ---- GRAD epilogue (batch-norm backward out of TMEM): rows are dimensions of view `side`
     int side;                 // 0: this pass produces dz1, 1: dz2
+    const void* z_self;       // 16-bit embeddings of this view / the other view restricted to the pass's dimensions: element (n, local row)
+    const void* z_other;      // at z[n * ld + local row]; raw bf16 (zfmt 0) or standardised fp16 (zfmt 1)
+    int ld_self, ld_other;
     void* dz;                 // dz[n * ld_dz + (row - row0)], dtype UmmaParams::io_dtype
     int ld_dz;
     const float* sq;          // row_sq / col_sq accumulated by CORR for these rows (global row index)
@@ -420,9 +448,7 @@ struct UmmaParams {
     double* loss_acc;
     // GRAD
     int io_dtype;                      // abt_dtype of dz
-    const void* zq1;                   // (N, D) 16-bit embeddings read by the epilogue: raw bf16 (zfmt 0) or standardised fp16 (zfmt 1)
-    const void* zq2;
-    int zfmt;
+    int zfmt;                          // format of PassCfg::z_self / z_other: 0 raw bf16, 1 standardised fp16
     const float* stats;                // StatSlot arrays
     const float* rs1; const float* rs2;   // HSIC: row sums of zh1 / zh2 over all dimensions
     float alpha, lambda, grad_scale;
@@ -458,8 +484,8 @@ template <> __device__ __forceinline__ void store_out<float>(float* p, float v) 
 template <typename T>
 __device__ __forceinline__ void grad_chunk(const uint32_t (&acc)[32], const UmmaParams& p, const PassCfg& pc, int row, int lrow, int n_base, int n_valid,
                                            float mu_s, float r_s, float mu_o, float r_o, float hs, float gd, float b) {
-    const unsigned short* zs = static_cast<const unsigned short*>(pc.side == 0 ? p.zq1 : p.zq2) + row;
-    const unsigned short* zo = static_cast<const unsigned short*>(pc.side == 0 ? p.zq2 : p.zq1) + row;
+    const unsigned short* zs = static_cast<const unsigned short*>(pc.z_self) + lrow;
+    const unsigned short* zo = static_cast<const unsigned short*>(pc.z_other) + lrow;
     const float* rso = pc.side == 0 ? p.rs2 : p.rs1;
     T* dz = static_cast<T*>(pc.dz) + lrow;
     const float rg = r_s * p.grad_scale;
@@ -473,8 +499,8 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&acc)[32], const Umma
         for (int u = 0; u < 16; ++u) {
             const int t = h * 16 + u;
             const size_t n = (size_t)(n_base + (t < n_valid ? t : 0));
-            zs_raw[u] = __ldg(zs + n * p.D);
-            zo_raw[u] = __ldg(zo + n * p.D);
+            zs_raw[u] = __ldg(zs + n * pc.ld_self);
+            zo_raw[u] = __ldg(zo + n * pc.ld_other);
             rsv[u] = p.hsic ? __ldg(rso + n) : 0.f;
         }
 #pragma unroll
@@ -577,7 +603,8 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const uint32_t tx = (kABytes + (uint32_t)bn_cta * BK * 2) * CG;     // both CTAs' bytes land on the leader's barrier
             const int bcol0 = tn * p.bn + (int)rank * bn_cta;
             const int a_mn = pc.a_mn;
-            const int arow = a_mn ? pc.row0 + tm * BM : tm * BM;
+            const int arow = a_mn ? pc.a_col0 + tm * BM : tm * BM;
+            const int bdr = pc.blocked_dr;
             for (int kb = 0; kb < p.kblocks; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
@@ -589,6 +616,9 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             // the tensor map spans global dimension indices (columns of z or of the full C)
                             tma_load_2d(sA, mA, &full_bar[stage], arow, kb * BK);
                             tma_load_2d(sA + 8192, mA, &full_bar[stage], arow + 64, kb * BK);
+                        } else if (bdr > 0) {
+                            const int qb = (kb * BK) / bdr;
+                            tma_load_2d(sA, mA, &full_bar[stage], kb * BK - qb * bdr, qb * bdr + arow);
                         } else {
                             // the tensor map spans the rows of the (possibly row-block compact) C matrix
                             tma_load_2d(sA, mA, &full_bar[stage], kb * BK, arow);
@@ -604,6 +634,9 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         if (a_mn) {
                             tma_load_2d_2sm(sA, mA, lbar, arow, kb * BK);
                             tma_load_2d_2sm(sA + 8192, mA, lbar, arow + 64, kb * BK);
+                        } else if (bdr > 0) {
+                            const int qb = (kb * BK) / bdr;
+                            tma_load_2d_2sm(sA, mA, lbar, kb * BK - qb * bdr, qb * bdr + arow);
                         } else {
                             tma_load_2d_2sm(sA, mA, lbar, kb * BK, arow);
                         }
@@ -731,8 +764,10 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         for (int k = 0; k < 4; ++k) sts128(stg_row + (((uint32_t)(k + 4) ^ sw) << 4), packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
                         fence_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
-                            tma_store_2d(mC, stg, jA, tm * BM + q * 32);       // rows / columns beyond the matrix are clipped by the tensor map
+                        if (lane == 0 && tm * BM + q * 32 < pc.row_end - pc.row0) {
+                            int sc0 = jA, sc1 = tm * BM + q * 32;
+                            if (pc.blocked_dr > 0) { const int qb = jA / pc.blocked_dr; sc0 = jA - qb * pc.blocked_dr; sc1 += qb * pc.blocked_dr; }
+                            tma_store_2d(mC, stg, sc0, sc1);       // rows / columns beyond the matrix are clipped by the tensor map
                             tma_store_commit();
                         }
                         if (pc.col_sq != nullptr) {
@@ -861,7 +896,7 @@ static TimingState g_timing;
 // Workspace layout.  `rows` = number of C rows this call materialises (D single-GPU, row_count in row-block mode);
 // `two_c` = a second C block for the transposed pass (row-block mode).
 struct WsLayout {
-    size_t misc, acc, stats, partials, keep, pack_local, pack_all, rs1, rs2, zb1, zb2, zh1, zh2, c1, c2, total;
+    size_t misc, acc, stats, partials, keep, pack_local, pack_all, rs1, rs2, zb1, zb2, zh1, zh2, zs1, zh1_blk, c1, c2, total;
     size_t zero_bytes;   // misc + acc: cleared at the start of every call
 };
 
@@ -882,6 +917,8 @@ static WsLayout ws_layout(int N, int D, int rows, int dtype, bool two_c, int wor
     L.zb2 = off; if (dtype != ABT_DTYPE_BF16) off = align_up(off + 2 * (size_t)N * D, 256);
     L.zh1 = off; off = align_up(off + 2 * (size_t)N * D, 256);
     L.zh2 = off; off = align_up(off + 2 * (size_t)N * D, 256);
+    L.zs1 = off; if (world > 0) off = align_up(off + 2 * (size_t)N * rows, 256);          // (N_g, Dr): view-1 columns of this rank's dimensions, all samples
+    L.zh1_blk = off; if (world > 0) off = align_up(off + 2 * (size_t)(N / world) * D, 256);  // (world, n_local, Dr): send buffer of that exchange
     L.c1 = off; off = align_up(off + 2 * (size_t)rows * D, 256);
     L.c2 = off; if (two_c) off = align_up(off + 2 * (size_t)rows * D, 256);
     L.total = off;
@@ -900,6 +937,7 @@ static int num_sms() {
 }
 
 static int g_cta_group = 2;     // 2 = CTA-pair kernel (default), 1 = single-CTA kernel (abt_debug_set key 6)
+static int g_dist_xchg = -1;    // multi-GPU exchange schedule: -1 = auto (4 ranks and more), 0 = never, 1 = whenever possible (abt_debug_set key 7)
 
 static int ensure_umma_attr() {
     static bool attr_set = false;
@@ -941,7 +979,10 @@ struct LossCall {
     int row_begin, row_count;   // dimensions owned by this call (0, D single-GPU)
     bool rows_mode;             // compute the C^T row block with a second CORR pass instead of reading C transposed
     bool zh_mode;               // z1 / z2 are standardised fp16 embeddings and the statistics are already in the workspace (multi-GPU)
-    int phase;                  // 0 = whole evaluation; 1 = everything except the dz2 GRAD pass; 2 = only the dz2 GRAD pass (after a phase-1 call)
+    int phase;                  // 0 = whole evaluation; 1 = everything except the dz2 GRAD pass; 2 = only the dz2 GRAD pass (after a phase-1 call);
+                                // exchange mode: bit mask 8 | F_FRONT (1) | F_DZ1 (2) | F_DZ2 (4)
+    bool xchg;                  // multi-GPU exchange mode: A of CORR = the (N, rows) view-1 slice at ws.zs1, C stored column-blocked, no second CORR
+                                // pass: the transposed block C[:, rows] (ws.c2) arrives by all-to-all before the dz2 pass
     float alpha, lambda; int hsic; float eps, momentum, grad_scale; int need;
     float* loss_out;            // single-GPU only
     double* loss_parts_out;     // row-block mode: 3 doubles copied out (off-diag sum c^2, off-diag sum c, on-diag sum)
@@ -976,7 +1017,10 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
     const bool timed = g_timing.enabled && g_timing.count < kTimingRing;
     cudaEvent_t* tev = timed ? g_timing.ev[g_timing.count] : nullptr;
     if (timed) cudaEventRecord(tev[0], stream);
-    const bool front = a.phase != 2;      // statistics + CORR belong to phases 0 and 1
+    // which parts of the evaluation this call runs: statistics hand-over + CORR (1), dz1 GEMM (2), dz2 GEMM (4)
+    const int pmask = a.xchg ? (a.phase & 7) : (a.phase == 0 ? 7 : (a.phase == 1 ? 3 : 4));
+    const bool front = (pmask & 1) != 0;
+    __half* ZS1 = reinterpret_cast<__half*>(ws + L.zs1);
     if (front) cudaMemsetAsync(ws + L.misc, 0, L.zero_bytes, stream);     // loss partial sums + row / column accumulators
     // ---- statistics
     if (!front) {
@@ -1000,10 +1044,14 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         // the statistics (and the on-diagonal loss sum) were produced by abt_bt_dist_normalize into this workspace
         cudaMemcpyAsync(loss_acc + 2, ws + L.keep, sizeof(double), cudaMemcpyDeviceToDevice, stream);
         if (a.hsic && need != 0) {
-            bt_rowsum_zh_kernel<<<N, 256, 0, stream>>>(static_cast<const __half*>(a.z1), N, D, rs1);
+            if (!a.xchg) bt_rowsum_zh_kernel<<<N, 256, 0, stream>>>(static_cast<const __half*>(a.z1), N, D, rs1);
             bt_rowsum_zh_kernel<<<N, 256, 0, stream>>>(static_cast<const __half*>(a.z2), N, D, rs2);
             count_launch(2);
         }
+    }
+    if (a.xchg && a.hsic && (pmask & 4) && (need & 2)) {       // view 1 is complete only now
+        bt_rowsum_zh_kernel<<<N, 256, 0, stream>>>(static_cast<const __half*>(a.z1), N, D, rs1);
+        count_launch();
     }
 
     const int cg = g_cta_group == 1 ? 1 : 2;
@@ -1013,7 +1061,8 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
     if (front) {
         CUtensorMap m1, m2;
         const CUtensorMapDataType odt = a.zh_mode ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-        if (int rc = make_map_16(&m1, odt, a.zh_mode ? a.z1 : zq1, N, D, 64, 64)) return rc;
+        if (a.xchg) { if (int rc = make_map_16(&m1, odt, ZS1, N, RC, 64, 64)) return rc; }
+        else if (int rc = make_map_16(&m1, odt, a.zh_mode ? a.z1 : zq1, N, D, 64, 64)) return rc;
         if (int rc = make_map_16(&m2, odt, a.zh_mode ? a.z2 : zq2, N, D, 64, 64)) return rc;
         UmmaParams p{};
         p.dc = g_desc;
@@ -1023,14 +1072,14 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         p.kblocks = (N + BK - 1) / BK;
         p.hsic = a.hsic; p.write_c = need != 0;
         p.loss_acc = loss_acc;
-        const bool second = a.rows_mode && (need & 2);       // the transposed block is only needed for dz2
+        const bool second = a.rows_mode && !a.xchg && (need & 2);       // the transposed block is only needed for dz2
         PassCfg c0{}, c1{};
-        c0.a_mn = 1; c0.row0 = R0; c0.row_end = R0 + RC;
+        c0.a_mn = 1; c0.row0 = R0; c0.row_end = R0 + RC; c0.a_col0 = a.xchg ? 0 : R0; c0.blocked_dr = a.xchg ? RC : 0;
         c0.row_nmu = stats + S_NMU1 * D; c0.row_rho = stats + S_RHO1 * D; c0.col_mu = stats + S_MU2 * D; c0.col_r = stats + S_R2 * D;
         if (a.zh_mode) { c0.row_nmu = stats + S_ZERO * D; c0.row_rho = stats + S_INVN * D; c0.col_mu = stats + S_ZERO * D; c0.col_r = stats + S_ONE * D; }
         c0.accumulate_loss = 1; c0.c_out = C1;
         c0.row_sq = (need & 1) ? accs + A_SQ1 * D : nullptr; c0.row_sum = accs + A_SUM1 * D;
-        c0.col_sq = (!a.rows_mode && (need & 2)) ? accs + A_SQ2 * D : nullptr; c0.col_sum = accs + A_SUM2 * D;
+        c0.col_sq = (!a.rows_mode && (need & 2)) ? accs + A_SQ2 * D : nullptr;      // exchange mode: bt_colsq_kernel on the received block c0.col_sum = accs + A_SUM2 * D;
         c1 = c0;
         c1.row_nmu = stats + S_NMU2 * D; c1.row_rho = stats + S_RHO2 * D; c1.col_mu = stats + S_MU1 * D; c1.col_r = stats + S_R1 * D;
         if (a.zh_mode) { c1.row_nmu = c0.row_nmu; c1.row_rho = c0.row_rho; c1.col_mu = c0.col_mu; c1.col_r = c0.col_r; }
@@ -1040,13 +1089,14 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         p.pass_count = second ? 2 : 1;
         // C is written by TMA stores of 32-row x 64-column boxes (row-block compact: RC rows)
         CUtensorMap mc1, mc2;
-        if (int rc = make_map_16(&mc1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C1, RC, D, 64, 32)) return rc;
+        if (a.xchg) { if (int rc = make_map_16(&mc1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C1, D, RC, 64, 32)) return rc; }      // column-blocked: (D, RC)
+        else if (int rc = make_map_16(&mc1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C1, RC, D, 64, 32)) return rc;
         if (int rc = make_map_16(&mc2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, second ? C2 : C1, RC, D, 64, 32)) return rc;
         if (int rc = launch_umma(cg, m1, m2, m2, m1, mc1, mc2, p, stream)) return rc;
     }
     if (timed) cudaEventRecord(tev[2], stream);
     // ---- GRAD (+ batch-norm backward epilogue)
-    const int gneed = a.phase == 1 ? (need & 1) : (a.phase == 2 ? (need & 2) : need);     // gradient passes of THIS call
+    const int gneed = ((pmask & 2) ? (need & 1) : 0) | ((pmask & 4) ? (need & 2) : 0);     // gradient passes of THIS call
     if (gneed != 0) {
         const int passes = (gneed == 3) ? 2 : 1;
         const int q = 16 * cg;                                  // UMMA N granularity (M = 128: 16, M = 256: 32 so that each CTA stages a multiple of 16)
@@ -1054,8 +1104,17 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         // small problems: narrower sample tiles instead of split-K, so that the epilogue always sees complete sums
         while (bn > 32 && row_tiles * ((N + bn - 1) / bn) * passes < num_sms() / cg) bn = ((bn / 2 + q - 1) / q) * q;
         CUtensorMap mCk, mCt, mZ2, mZ1;
-        if (int rc = make_map_16(&mCk, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C1, RC, D, 64, 128)) return rc;
-        if (a.rows_mode) {
+        if (a.xchg) {
+            if (int rc = make_map_16(&mCk, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C1, D, RC, 64, 128)) return rc;         // column-blocked C[rows, :]
+            if (int rc = make_map_16(&mCt, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C2, D, RC, 64, 64)) return rc;          // received C[:, rows], read MN-major
+            if (gneed & 2) {
+                const dim3 cgrid((RC / 2 + 255) / 256, 32);
+                bt_colsq_kernel<<<cgrid, 256, 0, stream>>>(C2, D, RC, (D + 31) / 32, accs + A_SQ2 * D + R0, accs + A_SUM2 * D + R0, a.hsic);
+                count_launch();
+            }
+        } else if (int rc = make_map_16(&mCk, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C1, RC, D, 64, 128)) return rc;
+        if (a.xchg) {
+        } else if (a.rows_mode) {
             if (int rc = make_map_16(&mCt, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C2, RC, D, 64, 128)) return rc;    // K-major rows of C^T
         } else {
             if (int rc = make_map_16(&mCt, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C1, RC, D, 64, 64)) return rc;     // the same C read MN-major
@@ -1072,14 +1131,21 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         p.hsic = a.hsic; p.write_c = 0;
         p.loss_acc = loss_acc;
         p.io_dtype = a.dtype; p.stats = stats; p.rs1 = rs1; p.rs2 = rs2;
-        p.zq1 = a.zh_mode ? a.z1 : static_cast<const void*>(zq1); p.zq2 = a.zh_mode ? a.z2 : static_cast<const void*>(zq2); p.zfmt = a.zh_mode ? 1 : 0;
+        p.zfmt = a.zh_mode ? 1 : 0;
+        const uint16_t* Z1 = static_cast<const uint16_t*>(a.zh_mode ? a.z1 : static_cast<const void*>(zq1));      // epilogue reads (16-bit elements)
+        const uint16_t* Z2 = static_cast<const uint16_t*>(a.zh_mode ? a.z2 : static_cast<const void*>(zq2));
         p.alpha = a.alpha; p.lambda = a.lambda; p.grad_scale = a.grad_scale; p.loss_out = a.loss_out;
         PassCfg d1{}, d2{};
         d1.a_mn = 0; d1.row0 = R0; d1.row_end = R0 + RC; d1.side = 0; d1.dz = a.dz1; d1.ld_dz = a.ld_dz;
         d1.sq = accs + A_SQ1 * D; d1.sm = accs + A_SUM1 * D;
+        d1.a_col0 = R0; d1.blocked_dr = a.xchg ? RC : 0;
+        d1.z_self = Z1 + R0; d1.ld_self = D; d1.z_other = Z2 + R0; d1.ld_other = D;
+        if (a.xchg) { d1.z_self = ZS1; d1.ld_self = RC; }          // view 1 may still be in flight: use the exchanged slice
         d2 = d1;
-        d2.a_mn = a.rows_mode ? 0 : 1; d2.side = 1; d2.dz = a.dz2;
+        d2.a_mn = (a.rows_mode && !a.xchg) ? 0 : 1; d2.side = 1; d2.dz = a.dz2; d2.blocked_dr = 0;
+        if (a.xchg) d2.a_col0 = 0;                                   // C[:, rows] is compact: (D, RC)
         d2.sq = accs + A_SQ2 * D; d2.sm = accs + A_SUM2 * D;
+        d2.z_self = Z2 + R0; d2.ld_self = D; d2.z_other = Z1 + R0; d2.ld_other = D;
         p.pass_count = passes;
         const CUtensorMap *a0, *b0, *a1, *b1;
         if (gneed & 1) { p.pass[0] = d1; a0 = &mCk; b0 = &mZ2; p.pass[1] = d2; a1 = &mCt; b1 = &mZ1; }
@@ -1151,6 +1217,7 @@ extern "C" int abt_debug_timing_read(float* stats_ms, float* corr_ms, float* gra
 extern "C" int abt_debug_set(int key, int value) {
     int* f[6] = {&g_desc.mn_lbo, &g_desc.mn_sbo, &g_desc.mn_kstep, &g_desc.k_lbo, &g_desc.k_sbo, &g_desc.k_kstep};
     if (key == 6) { g_cta_group = value == 1 ? 1 : 2; return 0; }
+    if (key == 7) { g_dist_xchg = value < 0 ? -1 : (value != 0 ? 1 : 0); return 0; }
     if (key < 0 || key >= 6) return set_error(ABT_ERR_ARG, "unknown debug key %d", key);
     *f[key] = value;
     return 0;
@@ -1294,8 +1361,8 @@ extern "C" int abt_bt_dist_stats_local(const void* z1, const void* z2, int dtype
 }
 
 template <typename T>
-static void dist_normalize(const void* z1, const void* z2, int N, int world, int rank, int D, float eps, float momentum, float* rm, float* rv,
-                           uint8_t* ws, const WsLayout& L, cudaStream_t stream) {
+static void dist_normalize(const void* z1, const void* z2, int N, int world, int rank, int D, int row_count, float eps, float momentum, float* rm,
+                           float* rv, uint8_t* ws, const WsLayout& L, cudaStream_t stream) {
     int splits = (N + 127) / 128;
     if (splits > kMaxRowSplits) splits = kMaxRowSplits;
     const int chunk = (N + splits - 1) / splits;
@@ -1305,7 +1372,8 @@ static void dist_normalize(const void* z1, const void* z2, int N, int world, int
     __half* zh2 = reinterpret_cast<__half*>(ws + L.zh2) + (size_t)rank * N * D;
     bt_normalize_global_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(z1), static_cast<const T*>(z2), N, world, D, chunk, eps, momentum,
                                                                      reinterpret_cast<const float*>(ws + L.pack_all), reinterpret_cast<float*>(ws + L.stats),
-                                                                     zh1, zh2, rm, rv, reinterpret_cast<double*>(ws + L.keep));
+                                                                     zh1, zh2, reinterpret_cast<__half*>(ws + L.zh1_blk), row_count, rm, rv,
+                                                                     reinterpret_cast<double*>(ws + L.keep));
     count_launch();
 }
 
@@ -1319,22 +1387,23 @@ extern "C" int abt_bt_dist_normalize(const void* z1, const void* z2, int dtype, 
     const WsLayout L = ws_layout(n_local * world, n_dims, row_count, ABT_DTYPE_BF16, true, world);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (dtype == ABT_DTYPE_BF16) dist_normalize<__nv_bfloat16>(z1, z2, n_local, world, rank, n_dims, eps, momentum, running_mean, running_var, ws, L, st);
-    else if (dtype == ABT_DTYPE_F16) dist_normalize<__half>(z1, z2, n_local, world, rank, n_dims, eps, momentum, running_mean, running_var, ws, L, st);
-    else dist_normalize<float>(z1, z2, n_local, world, rank, n_dims, eps, momentum, running_mean, running_var, ws, L, st);
+    if (dtype == ABT_DTYPE_BF16) dist_normalize<__nv_bfloat16>(z1, z2, n_local, world, rank, n_dims, row_count, eps, momentum, running_mean, running_var, ws, L, st);
+    else if (dtype == ABT_DTYPE_F16) dist_normalize<__half>(z1, z2, n_local, world, rank, n_dims, row_count, eps, momentum, running_mean, running_var, ws, L, st);
+    else dist_normalize<float>(z1, z2, n_local, world, rank, n_dims, row_count, eps, momentum, running_mean, running_var, ws, L, st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "dist normalize launch: %s", cudaGetErrorString(e));
     return 0;
 }
 
 static int dist_rows_call(int dtype, int n_local, int world, int n_dims, int row_begin, int row_count, float alpha, float lambda, int hsic,
-                          float grad_scale, int need, int phase, double* loss_parts, void* dzr1, void* dzr2, void* workspace, cudaStream_t stream) {
+                          float grad_scale, int need, int phase, double* loss_parts, void* dzr1, void* dzr2, void* workspace, cudaStream_t stream,
+                          bool xchg = false) {
     const int ng = n_local * world;
     const WsLayout L = ws_layout(ng, n_dims, row_count, ABT_DTYPE_BF16, true, world);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     LossCall c{};
     c.z1 = ws + L.zh1; c.z2 = ws + L.zh2; c.dtype = dtype; c.N = ng; c.D = n_dims;
-    c.row_begin = row_begin; c.row_count = row_count; c.rows_mode = true; c.zh_mode = true; c.phase = phase;
+    c.row_begin = row_begin; c.row_count = row_count; c.rows_mode = true; c.zh_mode = true; c.phase = phase; c.xchg = xchg;
     c.alpha = alpha; c.lambda = lambda; c.hsic = hsic; c.eps = 0.f; c.momentum = 0.f; c.grad_scale = grad_scale;
     c.need = need; c.loss_out = nullptr; c.loss_parts_out = loss_parts;
     c.dz1 = dzr1; c.dz2 = dzr2; c.ld_dz = row_count;
@@ -1457,34 +1526,41 @@ static DistLayout dist_layout(int n_local, int world, int D, int row_count) {
 }  // namespace abt
 
 struct abt_comm {
-    ncclComm_t comm;
+    ncclComm_t comm;          // embedding all-gathers (large)
+    ncclComm_t comm2;         // statistics packs, slice / block / gradient all-to-alls, loss all-reduce (small, latency-bound)
     int world, rank;
-    cudaStream_t cs;          // communication stream
-    cudaEvent_t ev[6];
+    cudaStream_t cs, cs2;     // one communication stream per communicator
+    cudaEvent_t ev[12];
 };
 
-extern "C" int abt_comm_unique_id(void* id128) {
-    if (id128 == nullptr) return set_error(ABT_ERR_ARG, "id buffer is null");
+extern "C" int abt_comm_unique_id(void* id256) {
+    if (id256 == nullptr) return set_error(ABT_ERR_ARG, "id buffer is null");
     if (int rc = load_nccl()) return rc;
-    ncclUniqueId id;
-    ABT_NCCL_OK(g_nccl.GetUniqueId(&id));
-    std::memcpy(id128, &id, sizeof(id));
+    ncclUniqueId id[2];
+    ABT_NCCL_OK(g_nccl.GetUniqueId(&id[0]));
+    ABT_NCCL_OK(g_nccl.GetUniqueId(&id[1]));
+    std::memcpy(id256, id, sizeof(id));
     return 0;
 }
 
-extern "C" int abt_comm_create(int world, int rank, const void* id128, abt_comm** out) {
-    if (id128 == nullptr || out == nullptr || world < 1 || rank < 0 || rank >= world) return set_error(ABT_ERR_ARG, "bad communicator arguments");
+extern "C" int abt_comm_create(int world, int rank, const void* id256, abt_comm** out) {
+    if (id256 == nullptr || out == nullptr || world < 1 || rank < 0 || rank >= world) return set_error(ABT_ERR_ARG, "bad communicator arguments");
     if (int rc = load_nccl()) return rc;
     if (int rc = check_device_sm100()) return rc;
     abt_comm* c = new abt_comm();
     c->world = world; c->rank = rank;
-    ncclUniqueId id;
-    std::memcpy(&id, id128, sizeof(id));
-    ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    ncclUniqueId id[2];
+    std::memcpy(id, id256, sizeof(id));
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id[0], rank);
+    if (r == ncclSuccess) r = g_nccl.CommInitRank(&c->comm2, world, id[1], rank);
     if (r != ncclSuccess) { delete c; return set_error(ABT_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (cudaStreamCreateWithPriority(&c->cs, cudaStreamNonBlocking, hi) != cudaSuccess) { g_nccl.CommDestroy(c->comm); delete c; return set_error(ABT_ERR_CUDA, "cudaStreamCreate failed"); }
+    if (cudaStreamCreateWithPriority(&c->cs, cudaStreamNonBlocking, hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->cs2, cudaStreamNonBlocking, hi) != cudaSuccess) {
+        g_nccl.CommDestroy(c->comm); g_nccl.CommDestroy(c->comm2); delete c;
+        return set_error(ABT_ERR_CUDA, "cudaStreamCreate failed");
+    }
     for (auto& e : c->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     *out = c;
     return 0;
@@ -1493,9 +1569,11 @@ extern "C" int abt_comm_create(int world, int rank, const void* id128, abt_comm*
 extern "C" int abt_comm_destroy(abt_comm* c) {
     if (c == nullptr) return 0;
     cudaStreamSynchronize(c->cs);
+    cudaStreamSynchronize(c->cs2);
     for (auto& e : c->ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->cs);
-    if (g_nccl.ok) g_nccl.CommDestroy(c->comm);
+    cudaStreamDestroy(c->cs2);
+    if (g_nccl.ok) { g_nccl.CommDestroy(c->comm); g_nccl.CommDestroy(c->comm2); }
     delete c;
     return 0;
 }
@@ -1511,12 +1589,12 @@ extern "C" int abt_bt_dist_step_workspace_bytes(int n_local, int world, int n_di
 static ncclDataType_t nccl_dtype(int dtype) { return dtype == ABT_DTYPE_BF16 ? ncclBfloat16 : (dtype == ABT_DTYPE_F16 ? ncclFloat16 : ncclFloat32); }
 
 // all-to-all of (world) equal slices: slice q of `send` goes to rank q, slice q of `recv` comes from rank q
-static int all_to_all(abt_comm* c, const void* send, void* recv, size_t slice_elems, int dtype, cudaStream_t st) {
+static int all_to_all(abt_comm* c, ncclComm_t comm, const void* send, void* recv, size_t slice_elems, int dtype, cudaStream_t st) {
     const size_t esz = dtype == ABT_DTYPE_F32 ? 4 : 2;
     ABT_NCCL_OK(g_nccl.GroupStart());
     for (int q = 0; q < c->world; ++q) {
-        ABT_NCCL_OK(g_nccl.Send(static_cast<const uint8_t*>(send) + (size_t)q * slice_elems * esz, slice_elems, nccl_dtype(dtype), q, c->comm, st));
-        ABT_NCCL_OK(g_nccl.Recv(static_cast<uint8_t*>(recv) + (size_t)q * slice_elems * esz, slice_elems, nccl_dtype(dtype), q, c->comm, st));
+        ABT_NCCL_OK(g_nccl.Send(static_cast<const uint8_t*>(send) + (size_t)q * slice_elems * esz, slice_elems, nccl_dtype(dtype), q, comm, st));
+        ABT_NCCL_OK(g_nccl.Recv(static_cast<uint8_t*>(recv) + (size_t)q * slice_elems * esz, slice_elems, nccl_dtype(dtype), q, comm, st));
     }
     ABT_NCCL_OK(g_nccl.GroupEnd());
     return 0;
@@ -1543,54 +1621,98 @@ extern "C" int abt_bt_dist_step(const abt_bt_dist_step_args* a, abt_comm* c, abt
     const size_t esz = a->dtype == ABT_DTYPE_F32 ? 4 : 2;
     const size_t slice = (size_t)N * Dr;                       // elements of one (source rank) slice of a gradient slab
 
-    // 1. local statistics -> all-gather of the 7 D-float packs (tiny: same stream)
-    if (int rc = abt_bt_dist_stats_local(a->z1, a->z2, a->dtype, N, world, D, Dr, a->workspace, stream_)) return rc;
-    ABT_NCCL_OK(g_nccl.AllGather(ws + L.pack_local, ws + L.pack_all, 7 * (size_t)D, ncclFloat32, c->comm, st));
-    // 2. global statistics + standardised local rows -> in-place all-gather of both views on the communication stream
-    if (int rc = abt_bt_dist_normalize(a->z1, a->z2, a->dtype, N, world, rank, D, Dr, a->eps, a->momentum, a->running_mean, a->running_var,
-                                       a->workspace, stream_)) return rc;
-    cudaEventRecord(c->ev[0], st);
-    cudaStreamWaitEvent(c->cs, c->ev[0], 0);
+    enum { E_P0, E_P1, E_N, E_A, E_B, E_S, E_C3, E_C, E_G1, E_D, E_G2, E_E };
+    auto chain = [](cudaStream_t from, cudaEvent_t ev, cudaStream_t to) { cudaEventRecord(ev, from); cudaStreamWaitEvent(to, ev, 0); };
     __half* zh1 = reinterpret_cast<__half*>(ws + L.zh1);
     __half* zh2 = reinterpret_cast<__half*>(ws + L.zh2);
-    ABT_NCCL_OK(g_nccl.GroupStart());
-    ABT_NCCL_OK(g_nccl.AllGather(zh1 + (size_t)rank * N * D, zh1, (size_t)N * D, ncclFloat16, c->comm, c->cs));
-    ABT_NCCL_OK(g_nccl.AllGather(zh2 + (size_t)rank * N * D, zh2, (size_t)N * D, ncclFloat16, c->comm, c->cs));
-    ABT_NCCL_OK(g_nccl.GroupEnd());
-    cudaEventRecord(c->ev[1], c->cs);
-    // whatever the caller enqueues here (the next batch's frontend) runs while the embeddings cross NVLink
-    if (a->overlap_cb != nullptr) a->overlap_cb(a->overlap_user);
-    cudaStreamWaitEvent(st, c->ev[1], 0);
-    // 3. row block of C and C^T; gradient slabs (N_g, D/R); the all-to-all of dz1 overlaps the dz2 GEMM
     double* parts = reinterpret_cast<double*>(ws + dl.parts);
-    const int phase_a = need == 3 ? 1 : 0;
-    if (int rc = dist_rows_call(a->dtype, N, world, D, R0, Dr, a->alpha, a->lambda, a->hsic, a->grad_scale, need, phase_a, parts, ws + dl.dzr1,
-                                ws + dl.dzr2, a->workspace, st)) return rc;
-    cudaEventRecord(c->ev[2], st);
-    cudaStreamWaitEvent(c->cs, c->ev[2], 0);
-    if (need & 1) { if (int rc = all_to_all(c, ws + dl.dzr1, ws + dl.recv1, slice, a->dtype, c->cs)) return rc; }
-    if (need == 2) { if (int rc = all_to_all(c, ws + dl.dzr2, ws + dl.recv2, slice, a->dtype, c->cs)) return rc; }
-    ABT_NCCL_OK(g_nccl.AllReduce(parts, parts, 3, ncclFloat64, ncclSum, c->comm, c->cs));
-    cudaEventRecord(c->ev[3], c->cs);
-    if (need == 3) {
-        if (int rc = dist_rows_call(a->dtype, N, world, D, R0, Dr, a->alpha, a->lambda, a->hsic, a->grad_scale, need, 2, parts, ws + dl.dzr1,
-                                    ws + dl.dzr2, a->workspace, st)) return rc;
-        cudaEventRecord(c->ev[4], st);
-        cudaStreamWaitEvent(c->cs, c->ev[4], 0);
-        if (int rc = all_to_all(c, ws + dl.dzr2, ws + dl.recv2, slice, a->dtype, c->cs)) return rc;
-        cudaEventRecord(c->ev[5], c->cs);
-    }
-    // 4. received slices -> (N, D) gradients of the local samples; loss scalar
-    cudaStreamWaitEvent(st, c->ev[3], 0);
     const int vec_per_slice = (int)((size_t)Dr * esz / 16);
     const size_t nvec = (size_t)world * N * vec_per_slice;
-    const unsigned blocks = (unsigned)((nvec + 255) / 256 < 148u * 8u ? (nvec + 255) / 256 : 148u * 8u);
-    if (need & 1) bt_unpermute_kernel<16><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(ws + dl.recv1), static_cast<uint4*>(a->dz1), world, N, vec_per_slice);
-    if (need == 2) bt_unpermute_kernel<16><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(ws + dl.recv2), static_cast<uint4*>(a->dz2), world, N, vec_per_slice);
-    bt_dist_loss_kernel<<<1, 32, 0, st>>>(parts, a->alpha, a->lambda, a->hsic, D, world, a->loss_out);
-    if (need == 3) {
-        cudaStreamWaitEvent(st, c->ev[5], 0);
-        bt_unpermute_kernel<16><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(ws + dl.recv2), static_cast<uint4*>(a->dz2), world, N, vec_per_slice);
+    const unsigned ublocks = (unsigned)((nvec + 255) / 256 < 148u * 8u ? (nvec + 255) / 256 : 148u * 8u);
+
+    // 1. local statistics -> all-gather of the 7 D-float packs
+    if (int rc = abt_bt_dist_stats_local(a->z1, a->z2, a->dtype, N, world, D, Dr, a->workspace, stream_)) return rc;
+    chain(st, c->ev[E_P0], c->cs2);
+    ABT_NCCL_OK(g_nccl.AllGather(ws + L.pack_local, ws + L.pack_all, 7 * (size_t)D, ncclFloat32, c->comm2, c->cs2));
+    chain(c->cs2, c->ev[E_P1], st);
+    // 2. global statistics + standardised local rows (+ the column-blocked copy of view 1)
+    if (int rc = abt_bt_dist_normalize(a->z1, a->z2, a->dtype, N, world, rank, D, Dr, a->eps, a->momentum, a->running_mean, a->running_var,
+                                       a->workspace, stream_)) return rc;
+    cudaEventRecord(c->ev[E_N], st);
+    cudaStreamWaitEvent(c->cs, c->ev[E_N], 0);
+    cudaStreamWaitEvent(c->cs2, c->ev[E_N], 0);
+    // measured on B200 / NVSwitch at N = 1024 per rank, D = 8192: at 2 ranks the C-block exchange (D^2 / 2 bytes) costs what the second
+    // CORR pass costs (0.96 vs 0.93 ms per step), at 8 ranks the exchange schedule wins (1.06 vs 1.14 ms)
+    const bool xchg = need == 3 && (Dr % 64) == 0 && (g_dist_xchg == 1 || (g_dist_xchg < 0 && world >= 4));
+    if (xchg) {
+        // Exchange schedule.  View 2 is gathered first; CORR (A = the view-1 columns of this rank's dimensions, which arrive by a small
+        // all-to-all) and the dz1 GEMM need nothing else and run while view 1 is still crossing NVLink.  The transposed block of C comes
+        // from an all-to-all of C blocks instead of a second CORR pass (6 N D^2 executed FLOP per rank, as on one GPU).
+        ABT_NCCL_OK(g_nccl.AllGather(zh2 + (size_t)rank * N * D, zh2, (size_t)N * D, ncclFloat16, c->comm, c->cs));
+        cudaEventRecord(c->ev[E_A], c->cs);
+        ABT_NCCL_OK(g_nccl.AllGather(zh1 + (size_t)rank * N * D, zh1, (size_t)N * D, ncclFloat16, c->comm, c->cs));
+        cudaEventRecord(c->ev[E_B], c->cs);
+        if (int rc = all_to_all(c, c->comm2, ws + L.zh1_blk, ws + L.zs1, (size_t)N * Dr, ABT_DTYPE_F16, c->cs2)) return rc;
+        cudaEventRecord(c->ev[E_S], c->cs2);
+        if (a->overlap_cb != nullptr) a->overlap_cb(a->overlap_user);
+        cudaStreamWaitEvent(st, c->ev[E_A], 0);
+        cudaStreamWaitEvent(st, c->ev[E_S], 0);
+        if (int rc = dist_rows_call(a->dtype, N, world, D, R0, Dr, a->alpha, a->lambda, a->hsic, a->grad_scale, need, 8 | 1, parts, ws + dl.dzr1,
+                                    ws + dl.dzr2, a->workspace, st, true)) return rc;
+        chain(st, c->ev[E_C3], c->cs2);
+        if (int rc = all_to_all(c, c->comm2, ws + L.c1, ws + L.c2, (size_t)Dr * Dr, ABT_DTYPE_F16, c->cs2)) return rc;      // C[rows_r, cols_q] -> rank q
+        cudaEventRecord(c->ev[E_C], c->cs2);
+        if (int rc = dist_rows_call(a->dtype, N, world, D, R0, Dr, a->alpha, a->lambda, a->hsic, a->grad_scale, need, 8 | 2, parts, ws + dl.dzr1,
+                                    ws + dl.dzr2, a->workspace, st, true)) return rc;
+        chain(st, c->ev[E_G1], c->cs2);
+        if (int rc = all_to_all(c, c->comm2, ws + dl.dzr1, ws + dl.recv1, slice, a->dtype, c->cs2)) return rc;
+        ABT_NCCL_OK(g_nccl.AllReduce(parts, parts, 3, ncclFloat64, ncclSum, c->comm2, c->cs2));
+        cudaEventRecord(c->ev[E_D], c->cs2);
+        cudaStreamWaitEvent(st, c->ev[E_B], 0);
+        cudaStreamWaitEvent(st, c->ev[E_C], 0);
+        if (int rc = dist_rows_call(a->dtype, N, world, D, R0, Dr, a->alpha, a->lambda, a->hsic, a->grad_scale, need, 8 | 4, parts, ws + dl.dzr1,
+                                    ws + dl.dzr2, a->workspace, st, true)) return rc;
+        chain(st, c->ev[E_G2], c->cs2);
+        if (int rc = all_to_all(c, c->comm2, ws + dl.dzr2, ws + dl.recv2, slice, a->dtype, c->cs2)) return rc;
+        cudaEventRecord(c->ev[E_E], c->cs2);
+        cudaStreamWaitEvent(st, c->ev[E_D], 0);
+        bt_unpermute_kernel<16><<<ublocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(ws + dl.recv1), static_cast<uint4*>(a->dz1), world, N, vec_per_slice);
+        bt_dist_loss_kernel<<<1, 32, 0, st>>>(parts, a->alpha, a->lambda, a->hsic, D, world, a->loss_out);
+        cudaStreamWaitEvent(st, c->ev[E_E], 0);
+        bt_unpermute_kernel<16><<<ublocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(ws + dl.recv2), static_cast<uint4*>(a->dz2), world, N, vec_per_slice);
+    } else {
+        // Plain schedule: both views gathered, then the row block of C and of C^T (second CORR pass); the all-to-all of dz1 overlaps
+        // the dz2 GEMM
+        ABT_NCCL_OK(g_nccl.GroupStart());
+        ABT_NCCL_OK(g_nccl.AllGather(zh1 + (size_t)rank * N * D, zh1, (size_t)N * D, ncclFloat16, c->comm, c->cs));
+        ABT_NCCL_OK(g_nccl.AllGather(zh2 + (size_t)rank * N * D, zh2, (size_t)N * D, ncclFloat16, c->comm, c->cs));
+        ABT_NCCL_OK(g_nccl.GroupEnd());
+        cudaEventRecord(c->ev[E_A], c->cs);
+        if (a->overlap_cb != nullptr) a->overlap_cb(a->overlap_user);
+        cudaStreamWaitEvent(st, c->ev[E_A], 0);
+        const int phase_a = need == 3 ? 1 : 0;
+        if (int rc = dist_rows_call(a->dtype, N, world, D, R0, Dr, a->alpha, a->lambda, a->hsic, a->grad_scale, need, phase_a, parts, ws + dl.dzr1,
+                                    ws + dl.dzr2, a->workspace, st)) return rc;
+        chain(st, c->ev[E_G1], c->cs2);
+        if (need & 1) { if (int rc = all_to_all(c, c->comm2, ws + dl.dzr1, ws + dl.recv1, slice, a->dtype, c->cs2)) return rc; }
+        if (need == 2) { if (int rc = all_to_all(c, c->comm2, ws + dl.dzr2, ws + dl.recv2, slice, a->dtype, c->cs2)) return rc; }
+        ABT_NCCL_OK(g_nccl.AllReduce(parts, parts, 3, ncclFloat64, ncclSum, c->comm2, c->cs2));
+        cudaEventRecord(c->ev[E_D], c->cs2);
+        if (need == 3) {
+            if (int rc = dist_rows_call(a->dtype, N, world, D, R0, Dr, a->alpha, a->lambda, a->hsic, a->grad_scale, need, 2, parts, ws + dl.dzr1,
+                                        ws + dl.dzr2, a->workspace, st)) return rc;
+            chain(st, c->ev[E_G2], c->cs2);
+            if (int rc = all_to_all(c, c->comm2, ws + dl.dzr2, ws + dl.recv2, slice, a->dtype, c->cs2)) return rc;
+            cudaEventRecord(c->ev[E_E], c->cs2);
+        }
+        cudaStreamWaitEvent(st, c->ev[E_D], 0);
+        if (need & 1) bt_unpermute_kernel<16><<<ublocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(ws + dl.recv1), static_cast<uint4*>(a->dz1), world, N, vec_per_slice);
+        if (need == 2) bt_unpermute_kernel<16><<<ublocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(ws + dl.recv2), static_cast<uint4*>(a->dz2), world, N, vec_per_slice);
+        bt_dist_loss_kernel<<<1, 32, 0, st>>>(parts, a->alpha, a->lambda, a->hsic, D, world, a->loss_out);
+        if (need == 3) {
+            cudaStreamWaitEvent(st, c->ev[E_E], 0);
+            bt_unpermute_kernel<16><<<ublocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(ws + dl.recv2), static_cast<uint4*>(a->dz2), world, N, vec_per_slice);
+        }
     }
     count_launch(need == 3 ? 3 : (need ? 2 : 1));
     cudaError_t e = cudaGetLastError();

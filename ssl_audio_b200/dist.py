@@ -159,7 +159,7 @@ _CUDA_BACKEND = CudaBackend()
 
 class NativeStep:
     """ONE library call per step (abt_bt_dist_step): private NCCL communicator + communication stream owned by the library.
-    The communicator is created once per (process group, device); its 128-byte NCCL id travels over torch.distributed."""
+    The communicator is created once per (process group, device); its NCCL ids (256 bytes) travel over torch.distributed."""
 
     _comms = {}
     _ws = {}
@@ -170,7 +170,7 @@ class NativeStep:
         if key not in cls._comms:
             lib = _lib.load()
             world, rank = dist.get_world_size(group), dist.get_rank(group)
-            ident = C.create_string_buffer(128)
+            ident = C.create_string_buffer(256)        # two NCCL ids: one communicator for the large gathers, one for the small exchanges
             if rank == 0:
                 _lib.check(lib.abt_comm_unique_id(ident))
             box = [bytes(ident.raw)]
@@ -178,7 +178,7 @@ class NativeStep:
             dist.broadcast_object_list(box, src=src, group=group)
             h = C.c_void_p()
             with torch.cuda.device(device):
-                _lib.check(lib.abt_comm_create(world, rank, C.create_string_buffer(box[0], 128), C.byref(h)))
+                _lib.check(lib.abt_comm_create(world, rank, C.create_string_buffer(box[0], 256), C.byref(h)))
             cls._comms[key] = h
         return cls._comms[key]
 

@@ -8,6 +8,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import abt_oracle as O
 from ssl_audio_b200 import dist as D
+from ssl_audio_b200 import _lib
 
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
@@ -15,7 +16,7 @@ dev = torch.device("cuda", lr)
 dist.init_process_group("nccl", device_id=dev)
 ok = True
 def rel(a, b): return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
-for (n, d, hsic, dt, need) in [(64, 256, False, torch.float32, (True, True)), (48, 512, True, torch.float32, (True, True)),
+for (n, d, hsic, dt, need) in [(64, 256, False, torch.float32, (True, True)), (48, 512, True, torch.float32, (True, True)), (96, 1024, True, torch.float32, (True, True)),
                                 (128, 2048, False, torch.bfloat16, (True, True)), (64, 256, False, torch.float32, (False, True))]:
     if d % (8 * world):
         continue
@@ -23,8 +24,9 @@ for (n, d, hsic, dt, need) in [(64, 256, False, torch.float32, (True, True)), (4
     z1 = torch.from_numpy(z1g[rank * n:(rank + 1) * n]).to(dev).to(dt)
     z2 = torch.from_numpy(z2g[rank * n:(rank + 1) * n]).to(dev).to(dt)
     rl, r1, r2, _ = O.bt_loss_forward_backward(z1g, z2g, 1.0, 0.005, hsic)
-    for mode in ("native", "c10d"):
+    for mode in ("native", "plain", "c10d"):
         os.environ["ABT_DIST_C10D"] = "1" if mode == "c10d" else "0"
+        _lib.load().abt_debug_set(7, 0 if mode == "plain" else 1)       # plain = native step without the exchange schedule
         rm, rv = torch.zeros(d, device=dev), torch.ones(d, device=dev)
         hook_calls = []
         loss, dz1, dz2 = D.bt_loss_fwd_bwd_global(z1, z2, 1.0, 0.005, hsic, running_mean=rm, running_var=rv, need_dz1=need[0], need_dz2=need[1],
