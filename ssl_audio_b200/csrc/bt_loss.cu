@@ -37,6 +37,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 namespace abt {
@@ -936,6 +937,16 @@ static int num_sms() {
     return g_num_sms;
 }
 
+// ABT_DEBUG_SYNC=1: synchronise after every stage of a loss evaluation and report which one failed
+static int debug_sync(cudaStream_t st, const char* stage) {
+    static const bool on = std::getenv("ABT_DEBUG_SYNC") != nullptr;
+    if (!on) return 0;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "stage '%s' failed: %s", stage, cudaGetErrorString(e));
+    return 0;
+}
+
 static int g_cta_group = 2;     // 2 = CTA-pair kernel (default), 1 = single-CTA kernel (abt_debug_set key 6)
 static int g_dist_xchg = -1;    // multi-GPU exchange schedule: -1 = auto (4 ranks and more), 0 = never, 1 = whenever possible (abt_debug_set key 7)
 
@@ -1035,6 +1046,7 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
                                                                   a.momentum, partials, stats, need != 0 ? zh1 : nullptr, need != 0 ? zh2 : nullptr,
                                                                   a.running_mean, a.running_var, loss_acc);
         count_launch(2);
+        if (int rc = debug_sync(stream, "statistics")) return rc;
         if (a.hsic && need != 0) {
             bt_rowsum_kernel<<<N, 256, 0, stream>>>(zq1, N, D, stats + S_MU1 * D, stats + S_R1 * D, rs1);
             bt_rowsum_kernel<<<N, 256, 0, stream>>>(zq2, N, D, stats + S_MU2 * D, stats + S_R2 * D, rs2);
@@ -1057,6 +1069,7 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
     const int cg = g_cta_group == 1 ? 1 : 2;
     const int row_tiles = (RC + BM * cg - 1) / (BM * cg);
     // ---- CORR: C[rows, :] (and, in row-block mode, C^T[rows, :] with the views swapped)
+    if (int rc = debug_sync(stream, "row sums (HSIC)")) return rc;
     if (timed) cudaEventRecord(tev[1], stream);
     if (front) {
         CUtensorMap m1, m2;
@@ -1079,7 +1092,8 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         if (a.zh_mode) { c0.row_nmu = stats + S_ZERO * D; c0.row_rho = stats + S_INVN * D; c0.col_mu = stats + S_ZERO * D; c0.col_r = stats + S_ONE * D; }
         c0.accumulate_loss = 1; c0.c_out = C1;
         c0.row_sq = (need & 1) ? accs + A_SQ1 * D : nullptr; c0.row_sum = accs + A_SUM1 * D;
-        c0.col_sq = (!a.rows_mode && (need & 2)) ? accs + A_SQ2 * D : nullptr;      // exchange mode: bt_colsq_kernel on the received block c0.col_sum = accs + A_SUM2 * D;
+        // (exchange mode: the column sums come from bt_colsq_kernel on the received block)
+        c0.col_sq = (!a.rows_mode && (need & 2)) ? accs + A_SQ2 * D : nullptr; c0.col_sum = accs + A_SUM2 * D;
         c1 = c0;
         c1.row_nmu = stats + S_NMU2 * D; c1.row_rho = stats + S_RHO2 * D; c1.col_mu = stats + S_MU1 * D; c1.col_r = stats + S_R1 * D;
         if (a.zh_mode) { c1.row_nmu = c0.row_nmu; c1.row_rho = c0.row_rho; c1.col_mu = c0.col_mu; c1.col_r = c0.col_r; }
@@ -1094,6 +1108,7 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         if (int rc = make_map_16(&mc2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, second ? C2 : C1, RC, D, 64, 32)) return rc;
         if (int rc = launch_umma(cg, m1, m2, m2, m1, mc1, mc2, p, stream)) return rc;
     }
+    if (int rc = debug_sync(stream, "CORR")) return rc;
     if (timed) cudaEventRecord(tev[2], stream);
     // ---- GRAD (+ batch-norm backward epilogue)
     const int gneed = ((pmask & 2) ? (need & 1) : 0) | ((pmask & 4) ? (need & 2) : 0);     // gradient passes of THIS call
@@ -1155,6 +1170,7 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         bt_loss_scalar_kernel<<<1, 32, 0, stream>>>(loss_acc, a.alpha, a.lambda, a.hsic, D, a.loss_out);
         count_launch();
     }
+    if (int rc = debug_sync(stream, "GRAD")) return rc;
     if (timed) { cudaEventRecord(tev[3], stream); ++g_timing.count; }
     if (a.loss_parts_out != nullptr && front) cudaMemcpyAsync(a.loss_parts_out, loss_acc, 3 * sizeof(double), cudaMemcpyDeviceToDevice, stream);
     cudaError_t e = cudaGetLastError();
@@ -1451,6 +1467,7 @@ struct NcclApi {
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*GroupStart)();
     ncclResult_t (*GroupEnd)();
+    ncclResult_t (*AlltoAll)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);   // NCCL >= 2.28, optional
     bool ok = false;
 };
 
@@ -1474,6 +1491,7 @@ static int load_nccl() {
     ABT_NCCL_SYM(GroupStart, "ncclGroupStart");
     ABT_NCCL_SYM(GroupEnd, "ncclGroupEnd");
 #undef ABT_NCCL_SYM
+    *reinterpret_cast<void**>(&g_nccl.AlltoAll) = dlsym(h, "ncclAlltoAll");
     g_nccl.ok = true;
     return 0;
 }
@@ -1591,6 +1609,10 @@ static ncclDataType_t nccl_dtype(int dtype) { return dtype == ABT_DTYPE_BF16 ? n
 // all-to-all of (world) equal slices: slice q of `send` goes to rank q, slice q of `recv` comes from rank q
 static int all_to_all(abt_comm* c, ncclComm_t comm, const void* send, void* recv, size_t slice_elems, int dtype, cudaStream_t st) {
     const size_t esz = dtype == ABT_DTYPE_F32 ? 4 : 2;
+    if (g_nccl.AlltoAll != nullptr) {          // one call instead of 2 R point-to-point operations
+        ABT_NCCL_OK(g_nccl.AlltoAll(send, recv, slice_elems, nccl_dtype(dtype), comm, st));
+        return 0;
+    }
     ABT_NCCL_OK(g_nccl.GroupStart());
     for (int q = 0; q < c->world; ++q) {
         ABT_NCCL_OK(g_nccl.Send(static_cast<const uint8_t*>(send) + (size_t)q * slice_elems * esz, slice_elems, nccl_dtype(dtype), q, comm, st));
