@@ -135,6 +135,7 @@ class ViewPlanner:
         self._lib = lib
         self._key = np.empty(624, dtype=np.uint32)
         self._staging = {}
+        self._layouts = {}
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -156,9 +157,12 @@ class ViewPlanner:
         lib, h = self._lib, self._h
         use_np = self._uses_numpy or time_crop_range > 0
         use_py = self._uses_pyrandom or wav_crop_range > 0
-        total, o1, o2, o3 = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
-        _lib.check(lib.abt_planner_packed_bytes(h, n_clips, C.byref(total), C.byref(o1), C.byref(o2), C.byref(o3)))
-        nbytes = total.value
+        lay = self._layouts.get(n_clips)
+        if lay is None:
+            total, o1, o2, o3 = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+            _lib.check(lib.abt_planner_packed_bytes(h, n_clips, C.byref(total), C.byref(o1), C.byref(o2), C.byref(o3)))
+            lay = self._layouts[n_clips] = (total.value, o1.value, o2.value, o3.value)
+        nbytes, off1, off2, off3 = lay
         slot = -1
         if device is not None:
             st = self._staging.get(device)
@@ -185,13 +189,13 @@ class ViewPlanner:
                                                          buf.ctypes.data, buf.nbytes))
         nv = self.n_views
         params = buf[:48 * nv * n_clips].view(VIEW_DTYPE).reshape(n_clips, nv)
-        starts = buf[o1.value:o1.value + 4 * n_clips].view(np.int32)
-        wav_starts = buf[o2.value:o2.value + 4 * n_clips].view(np.int32)
-        slots = buf[o3.value:o3.value + 4 * n_clips].view(np.int32)
+        starts = buf[off1:off1 + 4 * n_clips].view(np.int32)
+        wav_starts = buf[off2:off2 + 4 * n_clips].view(np.int32)
+        slots = buf[off3:off3 + 4 * n_clips].view(np.int32)
         plan = BatchPlan(starts, wav_starts, params, slots)
         if device is not None:
             dev = st.upload(slot, nbytes)
             base = dev.data_ptr()
             plan.dev = dev
-            plan.params_ptr, plan.starts_ptr, plan.wav_starts_ptr, plan.slots_ptr = base, base + o1.value, base + o2.value, base + o3.value
+            plan.params_ptr, plan.starts_ptr, plan.wav_starts_ptr, plan.slots_ptr = base, base + off1, base + off2, base + off3
         return plan
