@@ -196,7 +196,7 @@ def run_reference(args):
 def _config(args):
     return {"workload": f"hot-path step: frontend (BASELINE config 2: {args.batch} clips x {args.clip_seconds:g} s @16 kHz -> crop-first 64-mel log-mel -> "
                         f"two 96-frame views) + Barlow Twins loss fwd/bwd (N={args.batch} rows/GPU, D={args.dim}, bf16 in / fp32 accumulate)",
-            "per_gpu_batch": args.batch, "clip_seconds": args.clip_seconds, "projector_out_dim": args.dim, "frontend_mode": "crop-first (mode C)", "streams": "frontend and loss of a step overlap on two CUDA streams; at >= 4 GPUs the frontend is enqueued while the embedding all-gather is in flight",
+            "per_gpu_batch": args.batch, "clip_seconds": args.clip_seconds, "projector_out_dim": args.dim, "frontend_mode": "crop-first (mode C)", "streams": "frontend and loss of a step are issued on two CUDA streams (independent inputs); at >= 4 GPUs the frontend is enqueued while the embedding all-gather is in flight",
             "l2": "inputs larger than L2 (655 MB of waveforms, 128 MiB correlation matrix per step)", "parallelism": f"dp{args.gpus}"}
 
 
@@ -254,28 +254,41 @@ def run_ours(args):
     side_stream = torch.cuda.Stream(dev, priority=0)          # lowest priority; NCCL runs on a high-priority stream (below)
 
     cur = {}
+    inputs_ready = torch.cuda.Event()
 
     def frontend_on_side_stream():
-        side_stream.wait_stream(main_stream)
+        side_stream.wait_event(inputs_ready)
         with torch.cuda.stream(side_stream):
             cur["views"] = fe(cur["wav"])
 
-    # measured on this pool: at 2 ranks NCCL's all-gather kernel and the frontend kernels delay each other (2.9 ms vs 1.1 ms per step),
-    # at 8 ranks the overlap hides the frontend completely (1.26 ms vs 1.54 ms); BENCH_HOOK=0/1 overrides
-    use_hook = world >= 4 if os.environ.get("BENCH_HOOK") is None else os.environ["BENCH_HOOK"] == "1"
+    # Default: one host thread; at >= 4 ranks the frontend is enqueued from the objective's comm-overlap hook (right after the embedding
+    # all-gathers have been launched).  BENCH_THREAD=1 moves the frontend's host side to a worker thread instead (measured: no gain, the
+    # step is device-bound); BENCH_HOOK=0/1 overrides the hook placement.
+    use_thread = os.environ.get("BENCH_THREAD", "0") == "1"
+    # measured on this pool: at 2 ranks NCCL's all-gather kernels and the frontend kernels delay each other when the frontend is enqueued
+    # right behind the gathers; at 4 and 8 ranks that placement hides the frontend completely
+    use_hook = (world >= 4 if os.environ.get("BENCH_HOOK") is None else os.environ["BENCH_HOOK"] == "1") and not use_thread
+    pool = None
     if use_hook:
-        # multi-GPU: the frontend is enqueued from inside the objective, right after the all-gather of the standardised
-        # embeddings has been launched, so that its kernels run while the embeddings cross NVLink
         crit.comm_overlap_hook = frontend_on_side_stream
+    elif use_thread:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=1, initializer=lambda: torch.cuda.set_device(local_rank))
 
     def step(wav_d, z1_d, z2_d):
         a = z1_d.detach().requires_grad_(True)
         b = z2_d.detach().requires_grad_(True)
         cur["wav"] = wav_d
-        if not use_hook:
+        inputs_ready.record(main_stream)
+        fut = None
+        if pool is not None:
+            fut = pool.submit(frontend_on_side_stream)
+        elif not use_hook:
             frontend_on_side_stream()
         loss = crit(b, a, ngcrops_each=1)          # forward(student, teacher) as main.py:115 calls it
         loss.backward()
+        if fut is not None:
+            fut.result()
         main_stream.wait_stream(side_stream)
         return cur["views"], loss, a.grad, b.grad
 
