@@ -139,6 +139,12 @@ int abt_views_fwd(const abt_views_args* args, abt_stream_t stream);
 int abt_bank_push(const float* x, int64_t x_stride, int n_clips, int clip_elems, float* bank, int64_t bank_slot_stride,
                   const int32_t* slot, abt_stream_t stream);
 
+/* NormalizeBatch (augmentations.py:217-232; applied to every crop at main.py:62-66 under --post_norm): x (n_batch, n_channels, hw)
+ * fp32 -> out = (x - mean_c) / clamp(std_c, eps), mean and UNBIASED std per channel over the batch and both spatial axes.
+ * workspace: abt_normalize_batch_workspace_bytes() bytes of device memory. */
+int abt_normalize_batch_workspace_bytes(int n_channels, size_t* bytes);
+int abt_normalize_batch(const float* x, int n_batch, int n_channels, int hw, float* out, void* workspace, abt_stream_t stream);
+
 /* ===================================================================================== *
  *  Host planner [host]: replays the reference's RNG draw order (numpy legacy MT19937 global
  *  state + CPython `random` MT19937) for a whole batch and emits the parameter table.

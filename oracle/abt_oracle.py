@@ -355,6 +355,16 @@ def frontend_clip_wav_path(wav: np.ndarray, mel_cfg: MelConfig, unit_sec: float,
     return views, dict(start=start, views=recs), lms
 
 
+def normalize_batch(x: np.ndarray) -> np.ndarray:
+    """NormalizeBatch.forward (augmentations.py:228-231) with its default axis [0, 2, 3]: per-channel mean and UNBIASED std
+    (torch.std default) over batch, frequency and time, std clamped to [finfo.eps, finfo.max].  x: (B, C, F, T) float32."""
+    x = np.asarray(x, dtype=np.float32)
+    mean = x.astype(np.float64).mean(axis=(0, 2, 3), keepdims=True)
+    std = x.astype(np.float64).std(axis=(0, 2, 3), ddof=1, keepdims=True)
+    std = np.clip(std, F32_EPS, np.finfo(np.float32).max)
+    return ((x - mean) / std).astype(np.float32)
+
+
 # --------------------------------------------------------------------------------------
 # Barlow Twins objective
 # --------------------------------------------------------------------------------------

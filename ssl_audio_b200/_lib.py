@@ -121,6 +121,8 @@ SIGNATURES = {
                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "abt_views_fwd": (C.c_int, [C.POINTER(ViewsArgs), C.c_void_p]),
     "abt_bank_push": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "abt_normalize_batch_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
+    "abt_normalize_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "abt_planner_create": (C.c_int, [C.POINTER(PlanConfig), C.POINTER(C.c_void_p)]),
     "abt_planner_destroy": (C.c_int, [C.c_void_p]),
     "abt_planner_set_numpy_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),

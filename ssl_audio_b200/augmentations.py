@@ -19,7 +19,7 @@ import torch.nn as nn
 from . import _lib
 from .planner import VIEW_DTYPE, BatchPlan, ViewPlanner
 
-__all__ = ["RandomResizeCrop", "RandomLinearFader", "MixupBYOLA", "log_mixup_exp", "MixGaussianNoise", "ViewEngine"]
+__all__ = ["RandomResizeCrop", "RandomLinearFader", "MixupBYOLA", "log_mixup_exp", "MixGaussianNoise", "NormalizeBatch", "ViewEngine"]
 
 
 def _as_batch(x: torch.Tensor) -> Tuple[torch.Tensor, bool]:
@@ -270,3 +270,37 @@ class MixGaussianNoise(nn.Module):
 
     def forward(self, lms):
         raise NotImplementedError("MixGaussianNoise is outside the accelerated hot path (args.Gnoise must be False)")
+
+
+class NormalizeBatch(nn.Module):
+    """Normalization of an input batch (reference: augmentations.py:217-232, used per crop at main.py:62-66 under --post_norm):
+    `(X - X.mean(axis)) / clamp(X.std(axis), eps)` with `axis=[0, 2, 3]` -- per-channel statistics over batch, frequency and time,
+    unbiased std -- as two CUDA launches (abt_normalize_batch).  X: (B, C, F, T) CUDA fp32."""
+
+    def __init__(self, axis=[0, 2, 3]):
+        super().__init__()
+        if list(axis) != [0, 2, 3]:
+            raise NotImplementedError("only axis=[0, 2, 3] (the reference's only setting) is on the GPU path")
+        self.axis = axis
+        self._ws = {}
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        _check_cuda_f32(X, "X")
+        if X.dim() != 4:
+            raise ValueError(f"expected a batch (B, C, F, T), got {tuple(X.shape)}")
+        X = X.contiguous()
+        B, Cn, F, T = (int(v) for v in X.shape)
+        out = torch.empty_like(X)
+        lib = _lib.load()
+        key = (X.device.index, Cn)
+        if key not in self._ws:
+            nbytes = C.c_size_t()
+            _lib.check(lib.abt_normalize_batch_workspace_bytes(Cn, C.byref(nbytes)))
+            self._ws[key] = torch.empty(nbytes.value, dtype=torch.uint8, device=X.device)
+        with torch.cuda.device(X.device):
+            _lib.check(lib.abt_normalize_batch(X.data_ptr(), B, Cn, F * T, out.data_ptr(), self._ws[key].data_ptr(),
+                                               torch.cuda.current_stream(X.device).cuda_stream))
+        return out
+
+    def __repr__(self):
+        return self.__class__.__name__ + f"(axis={self.axis})"

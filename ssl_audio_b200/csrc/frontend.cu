@@ -414,6 +414,75 @@ __global__ void __launch_bounds__(128) wav_span_gather_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------
+// NormalizeBatch (augmentations.py:217-232, applied per crop at main.py:62-66): per-channel mean and UNBIASED std over the
+// batch, frequency and time axes, out = (x - mean) / max(std, eps).  Two launches: block partial sums (fp32 per thread over a
+// short strip, double across threads and blocks), then every block folds the partials and normalises its share.
+// ------------------------------------------------------------------------------------------
+constexpr int kNbBlocks = 256;     // partial sums per channel
+
+__global__ void __launch_bounds__(256) batch_stats_kernel(const float* __restrict__ x, int n_batch, int n_ch, int hw, double* __restrict__ partials) {
+    __shared__ double red[2][8];
+    const int ch = blockIdx.y;
+    const long long per_ch = (long long)n_batch * hw;
+    double s1 = 0.0, s2 = 0.0;
+    const float shift = __ldg(x + (size_t)ch * hw);      // shifted data: a large common offset must not cancel in the fp32 squares
+    for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i0 < per_ch; i0 += (long long)gridDim.x * blockDim.x * 8) {
+        float a = 0.f, q = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const long long i = i0 + k;
+            if (i < per_ch) {
+                const float v = __ldg(x + ((i / hw) * n_ch + ch) * hw + (i % hw)) - shift;
+                a += v; q = fmaf(v, v, q);
+            }
+        }
+        s1 += (double)a; s2 += (double)q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int w = 0; w < 8; ++w) { t1 += red[0][w]; t2 += red[1][w]; }
+        partials[((size_t)ch * gridDim.x + blockIdx.x) * 2] = t1;
+        partials[((size_t)ch * gridDim.x + blockIdx.x) * 2 + 1] = t2;
+    }
+}
+
+__global__ void __launch_bounds__(256) batch_norm_apply_kernel(const float* __restrict__ x, float* __restrict__ out, int n_batch, int n_ch, int hw,
+                                                               const double* __restrict__ partials, int n_partials) {
+    __shared__ double red[2][8];
+    __shared__ float ms[2];
+    const int ch = blockIdx.y;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) {
+        s1 += partials[((size_t)ch * n_partials + i) * 2];
+        s2 += partials[((size_t)ch * n_partials + i) * 2 + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int w = 0; w < 8; ++w) { t1 += red[0][w]; t2 += red[1][w]; }
+        const double n = (double)n_batch * hw;
+        const double dmean = t1 / n;                                                      // mean of the shifted data
+        const double var = n > 1.0 ? fmax((t2 - t1 * dmean) / (n - 1.0), 0.0) : 0.0;     // torch.std: unbiased
+        ms[0] = (float)((double)__ldg(x + (size_t)ch * hw) + dmean);
+        ms[1] = 1.0f / fmaxf((float)sqrt(var), kF32Eps);                                  // clamp(std, finfo.eps, finfo.max)
+    }
+    __syncthreads();
+    const float mean = ms[0], inv = ms[1];
+    const long long per_ch = (long long)n_batch * hw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_ch; i += (long long)gridDim.x * blockDim.x) {
+        const long long o = ((i / hw) * n_ch + ch) * hw + (i % hw);
+        out[o] = (__ldg(x + o) - mean) * inv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host: plan tables
 // ------------------------------------------------------------------------------------------
 static std::vector<float> linspace_f32(double start, double end, int steps) {
@@ -662,6 +731,28 @@ extern "C" int abt_bank_push(const float* x, int64_t x_stride, int n_clips, int 
     dim3 grid((clip_elems / 4 + 255) / 256, n_clips);
     bank_push_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, x_stride, clip_elems, bank, bank_slot_stride, slot);
     count_launch();
+    ABT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int abt_normalize_batch_workspace_bytes(int n_channels, size_t* bytes) {
+    if (bytes == nullptr || n_channels < 1) return set_error(ABT_ERR_ARG, "bad argument");
+    *bytes = sizeof(double) * 2 * (size_t)kNbBlocks * n_channels;
+    return 0;
+}
+
+extern "C" int abt_normalize_batch(const float* x, int n_batch, int n_channels, int hw, float* out, void* workspace, abt_stream_t stream) {
+    if (n_batch == 0) return 0;
+    if (x == nullptr || out == nullptr || workspace == nullptr) return set_error(ABT_ERR_ARG, "null argument");
+    if (n_batch < 0 || n_channels < 1 || n_channels > 65535 || hw < 1) return set_error(ABT_ERR_ARG, "bad shape");
+    if (int rc = check_device_sm100()) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const dim3 grid(kNbBlocks, n_channels);
+    batch_stats_kernel<<<grid, 256, 0, st>>>(x, n_batch, n_channels, hw, static_cast<double*>(workspace));
+    const long long per_ch = (long long)n_batch * hw;
+    const unsigned blocks = (unsigned)((per_ch + 1023) / 1024 < 148 * 8 ? (per_ch + 1023) / 1024 : 148 * 8);
+    batch_norm_apply_kernel<<<dim3(blocks, n_channels), 256, 0, st>>>(x, out, n_batch, n_channels, hw, static_cast<const double*>(workspace), kNbBlocks);
+    count_launch(2);
     ABT_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -240,3 +240,58 @@ def test_pinned_host_waveforms_zero_copy_span_path_is_bit_identical():
     assert origin.cpu().tolist()[0] == 0 and origin.cpu().tolist()[1] == 32000 - n.value
     with pytest.raises(RuntimeError):
         S.BatchFrontend(_args(), norm_stats=AS_STATS)(torch.from_numpy(wav))          # pageable host memory: refused
+
+
+def test_bench_size_frontend_1024_clips_of_10s():
+    """BASELINE config 2 at full size (1024 clips x 10 s, crop-first): crop starts equal the reference's np.random.randint draws
+    interleaved with the view draws (replayed by the oracle), eight spot-checked clips match the oracle's per-sample path, every
+    output is finite, and the full-log-mel mode agrees with crop-first on the same seed."""
+    import ssl_audio_b200 as S
+    B, L = 1024, 160000
+    g = torch.Generator(device="cuda").manual_seed(0)
+    wav = (0.1 * torch.randn(B, L, device="cuda", generator=g)).clamp_(-1, 1)
+    t = torch.arange(L, device="cuda", dtype=torch.float32) / 16000.0
+    wav += 0.3 * torch.sin(6.2831853 * (100.0 + 6900.0 * torch.rand(B, 1, device="cuda", generator=g)) * t[None, :])
+    np.random.seed(3); random.seed(3)
+    fe = S.BatchFrontend(_args(), norm_stats=AS_STATS, path="lms", mode="crop")
+    views = fe(wav)
+    starts = fe.last_plan.starts.copy()
+    v = torch.stack(views, 1)
+    assert bool(torch.isfinite(v).all())
+    assert starts.min() >= 0 and starts.max() <= 1001 - 97
+    # oracle replay of the first 8 clips (the draws are sequential, so a prefix is enough): same crop starts, same views
+    sub = wav[:8].cpu().numpy()
+    np.random.seed(3); random.seed(3)
+    st = O.MixupState()
+    lms = O.log_mel(sub)
+    for b in range(8):
+        ref, rec, _ = O.frontend_clip_lms_path(lms[b], AS_STATS, O.PairTransformConfig(), st)
+        assert int(starts[b]) == int(rec["start"])
+        assert np.abs(v[b].cpu().numpy() - np.stack(ref)).max() < 2e-3, b
+    # crop-first == full log-mel then crop (same seed -> same draws)
+    np.random.seed(3); random.seed(3)
+    fe2 = S.BatchFrontend(_args(), norm_stats=AS_STATS, path="lms", mode="full")
+    v2 = torch.stack(fe2(wav), 1)
+    assert np.array_equal(fe2.last_plan.starts, starts)
+    assert float((v - v2).abs().max()) < 1e-3
+
+
+def test_normalize_batch_matches_reference_golden(golden_dir):
+    """NormalizeBatch (--post_norm, main.py:62-66) against outputs of the reference module: a batch of log-mels, a multi-channel
+    batch with a large offset (cancellation), and a constant batch (std clamped to eps)."""
+    import ssl_audio_b200 as S
+    g = np.load(os.path.join(golden_dir, "postnorm.npz"))
+    mod = S.NormalizeBatch()
+    for tag in ("a", "b"):
+        y = mod(torch.from_numpy(g[f"{tag}_x"]).cuda()).cpu().numpy()
+        ref = g[f"{tag}_y"]
+        assert np.abs(y - ref).max() <= 1e-3 * max(1.0, np.abs(ref).max()), tag
+        assert np.abs(y - O.normalize_batch(g[f"{tag}_x"])).max() <= 1e-3 * max(1.0, np.abs(ref).max())
+    y = mod(torch.from_numpy(g["c_x"]).cuda()).cpu().numpy()       # constant input: (x - mean) / eps with mean == x -> exactly 0
+    assert np.array_equal(y, g["c_y"])
+    # bench-size batch: statistics of the result are (0, 1)
+    x = torch.randn(1024, 1, 64, 96, device="cuda") * 4.6 - 0.8
+    y = mod(x)
+    assert abs(float(y.mean())) < 1e-4 and abs(float(y.std()) - 1.0) < 1e-4
+    with pytest.raises(RuntimeError):
+        mod(torch.zeros(2, 1, 64, 96))

@@ -168,3 +168,43 @@ def test_full_size_properties_d8192():
         off += (blk ** 2).sum() - (dg ** 2).sum()
     ref_loss = on + 0.005 * off
     assert abs(loss12 - ref_loss) <= TOL * ref_loss, (loss12, ref_loss)
+
+
+def test_bench_size_properties_n1024_d8192():
+    """The bench workload (N = 1024 rows, D = 8192, bf16): same size-independent checks as above -- symmetry of the loss under swapping the
+    views, gradients in the batch-norm null space, 64 spot-checked gradient columns of BOTH views against the closed form, and the loss
+    against a float64 evaluation done row block by row block."""
+    n, d = 1024, 8192
+    z1, z2 = O.synth_embeddings(n, d, seed=2)
+    loss12, g1, g2, _ = _run(z1, z2, torch.bfloat16)
+    loss21, h2, h1, _ = _run(z2, z1, torch.bfloat16)
+    assert abs(loss12 - loss21) <= 1e-5 * abs(loss12)
+    assert _rel(g1, h1.astype(np.float64)) < 1e-2 and _rel(g2, h2.astype(np.float64)) < 1e-2
+    assert np.abs(g1.astype(np.float64).sum(0)).max() < 1e-2 * np.abs(g1).sum(0).max()
+    h1z, _, _, rr1 = O.batchnorm_train(z1.astype(np.float64))
+    h2z, _, _, rr2 = O.batchnorm_train(z2.astype(np.float64))
+    cols = np.arange(3, d, d // 64)
+    ar = np.arange(len(cols))
+    # dz1[:, cols]: rows `cols` of C
+    c_rows = h1z[:, cols].T @ h2z / n
+    G = 2 * 0.005 * c_rows
+    G[ar, cols] = 2 * (c_rows[ar, cols] - 1.0)
+    gh = h2z @ G.T / n
+    ref1 = (gh - gh.mean(0) - h1z[:, cols] * (gh * h1z[:, cols]).mean(0)) * rr1[cols]
+    assert _rel(g1[:, cols], ref1) < TOL + 4e-3
+    # dz2[:, cols]: columns `cols` of C
+    c_cols = h1z.T @ h2z[:, cols] / n
+    G = 2 * 0.005 * c_cols
+    G[cols, ar] = 2 * (c_cols[cols, ar] - 1.0)
+    gh = h1z @ G / n
+    ref2 = (gh - gh.mean(0) - h2z[:, cols] * (gh * h2z[:, cols]).mean(0)) * rr2[cols]
+    assert _rel(g2[:, cols], ref2) < TOL + 4e-3
+    on = off = 0.0
+    for s in range(0, d, 1024):
+        blk = h1z[:, s:s + 1024].T @ h2z / n
+        idx = np.arange(s, min(s + 1024, d))
+        dg = blk[idx - s, idx]
+        on += ((dg - 1) ** 2).sum()
+        off += (blk ** 2).sum() - (dg ** 2).sum()
+    ref_loss = on + 0.005 * off
+    assert abs(loss12 - ref_loss) <= TOL * ref_loss, (loss12, ref_loss)
