@@ -443,6 +443,8 @@ struct UmmaParams {
     int tiles_m, tiles_n, kblocks;   // per pass
     int pass_count;
     int bn;            // UMMA N of this launch (multiple of 16, <= 256)
+    int split_from;    // GRAD: tiles >= split_from (the last, partial wave) are processed as two half-width work items each, so that
+                       // the tail of the persistent schedule costs half a tile time; = tile count when nothing is split
     int ab_format;     // operand type of this launch: 1 = bf16, 0 = fp16
     int hsic;
     int write_c;
@@ -457,10 +459,14 @@ struct UmmaParams {
     PassCfg pass[2];
 };
 
-__device__ __forceinline__ void decode_work(const UmmaParams& p, int w, int& pass, int& tm, int& tn) {
+// work item -> (pass, row tile, column tile, half): half = -1 for a full-width tile, 0 / 1 for the halves of a split tile
+__device__ __forceinline__ void decode_work(const UmmaParams& p, int w, int& pass, int& tm, int& tn, int& half) {
+    int tile = w;
+    half = -1;
+    if (w >= p.split_from) { tile = p.split_from + ((w - p.split_from) >> 1); half = (w - p.split_from) & 1; }
     const int per_pass = p.tiles_m * p.tiles_n;
-    pass = w / per_pass;
-    const int r = w % per_pass;
+    pass = tile / per_pass;
+    const int r = tile % per_pass;
     tn = r % p.tiles_n; tm = r / p.tiles_n;
 }
 
@@ -565,10 +571,10 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t colstat_s = smem_u32(smem + kPipeBytes + kStoreBytes + 256);          // [acc][mu | r][256] floats
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_work = p.tiles_m * p.tiles_n * p.pass_count;      // tiles_m counts (128 * CG)-row tiles
+    const int total_tiles = p.tiles_m * p.tiles_n * p.pass_count;     // tiles_m counts (128 * CG)-row tiles
+    const int total_work = total_tiles + (total_tiles - p.split_from);  // split tiles count twice
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;          // 0 = leader of the pair
     const int work0 = blockIdx.x / CG, work_stride = gridDim.x / CG;
-    const int bn_cta = p.bn / CG;                                     // B columns (or rows) staged by this CTA
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapB0);
@@ -595,14 +601,16 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // ================= TMA producer (whole warp runs the loop so that the code stays warp-uniform; one elected lane issues) ==========
         int stage = 0; uint32_t phase = 0;
         for (int w = work0; w < total_work; w += work_stride) {
-            int pass, tm, tn;
-            decode_work(p, w, pass, tm, tn);
+            int pass, tm, tn, half;
+            decode_work(p, w, pass, tm, tn, half);
             tm = tm * CG + (int)rank;                 // this CTA's 128-row tile
             const PassCfg& pc = p.pass[pass];
             const CUtensorMap* mA = pass == 1 ? &mapA1 : &mapA0;
-            const CUtensorMap* mB = pass == 1 ? &mapB1 : &mapB0;
+            // half-width items of the GRAD tail use the B tensor maps with half the box rows (passed in the C-map slots)
+            const CUtensorMap* mB = half < 0 ? (pass == 1 ? &mapB1 : &mapB0) : (pass == 1 ? &mapC1 : &mapC0);
+            const int bn_cta = (half < 0 ? p.bn : p.bn / 2) / CG;               // B columns (or rows) staged by this CTA
             const uint32_t tx = (kABytes + (uint32_t)bn_cta * BK * 2) * CG;     // both CTAs' bytes land on the leader's barrier
-            const int bcol0 = tn * p.bn + (int)rank * bn_cta;
+            const int bcol0 = tn * p.bn + (half > 0 ? p.bn / 2 : 0) + (int)rank * bn_cta;
             const int a_mn = pc.a_mn;
             const int arow = a_mn ? pc.a_col0 + tm * BM : tm * BM;
             const int bdr = pc.blocked_dr;
@@ -662,10 +670,10 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int w = work0; w < total_work; w += work_stride) {
-            int pass, tm, tn;
-            decode_work(p, w, pass, tm, tn);
+            int pass, tm, tn, half;
+            decode_work(p, w, pass, tm, tn, half);
             const bool a_mn = p.pass[pass].a_mn != 0;
-            const uint32_t idesc = make_idesc_f16(BM * CG, p.bn, a_mn ? 1 : 0, b_mn ? 1 : 0, p.ab_format);
+            const uint32_t idesc = make_idesc_f16(BM * CG, half < 0 ? p.bn : p.bn / 2, a_mn ? 1 : 0, b_mn ? 1 : 0, p.ab_format);
             const uint32_t a_hi = a_mn ? hi_mn : hi_k, a_lo = a_mn ? lo_mn : lo_k, a_step = (uint32_t)(a_mn ? p.dc.mn_kstep : p.dc.k_kstep) >> 4;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
@@ -706,8 +714,8 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         int acc = 0; uint32_t acc_phase = 0;
         const int D = p.D;
         for (int w = work0; w < total_work; w += work_stride) {
-            int pass, tm, tn;
-            decode_work(p, w, pass, tm, tn);
+            int pass, tm, tn, half;
+            decode_work(p, w, pass, tm, tn, half);
             tm = tm * CG + (int)rank;
             const PassCfg& pc = p.pass[pass];
             const uint32_t cs_mu = colstat_s + acc * 2048, cs_r = cs_mu + 1024;
@@ -816,14 +824,15 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 if (p.hsic) b = fmaf(hs, pc.sm[rr], b);
                 const float mu_s = pc.side == 0 ? mu1 : mu2, r_s = pc.side == 0 ? r1 : r2;
                 const float mu_o = pc.side == 0 ? mu2 : mu1, r_o = pc.side == 0 ? r2 : r1;
-                const int nchunks = (p.bn + 31) / 32;
+                const int bn_i = half < 0 ? p.bn : p.bn / 2, n_off = tn * p.bn + (half > 0 ? p.bn / 2 : 0);
+                const int nchunks = (bn_i + 31) / 32;
                 for (int ch = hf; ch < nchunks; ch += 2) {
-                    const int n_base = tn * p.bn + ch * 32;
+                    const int n_base = n_off + ch * 32;
                     if (n_base >= p.N) break;                                  // warp-uniform
                     uint32_t r[32];
                     tmem_ld_32x32(t_addr + ch * 32, r);
                     tmem_ld_wait();
-                    const int n_valid = row_ok ? min(32, min(p.bn - ch * 32, p.N - n_base)) : 0;
+                    const int n_valid = row_ok ? min(32, min(bn_i - ch * 32, p.N - n_base)) : 0;
                     if (p.io_dtype == ABT_DTYPE_BF16) grad_chunk<__nv_bfloat16>(r, p, pc, rr, lrow, n_base, n_valid, mu_s, r_s, mu_o, r_o, hs, gd, b);
                     else if (p.io_dtype == ABT_DTYPE_F16) grad_chunk<__half>(r, p, pc, rr, lrow, n_base, n_valid, mu_s, r_s, mu_o, r_o, hs, gd, b);
                     else grad_chunk<float>(r, p, pc, rr, lrow, n_base, n_valid, mu_s, r_s, mu_o, r_o, hs, gd, b);
@@ -948,6 +957,7 @@ static int debug_sync(cudaStream_t st, const char* stage) {
 }
 
 static int g_cta_group = 2;     // 2 = CTA-pair kernel (default), 1 = single-CTA kernel (abt_debug_set key 6)
+static bool g_tail_split = true; // GRAD: split the last partial wave into half-width items (abt_debug_set key 8)
 static int g_dist_xchg = -1;    // multi-GPU exchange schedule: -1 = auto (4 ranks and more), 0 = never, 1 = whenever possible (abt_debug_set key 7)
 
 static int ensure_umma_attr() {
@@ -964,7 +974,8 @@ static int ensure_umma_attr() {
 // p.tiles_m counts (128 * cg)-row tiles
 static int launch_umma(int cg, const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1, const CUtensorMap& c0,
                        const CUtensorMap& c1, const UmmaParams& p, cudaStream_t stream) {
-    const int total = p.tiles_m * p.tiles_n * p.pass_count;
+    const int tiles = p.tiles_m * p.tiles_n * p.pass_count;
+    const int total = tiles + (p.split_from < tiles ? tiles - p.split_from : 0);
     const int slots = num_sms() / cg;
     const int grid = (total < slots ? total : slots) * cg;
     cudaLaunchConfig_t cfg{};
@@ -1083,6 +1094,7 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         p.bn = 256; p.ab_format = a.zh_mode ? 0 : 1;
         p.tiles_m = row_tiles; p.tiles_n = (D + p.bn - 1) / p.bn;
         p.kblocks = (N + BK - 1) / BK;
+        p.split_from = 1 << 30;                                 // set below once the pass count is known
         p.hsic = a.hsic; p.write_c = need != 0;
         p.loss_acc = loss_acc;
         const bool second = a.rows_mode && !a.xchg && (need & 2);       // the transposed block is only needed for dz2
@@ -1101,6 +1113,7 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         c1.row_sq = accs + A_SQ2 * D; c1.row_sum = accs + A_SUM2 * D; c1.col_sq = nullptr; c1.col_sum = nullptr;
         p.pass[0] = c0; p.pass[1] = c1;
         p.pass_count = second ? 2 : 1;
+        p.split_from = p.tiles_m * p.tiles_n * p.pass_count;    // CORR: no split (its tiles are short)
         // C is written by TMA stores of 32-row x 64-column boxes (row-block compact: RC rows)
         CUtensorMap mc1, mc2;
         if (a.xchg) { if (int rc = make_map_16(&mc1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C1, D, RC, 64, 32)) return rc; }      // column-blocked: (D, RC)
@@ -1162,10 +1175,20 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         d2.sq = accs + A_SQ2 * D; d2.sm = accs + A_SUM2 * D;
         d2.z_self = Z2 + R0; d2.ld_self = D; d2.z_other = Z1 + R0; d2.ld_other = D;
         p.pass_count = passes;
+        // tail of the persistent schedule: if the last wave fills at most half of the CTA slots, its tiles are split in two
+        // half-width items (one more half wave instead of one more full wave)
+        const int n_tiles = p.tiles_m * p.tiles_n * passes, slots = num_sms() / cg, rem = n_tiles % slots;
+        const bool split = g_tail_split && bn == 256 && n_tiles > slots && rem > 0 && 2 * rem <= slots;
+        p.split_from = split ? n_tiles - rem : n_tiles;
+        CUtensorMap mZ2h, mZ1h;
+        if (int rc = make_map_16(&mZ2h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zB2, N, D, 64, bn / 2 / cg)) return rc;
+        if (int rc = make_map_16(&mZ1h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zB1, N, D, 64, bn / 2 / cg)) return rc;
         const CUtensorMap *a0, *b0, *a1, *b1;
         if (gneed & 1) { p.pass[0] = d1; a0 = &mCk; b0 = &mZ2; p.pass[1] = d2; a1 = &mCt; b1 = &mZ1; }
         else { p.pass[0] = d2; a0 = &mCt; b0 = &mZ1; p.pass[1] = d2; a1 = &mCt; b1 = &mZ1; }
-        if (int rc = launch_umma(cg, *a0, *b0, *a1, *b1, *a0, *a0, p, stream)) return rc;
+        const CUtensorMap* h0 = (b0 == &mZ2) ? &mZ2h : &mZ1h;
+        const CUtensorMap* h1 = (b1 == &mZ2) ? &mZ2h : &mZ1h;
+        if (int rc = launch_umma(cg, *a0, *b0, *a1, *b1, *h0, *h1, p, stream)) return rc;
     } else if (a.loss_out != nullptr && need == 0) {
         bt_loss_scalar_kernel<<<1, 32, 0, stream>>>(loss_acc, a.alpha, a.lambda, a.hsic, D, a.loss_out);
         count_launch();
@@ -1233,6 +1256,7 @@ extern "C" int abt_debug_timing_read(float* stats_ms, float* corr_ms, float* gra
 extern "C" int abt_debug_set(int key, int value) {
     int* f[6] = {&g_desc.mn_lbo, &g_desc.mn_sbo, &g_desc.mn_kstep, &g_desc.k_lbo, &g_desc.k_sbo, &g_desc.k_kstep};
     if (key == 6) { g_cta_group = value == 1 ? 1 : 2; return 0; }
+    if (key == 8) { g_tail_split = value != 0; return 0; }
     if (key == 7) { g_dist_xchg = value < 0 ? -1 : (value != 0 ? 1 : 0); return 0; }
     if (key < 0 || key >= 6) return set_error(ABT_ERR_ARG, "unknown debug key %d", key);
     *f[key] = value;
