@@ -81,39 +81,81 @@ template <> struct Ld2<float> {
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-constexpr int kColsPerBlock = 64;   // 32 lanes x 2 columns
+constexpr int kColsPerBlock = 64;   // multi-GPU normalise kernel: 32 lanes x 2 columns
 constexpr int kRowGroups = 8;       // 256 threads per block; the grid's second dimension splits the rows
 constexpr int kColThreads = kRowGroups * 32;
-constexpr int kMaxRowSplits = 8;
+constexpr int kMaxRowSplits = 32;
+constexpr int kVecCols = 8;                       // columns per thread: one 16-byte load of 16-bit embeddings
+constexpr int kWideCols = 32 * kVecCols;          // 256 columns per block
+
+// eight consecutive embeddings of type T as floats (16-byte loads)
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[2 * k] = __uint_as_float(w[k] << 16); v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+}
+template <> __device__ __forceinline__ void load8<__half>(const __half* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k])); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <typename T> struct NeedsRound { static constexpr bool value = true; };
+template <> struct NeedsRound<__nv_bfloat16> { static constexpr bool value = false; };     // already bf16: rounding is the identity
 
 // ------------------------------------------------------------------------------------------
-// 1. partial column sums: block (cb, rs) handles 64 columns x rows [rs * chunk, (rs + 1) * chunk)
+// 1. partial column sums: block (cb, rs) handles 256 columns x rows [rs * chunk, (rs + 1) * chunk), 16-byte loads
 //    partials[(rs * 5 + k) * D + col], k = sum da, sum da^2, sum db, sum db^2, sum da db  (da = z1 - z1[0], shifted data)
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kColThreads) bt_colstat_kernel(const T* __restrict__ z1, const T* __restrict__ z2, int N, int D, int chunk,
                                                                  float* __restrict__ partials, __nv_bfloat16* __restrict__ zb1,
-                                                                 __nv_bfloat16* __restrict__ zb2) {
-    __shared__ float red[kRowGroups][5][kColsPerBlock];
+                                                                 __nv_bfloat16* __restrict__ zb2, unsigned int* __restrict__ counters, float eps,
+                                                                 float momentum, float* __restrict__ stats, float* __restrict__ running_mean,
+                                                                 float* __restrict__ running_var, double* __restrict__ loss_acc) {
+    __shared__ float red[kRowGroups][5][kWideCols];
+    __shared__ float on_red[8];
+    __shared__ int is_last;
     const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    const int col = blockIdx.x * kColsPerBlock + lane * 2;
+    const int col = blockIdx.x * kWideCols + lane * kVecCols;
     const int n0 = blockIdx.y * chunk, n1 = min(N, n0 + chunk);
-    float s1[2] = {0, 0}, q1[2] = {0, 0}, s2[2] = {0, 0}, q2[2] = {0, 0}, x12[2] = {0, 0};
+    float s1[8], q1[8], s2[8], q2[8], x12[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { s1[c] = q1[c] = s2[c] = q2[c] = x12[c] = 0.f; }
     if (col < D) {
         // shifted-data sums: subtract row 0 so that |mu| >> sigma does not cancel in fp32
-        const float2 a = Ld2<T>::ld(z1 + col), b = Ld2<T>::ld(z2 + col);
-        const float k1[2] = {bf16_round(a.x), bf16_round(a.y)}, k2[2] = {bf16_round(b.x), bf16_round(b.y)};
-#pragma unroll 4
+        float k1[8], k2[8];
+        load8<T>(z1 + col, k1); load8<T>(z2 + col, k2);
+        if (NeedsRound<T>::value) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { k1[c] = bf16_round(k1[c]); k2[c] = bf16_round(k2[c]); }
+        }
+#pragma unroll 2
         for (int n = n0 + rg; n < n1; n += kRowGroups) {
-            const float2 a2 = Ld2<T>::ld(z1 + (size_t)n * D + col), b2 = Ld2<T>::ld(z2 + (size_t)n * D + col);
-            // the tensor cores consume bf16: statistics are those of the bf16-rounded embeddings
-            const float av[2] = {bf16_round(a2.x), bf16_round(a2.y)}, bv[2] = {bf16_round(b2.x), bf16_round(b2.y)};
-            if (zb1 != nullptr) {
-                Ld2<__nv_bfloat16>::st(zb1 + (size_t)n * D + col, av[0], av[1]);
-                Ld2<__nv_bfloat16>::st(zb2 + (size_t)n * D + col, bv[0], bv[1]);
+            float av[8], bv[8];
+            load8<T>(z1 + (size_t)n * D + col, av); load8<T>(z2 + (size_t)n * D + col, bv);
+            if (NeedsRound<T>::value) {
+                // the tensor cores consume bf16: statistics are those of the bf16-rounded embeddings
+                uint32_t pa[4], pb[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    pa[c] = pack_bf16x2(av[2 * c], av[2 * c + 1]); pb[c] = pack_bf16x2(bv[2 * c], bv[2 * c + 1]);
+                    av[2 * c] = __uint_as_float(pa[c] << 16); av[2 * c + 1] = __uint_as_float(pa[c] & 0xffff0000u);
+                    bv[2 * c] = __uint_as_float(pb[c] << 16); bv[2 * c + 1] = __uint_as_float(pb[c] & 0xffff0000u);
+                }
+                if (zb1 != nullptr) {
+                    *reinterpret_cast<uint4*>(zb1 + (size_t)n * D + col) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+                    *reinterpret_cast<uint4*>(zb2 + (size_t)n * D + col) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+                }
             }
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < 8; ++c) {
                 const float da = av[c] - k1[c], db = bv[c] - k2[c];
                 s1[c] += da; q1[c] = fmaf(da, da, q1[c]);
                 s2[c] += db; q2[c] = fmaf(db, db, q2[c]);
@@ -122,92 +164,110 @@ __global__ void __launch_bounds__(kColThreads) bt_colstat_kernel(const T* __rest
         }
     }
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        red[rg][0][lane * 2 + c] = s1[c]; red[rg][1][lane * 2 + c] = q1[c];
-        red[rg][2][lane * 2 + c] = s2[c]; red[rg][3][lane * 2 + c] = q2[c];
-        red[rg][4][lane * 2 + c] = x12[c];
+    for (int c = 0; c < 8; ++c) {      // [c][lane] order: conflict-free (column lane * 8 + c lives at c * 32 + lane)
+        red[rg][0][c * 32 + lane] = s1[c]; red[rg][1][c * 32 + lane] = q1[c];
+        red[rg][2][c * 32 + lane] = s2[c]; red[rg][3][c * 32 + lane] = q2[c];
+        red[rg][4][c * 32 + lane] = x12[c];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 5 * kColsPerBlock; i += kColThreads) {
-        const int k = i / kColsPerBlock, c = i % kColsPerBlock, gc = blockIdx.x * kColsPerBlock + c;
+    for (int i = threadIdx.x; i < 5 * kWideCols; i += kColThreads) {
+        const int k = i / kWideCols, sidx = i % kWideCols, gc = blockIdx.x * kWideCols + (sidx & 31) * 8 + (sidx >> 5);
         if (gc < D) {
             float t = 0.f;
 #pragma unroll
-            for (int g = 0; g < kRowGroups; ++g) t += red[g][k][c];
+            for (int g = 0; g < kRowGroups; ++g) t += red[g][k][sidx];
             partials[((size_t)blockIdx.y * 5 + k) * D + gc] = t;
         }
+    }
+    if (counters == nullptr) return;      // multi-GPU: the partial sums are packed and exchanged instead
+    // the LAST row chunk of this column block to finish folds the partial sums in a fixed order (deterministic) into the statistics
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(counters + blockIdx.x, 1u) == gridDim.y - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    float on = 0.f;
+    const int c = threadIdx.x, gc = blockIdx.x * kWideCols + c;
+    if (gc < D) {
+        float t[5] = {0, 0, 0, 0, 0};
+        for (int sp = 0; sp < (int)gridDim.y; ++sp)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) t[k] += __ldcg(partials + ((size_t)sp * 5 + k) * D + gc);
+        const float invN = 1.0f / (float)N;
+        const float2 f1 = Ld2<T>::ld(z1 + (gc & ~1)), f2 = Ld2<T>::ld(z2 + (gc & ~1));
+        const float sh1 = bf16_round((gc & 1) ? f1.y : f1.x), sh2 = bf16_round((gc & 1) ? f2.y : f2.x);
+        const float m1 = t[0] * invN, m2 = t[2] * invN;
+        const float var1 = fmaxf(t[1] * invN - m1 * m1, 0.f), var2 = fmaxf(t[3] * invN - m2 * m2, 0.f);
+        const float cov = t[4] * invN - m1 * m2;
+        const float mu1 = sh1 + m1, mu2 = sh2 + m2;
+        const float r1 = rsqrtf(var1 + eps), r2 = rsqrtf(var2 + eps);
+        // one Newton step: rsqrtf is ~2 ulp, BatchNorm uses a correctly rounded 1/sqrt
+        const float r1n = r1 * (1.5f - 0.5f * (var1 + eps) * r1 * r1), r2n = r2 * (1.5f - 0.5f * (var2 + eps) * r2 * r2);
+        const float cd = cov * r1n * r2n;
+        stats[S_MU1 * D + gc] = mu1; stats[S_R1 * D + gc] = r1n;
+        stats[S_MU2 * D + gc] = mu2; stats[S_R2 * D + gc] = r2n;
+        stats[S_CDIAG * D + gc] = cd;
+        stats[S_NMU1 * D + gc] = -(float)N * mu1; stats[S_RHO1 * D + gc] = r1n * invN;
+        stats[S_NMU2 * D + gc] = -(float)N * mu2; stats[S_RHO2 * D + gc] = r2n * invN;
+        on = (cd - 1.0f) * (cd - 1.0f);
+        if (running_mean != nullptr) {
+            // BatchNorm1d training-mode side effect, view 1 then view 2 (utils/loss.py:17)
+            const float unb = (N > 1) ? (float)N / (float)(N - 1) : 1.0f;
+            float rm = running_mean[gc], rv = running_var[gc];
+            rm = (1.f - momentum) * rm + momentum * mu1; rv = (1.f - momentum) * rv + momentum * var1 * unb;
+            rm = (1.f - momentum) * rm + momentum * mu2; rv = (1.f - momentum) * rv + momentum * var2 * unb;
+            running_mean[gc] = rm; running_var[gc] = rv;
+        }
+    }
+    // on-diagonal loss sum_i (C_ii - 1)^2: one double atomic per column block
+    on = warp_sum(on);
+    if (lane == 0) on_red[rg] = on;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tsum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tsum += on_red[w];
+        atomicAdd(loss_acc + 2, (double)tsum);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// 2. statistics from the partial sums (fixed summation order: deterministic), then the standardised fp16 embeddings
+// 2. the standardised fp16 embeddings (operand B of the gradient GEMMs; |zh| <= sqrt(N)): elementwise, 16-byte accesses
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kColThreads) bt_normalize_kernel(const T* __restrict__ z1, const T* __restrict__ z2, int N, int D, int chunk,
-                                                                   int n_splits, float eps, float momentum, const float* __restrict__ partials,
-                                                                   float* __restrict__ stats, __half* __restrict__ zh1, __half* __restrict__ zh2,
-                                                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                                                   double* __restrict__ loss_acc) {
-    __shared__ float colstat[4][kColsPerBlock];   // mu1, r1, mu2, r2 of this block's columns
-    __shared__ float on_red[2];
+                                                                   const float* __restrict__ stats, __half* __restrict__ zh1,
+                                                                   __half* __restrict__ zh2) {
     const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    const int col = blockIdx.x * kColsPerBlock + lane * 2;
-    float on = 0.f;
-    if (threadIdx.x < kColsPerBlock) {
-        const int c = threadIdx.x, gc = blockIdx.x * kColsPerBlock + c;
-        if (gc < D) {
-            float t[5] = {0, 0, 0, 0, 0};
-            for (int s = 0; s < n_splits; ++s)
+    const int col = blockIdx.x * kWideCols + lane * kVecCols;
+    if (col >= D) return;
+    float m1[8], q1r[8], m2[8], q2r[8];
 #pragma unroll
-                for (int k = 0; k < 5; ++k) t[k] += partials[((size_t)s * 5 + k) * D + gc];
-            const float invN = 1.0f / (float)N;
-            const float kk1 = bf16_round(Ld2<T>::ld(z1 + (gc & ~1)).x), kk1b = bf16_round(Ld2<T>::ld(z1 + (gc & ~1)).y);
-            const float kk2 = bf16_round(Ld2<T>::ld(z2 + (gc & ~1)).x), kk2b = bf16_round(Ld2<T>::ld(z2 + (gc & ~1)).y);
-            const float sh1 = (gc & 1) ? kk1b : kk1, sh2 = (gc & 1) ? kk2b : kk2;
-            const float m1 = t[0] * invN, m2 = t[2] * invN;
-            const float var1 = fmaxf(t[1] * invN - m1 * m1, 0.f), var2 = fmaxf(t[3] * invN - m2 * m2, 0.f);
-            const float cov = t[4] * invN - m1 * m2;
-            const float mu1 = sh1 + m1, mu2 = sh2 + m2;
-            const float r1 = rsqrtf(var1 + eps), r2 = rsqrtf(var2 + eps);
-            // one Newton step: rsqrtf is ~2 ulp, BatchNorm uses a correctly rounded 1/sqrt
-            const float r1n = r1 * (1.5f - 0.5f * (var1 + eps) * r1 * r1), r2n = r2 * (1.5f - 0.5f * (var2 + eps) * r2 * r2);
-            const float cd = cov * r1n * r2n;
-            colstat[0][c] = mu1; colstat[1][c] = r1n; colstat[2][c] = mu2; colstat[3][c] = r2n;
-            if (blockIdx.y == 0) {
-                stats[S_MU1 * D + gc] = mu1; stats[S_R1 * D + gc] = r1n;
-                stats[S_MU2 * D + gc] = mu2; stats[S_R2 * D + gc] = r2n;
-                stats[S_CDIAG * D + gc] = cd;
-                stats[S_NMU1 * D + gc] = -(float)N * mu1; stats[S_RHO1 * D + gc] = r1n * invN;
-                stats[S_NMU2 * D + gc] = -(float)N * mu2; stats[S_RHO2 * D + gc] = r2n * invN;
-                on = (cd - 1.0f) * (cd - 1.0f);
-                if (running_mean != nullptr) {
-                    // BatchNorm1d training-mode side effect, view 1 then view 2 (utils/loss.py:17)
-                    const float unb = (N > 1) ? (float)N / (float)(N - 1) : 1.0f;
-                    float rm = running_mean[gc], rv = running_var[gc];
-                    rm = (1.f - momentum) * rm + momentum * mu1; rv = (1.f - momentum) * rv + momentum * var1 * unb;
-                    rm = (1.f - momentum) * rm + momentum * mu2; rv = (1.f - momentum) * rv + momentum * var2 * unb;
-                    running_mean[gc] = rm; running_var[gc] = rv;
-                }
-            }
-        }
-        // on-diagonal loss sum_i (C_ii - 1)^2: one double atomic per column block
-        on = warp_sum(on);
-        if (lane == 0) on_red[threadIdx.x >> 5] = on;
+    for (int c4 = 0; c4 < 2; ++c4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(stats + S_MU1 * D + col) + c4), b = __ldg(reinterpret_cast<const float4*>(stats + S_R1 * D + col) + c4);
+        const float4 e = __ldg(reinterpret_cast<const float4*>(stats + S_MU2 * D + col) + c4), f = __ldg(reinterpret_cast<const float4*>(stats + S_R2 * D + col) + c4);
+        m1[4 * c4] = a.x; m1[4 * c4 + 1] = a.y; m1[4 * c4 + 2] = a.z; m1[4 * c4 + 3] = a.w;
+        q1r[4 * c4] = b.x; q1r[4 * c4 + 1] = b.y; q1r[4 * c4 + 2] = b.z; q1r[4 * c4 + 3] = b.w;
+        m2[4 * c4] = e.x; m2[4 * c4 + 1] = e.y; m2[4 * c4 + 2] = e.z; m2[4 * c4 + 3] = e.w;
+        q2r[4 * c4] = f.x; q2r[4 * c4 + 1] = f.y; q2r[4 * c4 + 2] = f.z; q2r[4 * c4 + 3] = f.w;
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && blockIdx.y == 0) atomicAdd(loss_acc + 2, (double)(on_red[0] + on_red[1]));
-    // standardised embeddings in fp16 (operand B of the gradient GEMMs; |zh| <= sqrt(N))
-    if (col < D && zh1 != nullptr) {
-        const float m1[2] = {colstat[0][lane * 2], colstat[0][lane * 2 + 1]}, q1r[2] = {colstat[1][lane * 2], colstat[1][lane * 2 + 1]};
-        const float m2[2] = {colstat[2][lane * 2], colstat[2][lane * 2 + 1]}, q2r[2] = {colstat[3][lane * 2], colstat[3][lane * 2 + 1]};
-        const int n0 = blockIdx.y * chunk, n1 = min(N, n0 + chunk);
-#pragma unroll 4
-        for (int n = n0 + rg; n < n1; n += kRowGroups) {
-            const size_t o = (size_t)n * D + col;
-            const float2 a2 = Ld2<T>::ld(z1 + o), b2 = Ld2<T>::ld(z2 + o);
-            Ld2<__half>::st(zh1 + o, (bf16_round(a2.x) - m1[0]) * q1r[0], (bf16_round(a2.y) - m1[1]) * q1r[1]);
-            Ld2<__half>::st(zh2 + o, (bf16_round(b2.x) - m2[0]) * q2r[0], (bf16_round(b2.y) - m2[1]) * q2r[1]);
+    const int n0 = blockIdx.y * chunk, n1 = min(N, n0 + chunk);
+#pragma unroll 2
+    for (int n = n0 + rg; n < n1; n += kRowGroups) {
+        const size_t o = (size_t)n * D + col;
+        float av[8], bv[8];
+        load8<T>(z1 + o, av); load8<T>(z2 + o, bv);
+        uint32_t ha[4], hb[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float a0 = av[2 * c], a1 = av[2 * c + 1], b0 = bv[2 * c], b1 = bv[2 * c + 1];
+            if (NeedsRound<T>::value) { a0 = bf16_round(a0); a1 = bf16_round(a1); b0 = bf16_round(b0); b1 = bf16_round(b1); }
+            ha[c] = pack_f16x2((a0 - m1[2 * c]) * q1r[2 * c], (a1 - m1[2 * c + 1]) * q1r[2 * c + 1]);
+            hb[c] = pack_f16x2((b0 - m2[2 * c]) * q2r[2 * c], (b1 - m2[2 * c + 1]) * q2r[2 * c + 1]);
         }
+        *reinterpret_cast<uint4*>(zh1 + o) = make_uint4(ha[0], ha[1], ha[2], ha[3]);
+        *reinterpret_cast<uint4*>(zh2 + o) = make_uint4(hb[0], hb[1], hb[2], hb[3]);
     }
 }
 
@@ -781,21 +841,29 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         }
                         if (pc.col_sq != nullptr) {
                             // column sums over this warp's 32 rows from the staged (fp16) box: lane l owns columns jA + 2l, 2l + 1
-                            float sq0 = 0.f, sq1 = 0.f, sm0 = 0.f, sm1 = 0.f;
+                            float sq0 = 0.f, sq1 = 0.f;
                             const uint32_t woff = (uint32_t)(lane & 3) * 4u, kc = (uint32_t)(lane >> 2);
+                            if (!p.hsic) {
 #pragma unroll
-                            for (int r = 0; r < 32; ++r) {
-                                const uint32_t w = lds32(stg + (uint32_t)r * 128u + ((kc ^ (uint32_t)(r & 7)) << 4) + woff);
-                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
-                                sq0 = fmaf(f.x, f.x, sq0); sq1 = fmaf(f.y, f.y, sq1);
-                                sm0 += f.x; sm1 += f.y;
-                            }
-                            atomicAdd(pc.col_sq + jA + 2 * lane, sq0);
-                            atomicAdd(pc.col_sq + jA + 2 * lane + 1, sq1);
-                            if (p.hsic) {
+                                for (int r = 0; r < 32; ++r) {
+                                    const uint32_t w = lds32(stg + (uint32_t)r * 128u + ((kc ^ (uint32_t)(r & 7)) << 4) + woff);
+                                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                                    sq0 = fmaf(f.x, f.x, sq0); sq1 = fmaf(f.y, f.y, sq1);
+                                }
+                            } else {
+                                float sm0 = 0.f, sm1 = 0.f;
+#pragma unroll
+                                for (int r = 0; r < 32; ++r) {
+                                    const uint32_t w = lds32(stg + (uint32_t)r * 128u + ((kc ^ (uint32_t)(r & 7)) << 4) + woff);
+                                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                                    sq0 = fmaf(f.x, f.x, sq0); sq1 = fmaf(f.y, f.y, sq1);
+                                    sm0 += f.x; sm1 += f.y;
+                                }
                                 atomicAdd(pc.col_sum + jA + 2 * lane, sm0);
                                 atomicAdd(pc.col_sum + jA + 2 * lane + 1, sm1);
                             }
+                            atomicAdd(pc.col_sq + jA + 2 * lane, sq0);
+                            atomicAdd(pc.col_sq + jA + 2 * lane + 1, sq1);
                         }
                     }
                 }
@@ -906,7 +974,7 @@ static TimingState g_timing;
 // Workspace layout.  `rows` = number of C rows this call materialises (D single-GPU, row_count in row-block mode);
 // `two_c` = a second C block for the transposed pass (row-block mode).
 struct WsLayout {
-    size_t misc, acc, stats, partials, keep, pack_local, pack_all, rs1, rs2, zb1, zb2, zh1, zh2, zs1, zh1_blk, c1, c2, total;
+    size_t misc, acc, counters, stats, partials, keep, pack_local, pack_all, rs1, rs2, zb1, zb2, zh1, zh2, zs1, zh1_blk, c1, c2, total;
     size_t zero_bytes;   // misc + acc: cleared at the start of every call
 };
 
@@ -915,6 +983,7 @@ static WsLayout ws_layout(int N, int D, int rows, int dtype, bool two_c, int wor
     size_t off = 0;
     L.misc = off; off += 256;
     L.acc = off; off = align_up(off + sizeof(float) * A_COUNT * (size_t)D, 256);
+    L.counters = off; off = align_up(off + sizeof(unsigned int) * (((size_t)D + kWideCols - 1) / kWideCols), 256);     // statistics: arrival counters per column block
     L.zero_bytes = off;
     L.stats = off; off = align_up(off + sizeof(float) * S_COUNT * (size_t)D, 256);
     L.partials = off; off = align_up(off + sizeof(float) * 5 * kMaxRowSplits * (size_t)D, 256);
@@ -994,6 +1063,17 @@ static int launch_umma(int cg, const CUtensorMap& a0, const CUtensorMap& b0, con
     return 0;
 }
 
+// row chunks of the statistics kernels: about 64 rows per block, but at least two blocks per SM over the whole grid
+static int stat_splits(int N, int D) {
+    const int col_blocks = (D + kWideCols - 1) / kWideCols;
+    int splits = (N + 63) / 64;
+    const int want = (2 * num_sms() + col_blocks - 1) / col_blocks;
+    if (splits < want) splits = want;
+    if (splits > (N + 7) / 8) splits = (N + 7) / 8;
+    if (splits > kMaxRowSplits) splits = kMaxRowSplits;
+    return splits < 1 ? 1 : splits;
+}
+
 // Everything one loss evaluation needs, for both the single-GPU and the row-block entry points.
 struct LossCall {
     const void* z1; const void* z2; int dtype;
@@ -1047,15 +1127,15 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
     // ---- statistics
     if (!front) {
     } else if (!a.zh_mode) {
-        int splits = (N + 127) / 128;
-        if (splits > kMaxRowSplits) splits = kMaxRowSplits;
+        int splits = stat_splits(N, D);
         const int chunk = (N + splits - 1) / splits;
         splits = (N + chunk - 1) / chunk;
-        const dim3 sgrid(col_blocks, splits);
-        bt_colstat_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, chunk, partials, zb1, zb2);
-        bt_normalize_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, chunk, splits, a.eps,
-                                                                  a.momentum, partials, stats, need != 0 ? zh1 : nullptr, need != 0 ? zh2 : nullptr,
-                                                                  a.running_mean, a.running_var, loss_acc);
+        const dim3 sgrid((D + kWideCols - 1) / kWideCols, splits);
+        bt_colstat_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, chunk, partials, zb1, zb2,
+                                                                reinterpret_cast<unsigned int*>(ws + L.counters), a.eps, a.momentum, stats,
+                                                                a.running_mean, a.running_var, loss_acc);
+        if (need != 0)
+            bt_normalize_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, chunk, stats, zh1, zh2);
         count_launch(2);
         if (int rc = debug_sync(stream, "statistics")) return rc;
         if (a.hsic && need != 0) {
@@ -1370,13 +1450,13 @@ extern "C" int abt_bt_dist_layout_query(int n_local, int world, int n_dims, int 
 template <typename T>
 static int dist_stats_local(const void* z1, const void* z2, int N, int D, uint8_t* ws, const WsLayout& L, cudaStream_t stream) {
     float* partials = reinterpret_cast<float*>(ws + L.partials);
-    int splits = (N + 127) / 128;
-    if (splits > kMaxRowSplits) splits = kMaxRowSplits;
+    int splits = stat_splits(N, D);
     const int chunk = (N + splits - 1) / splits;
     splits = (N + chunk - 1) / chunk;
-    const dim3 sgrid((D + kColsPerBlock - 1) / kColsPerBlock, splits);
+    const dim3 sgrid((D + kWideCols - 1) / kWideCols, splits);
     cudaMemsetAsync(ws + L.keep, 0, 256, stream);
-    bt_colstat_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(z1), static_cast<const T*>(z2), N, D, chunk, partials, nullptr, nullptr);
+    bt_colstat_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(z1), static_cast<const T*>(z2), N, D, chunk, partials, nullptr, nullptr,
+                                                            nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr);
     bt_stat_pack_kernel<T><<<(D + 255) / 256, 256, 0, stream>>>(static_cast<const T*>(z1), static_cast<const T*>(z2), D, splits, partials,
                                                                 reinterpret_cast<float*>(ws + L.pack_local));
     count_launch(2);
@@ -1404,7 +1484,7 @@ template <typename T>
 static void dist_normalize(const void* z1, const void* z2, int N, int world, int rank, int D, int row_count, float eps, float momentum, float* rm,
                            float* rv, uint8_t* ws, const WsLayout& L, cudaStream_t stream) {
     int splits = (N + 127) / 128;
-    if (splits > kMaxRowSplits) splits = kMaxRowSplits;
+    if (splits > 8) splits = 8;
     const int chunk = (N + splits - 1) / splits;
     splits = (N + chunk - 1) / chunk;
     const dim3 sgrid((D + kColsPerBlock - 1) / kColsPerBlock, splits);
