@@ -443,7 +443,7 @@ def run_ours(args):
                      "note": "log-mel + views launches; FP32-pipe bound (1024-pt FFT per frame), see DESIGN.md"},
         "loss_value": loss_val,
     }
-    if args.cpu_baseline:
+    if args.cpu_baseline and world == 1:          # the CPU baseline is timed on rank 0 of the single-GPU run only
         line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -109,8 +109,27 @@ template <> __device__ __forceinline__ void load8<float>(const float* p, float (
 template <typename T> struct NeedsRound { static constexpr bool value = true; };
 template <> struct NeedsRound<__nv_bfloat16> { static constexpr bool value = false; };     // already bf16: rounding is the identity
 
+constexpr int kStatVec = 4;                       // statistics kernel: 4 columns per thread (8-byte loads keep it at ~50 registers, 5 blocks / SM)
+constexpr int kStatCols = 32 * kStatVec;          // 128 columns per block
+
+template <typename T> __device__ __forceinline__ void load4(const T* p, float (&v)[4]);
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+    v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void load4<__half>(const __half* p, float (&v)[4]) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <> __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+
 // ------------------------------------------------------------------------------------------
-// 1. partial column sums: block (cb, rs) handles 256 columns x rows [rs * chunk, (rs + 1) * chunk), 16-byte loads
+// 1. partial column sums: block (cb, rs) handles 128 columns x rows [rs * chunk, (rs + 1) * chunk)
 //    partials[(rs * 5 + k) * D + col], k = sum da, sum da^2, sum db, sum db^2, sum da db  (da = z1 - z1[0], shifted data)
 // ------------------------------------------------------------------------------------------
 template <typename T>
@@ -119,43 +138,43 @@ __global__ void __launch_bounds__(kColThreads) bt_colstat_kernel(const T* __rest
                                                                  __nv_bfloat16* __restrict__ zb2, unsigned int* __restrict__ counters, float eps,
                                                                  float momentum, float* __restrict__ stats, float* __restrict__ running_mean,
                                                                  float* __restrict__ running_var, double* __restrict__ loss_acc) {
-    __shared__ float red[kRowGroups][5][kWideCols];
+    __shared__ float red[kRowGroups][5][kStatCols];
     __shared__ float on_red[8];
     __shared__ int is_last;
     const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    const int col = blockIdx.x * kWideCols + lane * kVecCols;
+    const int col = blockIdx.x * kStatCols + lane * kStatVec;
     const int n0 = blockIdx.y * chunk, n1 = min(N, n0 + chunk);
-    float s1[8], q1[8], s2[8], q2[8], x12[8];
+    float s1[4], q1[4], s2[4], q2[4], x12[4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { s1[c] = q1[c] = s2[c] = q2[c] = x12[c] = 0.f; }
+    for (int c = 0; c < 4; ++c) { s1[c] = q1[c] = s2[c] = q2[c] = x12[c] = 0.f; }
     if (col < D) {
         // shifted-data sums: subtract row 0 so that |mu| >> sigma does not cancel in fp32
-        float k1[8], k2[8];
-        load8<T>(z1 + col, k1); load8<T>(z2 + col, k2);
+        float k1[4], k2[4];
+        load4<T>(z1 + col, k1); load4<T>(z2 + col, k2);
         if (NeedsRound<T>::value) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) { k1[c] = bf16_round(k1[c]); k2[c] = bf16_round(k2[c]); }
+            for (int c = 0; c < 4; ++c) { k1[c] = bf16_round(k1[c]); k2[c] = bf16_round(k2[c]); }
         }
-#pragma unroll 2
+#pragma unroll 4
         for (int n = n0 + rg; n < n1; n += kRowGroups) {
-            float av[8], bv[8];
-            load8<T>(z1 + (size_t)n * D + col, av); load8<T>(z2 + (size_t)n * D + col, bv);
+            float av[4], bv[4];
+            load4<T>(z1 + (size_t)n * D + col, av); load4<T>(z2 + (size_t)n * D + col, bv);
             if (NeedsRound<T>::value) {
                 // the tensor cores consume bf16: statistics are those of the bf16-rounded embeddings
-                uint32_t pa[4], pb[4];
+                uint32_t pa[2], pb[2];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     pa[c] = pack_bf16x2(av[2 * c], av[2 * c + 1]); pb[c] = pack_bf16x2(bv[2 * c], bv[2 * c + 1]);
                     av[2 * c] = __uint_as_float(pa[c] << 16); av[2 * c + 1] = __uint_as_float(pa[c] & 0xffff0000u);
                     bv[2 * c] = __uint_as_float(pb[c] << 16); bv[2 * c + 1] = __uint_as_float(pb[c] & 0xffff0000u);
                 }
                 if (zb1 != nullptr) {
-                    *reinterpret_cast<uint4*>(zb1 + (size_t)n * D + col) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
-                    *reinterpret_cast<uint4*>(zb2 + (size_t)n * D + col) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+                    *reinterpret_cast<uint2*>(zb1 + (size_t)n * D + col) = make_uint2(pa[0], pa[1]);
+                    *reinterpret_cast<uint2*>(zb2 + (size_t)n * D + col) = make_uint2(pb[0], pb[1]);
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
                 const float da = av[c] - k1[c], db = bv[c] - k2[c];
                 s1[c] += da; q1[c] = fmaf(da, da, q1[c]);
                 s2[c] += db; q2[c] = fmaf(db, db, q2[c]);
@@ -164,14 +183,14 @@ __global__ void __launch_bounds__(kColThreads) bt_colstat_kernel(const T* __rest
         }
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {      // [c][lane] order: conflict-free (column lane * 8 + c lives at c * 32 + lane)
+    for (int c = 0; c < 4; ++c) {      // [c][lane] order: conflict-free (column lane * 4 + c lives at c * 32 + lane)
         red[rg][0][c * 32 + lane] = s1[c]; red[rg][1][c * 32 + lane] = q1[c];
         red[rg][2][c * 32 + lane] = s2[c]; red[rg][3][c * 32 + lane] = q2[c];
         red[rg][4][c * 32 + lane] = x12[c];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 5 * kWideCols; i += kColThreads) {
-        const int k = i / kWideCols, sidx = i % kWideCols, gc = blockIdx.x * kWideCols + (sidx & 31) * 8 + (sidx >> 5);
+    for (int i = threadIdx.x; i < 5 * kStatCols; i += kColThreads) {
+        const int k = i / kStatCols, sidx = i % kStatCols, gc = blockIdx.x * kStatCols + (sidx & 31) * kStatVec + (sidx >> 5);
         if (gc < D) {
             float t = 0.f;
 #pragma unroll
@@ -188,8 +207,8 @@ __global__ void __launch_bounds__(kColThreads) bt_colstat_kernel(const T* __rest
     if (!is_last) return;
     __threadfence();
     float on = 0.f;
-    const int c = threadIdx.x, gc = blockIdx.x * kWideCols + c;
-    if (gc < D) {
+    const int c = threadIdx.x, gc = blockIdx.x * kStatCols + c;
+    if (c < kStatCols && gc < D) {
         float t[5] = {0, 0, 0, 0, 0};
         for (int sp = 0; sp < (int)gridDim.y; ++sp)
 #pragma unroll
@@ -983,7 +1002,7 @@ static WsLayout ws_layout(int N, int D, int rows, int dtype, bool two_c, int wor
     size_t off = 0;
     L.misc = off; off += 256;
     L.acc = off; off = align_up(off + sizeof(float) * A_COUNT * (size_t)D, 256);
-    L.counters = off; off = align_up(off + sizeof(unsigned int) * (((size_t)D + kWideCols - 1) / kWideCols), 256);     // statistics: arrival counters per column block
+    L.counters = off; off = align_up(off + sizeof(unsigned int) * (((size_t)D + kStatCols - 1) / kStatCols), 256);     // statistics: arrival counters per column block
     L.zero_bytes = off;
     L.stats = off; off = align_up(off + sizeof(float) * S_COUNT * (size_t)D, 256);
     L.partials = off; off = align_up(off + sizeof(float) * 5 * kMaxRowSplits * (size_t)D, 256);
@@ -1065,8 +1084,8 @@ static int launch_umma(int cg, const CUtensorMap& a0, const CUtensorMap& b0, con
 
 // row chunks of the statistics kernels: about 64 rows per block, but at least two blocks per SM over the whole grid
 static int stat_splits(int N, int D) {
-    const int col_blocks = (D + kWideCols - 1) / kWideCols;
-    int splits = (N + 63) / 64;
+    const int col_blocks = (D + kStatCols - 1) / kStatCols;
+    int splits = (N + 127) / 128;
     const int want = (2 * num_sms() + col_blocks - 1) / col_blocks;
     if (splits < want) splits = want;
     if (splits > (N + 7) / 8) splits = (N + 7) / 8;
@@ -1130,12 +1149,17 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         int splits = stat_splits(N, D);
         const int chunk = (N + splits - 1) / splits;
         splits = (N + chunk - 1) / chunk;
-        const dim3 sgrid((D + kWideCols - 1) / kWideCols, splits);
-        bt_colstat_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, chunk, partials, zb1, zb2,
+        const dim3 cgrid((D + kStatCols - 1) / kStatCols, splits);
+        bt_colstat_kernel<T><<<cgrid, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, chunk, partials, zb1, zb2,
                                                                 reinterpret_cast<unsigned int*>(ws + L.counters), a.eps, a.momentum, stats,
                                                                 a.running_mean, a.running_var, loss_acc);
-        if (need != 0)
-            bt_normalize_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, chunk, stats, zh1, zh2);
+        if (need != 0) {
+            int nsplits = (N + 63) / 64;                           // elementwise: 64 rows x 256 columns per block
+            if (nsplits > 64) nsplits = 64;
+            const int nchunk = (N + nsplits - 1) / nsplits;
+            const dim3 ngrid((D + kWideCols - 1) / kWideCols, (N + nchunk - 1) / nchunk);
+            bt_normalize_kernel<T><<<ngrid, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, nchunk, stats, zh1, zh2);
+        }
         count_launch(2);
         if (int rc = debug_sync(stream, "statistics")) return rc;
         if (a.hsic && need != 0) {
@@ -1453,7 +1477,7 @@ static int dist_stats_local(const void* z1, const void* z2, int N, int D, uint8_
     int splits = stat_splits(N, D);
     const int chunk = (N + splits - 1) / splits;
     splits = (N + chunk - 1) / chunk;
-    const dim3 sgrid((D + kWideCols - 1) / kWideCols, splits);
+    const dim3 sgrid((D + kStatCols - 1) / kStatCols, splits);
     cudaMemsetAsync(ws + L.keep, 0, 256, stream);
     bt_colstat_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(z1), static_cast<const T*>(z2), N, D, chunk, partials, nullptr, nullptr,
                                                             nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr);

@@ -120,6 +120,10 @@ class _BTLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("BarlowTwinsLoss: the gradients of this evaluation were already consumed (they are scaled in place by "
+                               "grad_output); call the loss again instead of back-propagating twice through the same graph")
+        ctx.consumed = True
         dz1, dz2 = ctx.saved_tensors
         # the stored gradients are this call's own buffers (never exposed before): scale both in place with one launch
         g1 = dz1 if ctx.has[0] else None
