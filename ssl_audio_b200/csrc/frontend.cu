@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
             }
         }
     }
-    for (int i = tid; i < a.nnz; i += blockDim.x) s_melw[i] = a.mel_w[i];
+    for (int i = tid; i < a.nnz; i += blockDim.x) s_melw[i] = 0.25f * a.mel_w[i];      // x 1/4: see the power spectrum below (exact scaling)
     if (tid < kMels) {
         s_mel_start[tid] = a.mel_start[tid];
         s_mel_start[kMels + tid] = a.mel_len[tid];
@@ -190,11 +190,11 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
                 if (lane == 0) { qr = re[pq0]; qi = im[pq0]; }
                 const float ar = re[p] + qr, ai = im[p] - qi;     // 2 A[k]
                 const float br = im[p] + qi, bi = qr - re[p];     // 2 B[k]
-                sc[32 * k1 + lane] = make_float2(0.25f * (ar * ar + ai * ai), 0.25f * (br * br + bi * bi));
+                sc[32 * k1 + lane] = make_float2(ar * ar + ai * ai, br * br + bi * bi);      // 4 |A|^2, 4 |B|^2: the 1/4 lives in the mel weights
             }
-            if (lane == 0) {   // k = 512 pairs with itself
+            if (lane == 0) {   // k = 512 pairs with itself: Z[512] = A[512] + i B[512] with both real
                 const int p16 = bitrev5(16);
-                sc[512] = make_float2(re[p16] * re[p16], im[p16] * im[p16]);
+                sc[512] = make_float2(4.0f * re[p16] * re[p16], 4.0f * im[p16] * im[p16]);
             }
             __syncwarp();
             // sparse mel projection: this lane owns bands `lane` and `63 - lane` of both frames
@@ -203,16 +203,30 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
                 const int m = hm == 0 ? lane : (kMels - 1 - lane);
                 const int ks = s_mel_start[m], kl = s_mel_start[kMels + m];
                 const float* w = s_melw + s_mel_start[2 * kMels + m];
-                const float2* pp = sc + ks;
                 float ma = 0.f, mb = 0.f;
-#pragma unroll 4
-                for (int t = 0; t < kl; ++t) {
-                    const float wt = w[t];
-                    const float2 pv = pp[t];
-                    ma = fmaf(wt, pv.x, ma);
-                    mb = fmaf(wt, pv.y, mb);
+                // two bins per iteration: 16-byte read of (Pa, Pb) x 2 and 8-byte read of two weights (the host aligns every band's
+                // weight array so that even bins sit at even offsets)
+                int k = ks;
+                const int kend = ks + kl;
+                if ((k & 1) && k < kend) {
+                    const float wt = w[0];
+                    const float2 pv = sc[k];
+                    ma = fmaf(wt, pv.x, ma); mb = fmaf(wt, pv.y, mb);
+                    ++k;
                 }
-                float la = logf(ma + kF32Eps), lb = logf(mb + kF32Eps);
+#pragma unroll 2
+                for (; k + 1 < kend; k += 2) {
+                    const float2 wt = *reinterpret_cast<const float2*>(w + (k - ks));
+                    const float4 pv = *reinterpret_cast<const float4*>(sc + k);
+                    ma = fmaf(wt.x, pv.x, ma); mb = fmaf(wt.x, pv.y, mb);
+                    ma = fmaf(wt.y, pv.z, ma); mb = fmaf(wt.y, pv.w, mb);
+                }
+                if (k < kend) {
+                    const float wt = w[k - ks];
+                    const float2 pv = sc[k];
+                    ma = fmaf(wt, pv.x, ma); mb = fmaf(wt, pv.y, mb);
+                }
+                float la = __logf(ma + kF32Eps), lb = __logf(mb + kF32Eps);      // lg2.approx * ln 2: |err| ~ 1e-6, far inside the 1e-3 log-mel tolerance
                 if (a.apply_norm) { la = (la - a.norm_mean) * a.inv_std; lb = (lb - a.norm_mean) * a.inv_std; }
                 s_out[m * (kTileFrames + 1) + fa] = la;
                 s_out[m * (kTileFrames + 1) + fb] = lb;
@@ -550,6 +564,8 @@ extern "C" int abt_logmel_plan_create(const abt_mel_config* cfg, abt_logmel_plan
         }
         start[m] = first < 0 ? 0 : first;
         len[m] = first < 0 ? 0 : last - first + 1;
+        // the kernel reads two weights at a time: bin k of band m lives at off[m] + (k - start[m]), and that index must have the parity of k
+        if ((((int)weights.size() - start[m]) & 1) != 0) weights.push_back(0.f);
         off[m] = (int)weights.size();
         for (int k = 0; k < len[m]; ++k) weights.push_back(col[start[m] + k]);
         if (len[m] > max_len) max_len = len[m];
