@@ -405,26 +405,34 @@ __global__ void bank_push_kernel(const float* __restrict__ x, long long x_stride
 // crop-first input staging: copy only the samples the cropped frames need, (n_fft + (n_frames-1) hop) per clip,
 // from the waveforms -- which may live in MAPPED PINNED HOST memory (zero-copy reads over PCIe) -- into a compact
 // device buffer.  For 10 s clips and a 96-frame crop this moves 65 KB instead of 640 KB per clip across PCIe.
-// Small footprint on purpose (128 threads, no shared memory): it co-resides with the compute kernels of the
-// previous step.
+// Minimal footprint on purpose -- ONE warp per SM, 32 registers per thread, no shared memory, persistent over the clips: the
+// tensor-core kernel of the objective leaves exactly 1024 registers per SM free, so this kernel stays resident next to it and the
+// PCIe reads (about 1.3 ms per 1024-clip batch) overlap the compute of the previous step instead of serialising with it.  Four
+// independent 16-byte loads per lane keep ~300 KB in flight over PCIe, enough to saturate it.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) wav_span_gather_kernel(const float* __restrict__ wav, long long row_stride, int n_samples,
-                                                              const int* __restrict__ frame_start, int hop, int half_fft, int span_len,
-                                                              float* __restrict__ spans, int* __restrict__ origin) {
-    const int clip = blockIdx.y;
-    const int f0 = frame_start ? max(frame_start[clip], 0) : 0;
-    int o = f0 * hop - half_fft;                 // first padded-coordinate sample of the crop, in clip coordinates
-    o = min(o, n_samples - span_len);
-    o = max(o, 0);
-    o &= ~3;                                     // keep 16-byte alignment of the source (rows are 16-byte aligned)
-    if (blockIdx.x == 0 && threadIdx.x == 0) origin[clip] = o;
-    const int len = min(span_len, n_samples - o);
-    const float* src = wav + (long long)clip * row_stride + o;
-    float* dst = spans + (long long)clip * span_len;
-    const int n4 = len >> 2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
-        reinterpret_cast<float4*>(dst)[i] = __ldcs(reinterpret_cast<const float4*>(src) + i);
-    if (blockIdx.x == 0 && threadIdx.x < (len & 3)) dst[(n4 << 2) + threadIdx.x] = src[(n4 << 2) + threadIdx.x];
+__global__ void __maxnreg__(32) wav_span_gather_kernel(const float* __restrict__ wav, long long row_stride, int n_samples, int n_clips,
+                                                             const int* __restrict__ frame_start, int hop, int half_fft, int span_len,
+                                                             float* __restrict__ spans, int* __restrict__ origin) {
+    const int lane = threadIdx.x;
+    for (int clip = blockIdx.x; clip < n_clips; clip += gridDim.x) {
+        const int f0 = frame_start ? max(frame_start[clip], 0) : 0;
+        int o = f0 * hop - half_fft;                 // first padded-coordinate sample of the crop, in clip coordinates
+        o = min(o, n_samples - span_len);
+        o = max(o, 0);
+        o &= ~3;                                     // keep 16-byte alignment of the source (rows are 16-byte aligned)
+        if (lane == 0) origin[clip] = o;
+        const int len = min(span_len, n_samples - o);
+        const float4* src = reinterpret_cast<const float4*>(wav + (long long)clip * row_stride + o);
+        float4* dst = reinterpret_cast<float4*>(spans + (long long)clip * span_len);
+        const int n4 = len >> 2;
+        int i = lane;
+        for (; i + 96 < n4; i += 128) {
+            const float4 v0 = __ldcs(src + i), v1 = __ldcs(src + i + 32), v2 = __ldcs(src + i + 64), v3 = __ldcs(src + i + 96);
+            dst[i] = v0; dst[i + 32] = v1; dst[i + 64] = v2; dst[i + 96] = v3;
+        }
+        for (; i < n4; i += 32) dst[i] = __ldcs(src + i);
+        if (lane < (len & 3)) reinterpret_cast<float*>(dst)[(n4 << 2) + lane] = reinterpret_cast<const float*>(src)[(n4 << 2) + lane];
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -675,9 +683,11 @@ extern "C" int abt_wav_span_gather(const abt_logmel_plan* plan, const float* wav
         if (e != cudaSuccess) return set_error(ABT_ERR_ARG, "host waveforms must be in mapped pinned memory (cudaHostAlloc / cudaHostRegister): %s", cudaGetErrorString(e));
         src = static_cast<const float*>(dptr);
     }
-    dim3 grid(4, n_clips);
-    wav_span_gather_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, wav_row_stride, n_samples, frame_start, plan->cfg.hop_length,
-                                                                                       kNfft / 2, span_len, spans, span_origin);
+    int n_sm = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    const int grid = n_clips < n_sm ? n_clips : n_sm;
+    wav_span_gather_kernel<<<grid, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, wav_row_stride, n_samples, n_clips, frame_start,
+                                                                                     plan->cfg.hop_length, kNfft / 2, span_len, spans, span_origin);
     count_launch();
     ABT_CUDA_OK(cudaGetLastError());
     return 0;
