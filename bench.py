@@ -440,7 +440,10 @@ def run_ours(args):
                      "peak_source": peaks["source"] + " (bf16_tflops burst figure: the launches are timed alone, in short bursts at boost clocks)"},
         "frontend": {"ms_per_step": fe_ms, "clips_per_s": B / (fe_ms * 1e-3), "algorithmic_bytes_per_step": fe_bytes,
                      "achieved_gbs": fe_bytes / (fe_ms * 1e-3) / 1e9, "hbm_frac": fe_bytes / (fe_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                     "note": "log-mel + views launches; FP32-pipe bound (1024-pt FFT per frame), see DESIGN.md"},
+                     "algorithmic_fp32_tflops": B * 2.84e6 / (fe_ms * 1e-3) / 1e12, "fp32_peak_tflops": 74.4,
+                     "note": "log-mel + views launches of a frontend-only pass; DRAM traffic = algorithmic bytes, but the kernel is bound by shared-memory "
+                             "bandwidth and FP32 issue (1024-point FFT per 160 new samples: 2.84 MFLOP per clip against 187 776 B), see DESIGN.md and "
+                             "profiles/r1_ncu_summary.md; fp32 peak = 148 SMs x 128 FMA/clk x 1.965 GHz"},
         "loss_value": loss_val,
     }
     if args.cpu_baseline and world == 1:          # the CPU baseline is timed on rank 0 of the single-GPU run only

@@ -310,9 +310,11 @@ __global__ void __launch_bounds__(kViewThreads) views_kernel(const abt_views_arg
 
     // ---- phase 1: canvas rows [ci, ci + chh)   (augmentations.py:43-48, :81-85)
     if (((a.canvas_w | x0 | a.in_w) & 3) == 0) {
-        const int g_per_row = a.canvas_w >> 2;
-        for (int g = tid; g < chh * g_per_row; g += kViewThreads) {
-            const int r = ci + g / g_per_row, col = (g % g_per_row) << 2;
+        // only the crop box is ever read by the taps: rows [ci, ci + chh), float4 groups covering columns [cj, cj + cww);
+        // a thread keeps its column group and strides over the rows (one integer division per thread, none per element)
+        const int c_lo = cj & ~3, n_groups = ((cj + cww + 3) >> 2) - (cj >> 2);
+        const int rows_per_pass = kViewThreads / n_groups, gsub = tid / n_groups, col = c_lo + ((tid % n_groups) << 2);
+        for (int r = ci + gsub; gsub < rows_per_pass && r < ci + chh; r += rows_per_pass) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r >= y0 && r < y0 + a.in_h && col >= x0 && col < x0 + a.in_w) {
                 const int e = (r - y0) * a.in_w + (col - x0);
