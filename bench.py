@@ -196,7 +196,7 @@ def run_reference(args):
 def _config(args):
     return {"workload": f"hot-path step: frontend (BASELINE config 2: {args.batch} clips x {args.clip_seconds:g} s @16 kHz -> crop-first 64-mel log-mel -> "
                         f"two 96-frame views) + Barlow Twins loss fwd/bwd (N={args.batch} rows/GPU, D={args.dim}, bf16 in / fp32 accumulate)",
-            "per_gpu_batch": args.batch, "clip_seconds": args.clip_seconds, "projector_out_dim": args.dim, "frontend_mode": "crop-first (mode C)", "streams": "frontend and loss of a step are issued on two CUDA streams (independent inputs); at >= 4 GPUs the frontend is enqueued while the embedding all-gather is in flight",
+            "per_gpu_batch": args.batch, "clip_seconds": args.clip_seconds, "projector_out_dim": args.dim, "frontend_mode": "crop-first (mode C)", "streams": "frontend and loss of a step are issued on two CUDA streams (independent inputs); on several GPUs the frontend is enqueued while the embedding all-gather is in flight",
             "l2": "inputs larger than L2 (655 MB of waveforms, 128 MiB correlation matrix per step)", "parallelism": f"dp{args.gpus}"}
 
 
@@ -261,13 +261,14 @@ def run_ours(args):
         with torch.cuda.stream(side_stream):
             cur["views"] = fe(cur["wav"])
 
-    # Default: one host thread; at >= 4 ranks the frontend is enqueued from the objective's comm-overlap hook (right after the embedding
+    # Default: one host thread; on several GPUs the frontend is enqueued from the objective's comm-overlap hook (right after the embedding
     # all-gathers have been launched).  BENCH_THREAD=1 moves the frontend's host side to a worker thread instead (measured: no gain, the
     # step is device-bound); BENCH_HOOK=0/1 overrides the hook placement.
     use_thread = os.environ.get("BENCH_THREAD", "0") == "1"
-    # measured on this pool: at 2 ranks NCCL's all-gather kernels and the frontend kernels delay each other when the frontend is enqueued
-    # right behind the gathers; at 4 and 8 ranks that placement hides the frontend completely
-    use_hook = (world >= 4 if os.environ.get("BENCH_HOOK") is None else os.environ["BENCH_HOOK"] == "1") and not use_thread
+    # multi-GPU: the frontend is enqueued from the objective's comm-overlap hook, i.e. right after the embedding all-gathers have been
+    # launched.  Enqueueing it at step start instead lets its kernels race NCCL's for the SMs: measured bimodal at 2 ranks (0.93 or
+    # 1.61 ms per step from run to run) against a steady 0.91 ms with the hook.
+    use_hook = (world > 1 if os.environ.get("BENCH_HOOK") is None else os.environ["BENCH_HOOK"] == "1") and not use_thread
     pool = None
     if use_hook:
         crit.comm_overlap_hook = frontend_on_side_stream
