@@ -152,6 +152,31 @@ class BatchFrontend(nn.Module):
         self.last_plan = plan
         return tf.views_from_plan(ring, plan.slots_ptr, int(ring.shape[1]), plan)
 
+    # -- two-step form of the crop-first device path: host work first, launches later ------------------------------
+    def prepare(self, wav: torch.Tensor):
+        """Host half of `forward` for device waveforms (path "lms", mode "crop"): draws the batch's random parameters in the
+        reference's order and uploads them (one async copy on the current stream).  `launch(handle)` then only enqueues the two
+        kernels, so a trainer can plan early and launch exactly where it wants the kernels to overlap something else."""
+        if not wav.is_cuda or wav.dtype != torch.float32 or wav.dim() != 2:
+            raise ValueError("wav must be a CUDA float32 tensor (B, L)")
+        if self.path != "lms" or self.mode != "crop":
+            raise ValueError("prepare/launch cover the crop-first lms path only")
+        wav = wav.contiguous()
+        B, L = int(wav.shape[0]), int(wav.shape[1])
+        eng = self.transform.engine(B)
+        ring = eng.ensure_ring(wav.device)
+        T_full = self.logmel_raw.n_frames(L)
+        crop_range = T_full - self.crop_frames if T_full > self.crop_frames else 0
+        plan = eng.planner.plan(B, time_crop_range=crop_range, device=wav.device)
+        return (wav, L, ring, plan)
+
+    def launch(self, handle) -> List[torch.Tensor]:
+        wav, L, ring, plan = handle
+        stride = int(ring.shape[1])
+        self.logmel_norm.crop_into(wav, L, 0, plan.starts_ptr, self.crop_frames, ring, plan.slots_ptr, stride)
+        self.last_plan = plan
+        return self.transform.views_from_plan(ring, plan.slots_ptr, stride, plan)
+
     # -- waveform input ---------------------------------------------------------------------------
     def forward(self, wav: torch.Tensor) -> List[torch.Tensor]:
         """wav (B, L) fp32, CUDA or PINNED host memory -> list of views [(B,1,F,T), (B,1,F,T), local crops...]."""
@@ -170,9 +195,7 @@ class BatchFrontend(nn.Module):
             if self.mode == "full":
                 self.last_lms = self.logmel_raw(wav)
                 return self.forward_lms(self.last_lms)
-            crop_range = T_full - self.crop_frames if T_full > self.crop_frames else 0
-            plan = eng.planner.plan(B, time_crop_range=crop_range, device=wav.device)
-            self.logmel_norm.crop_into(wav, L, 0, plan.starts_ptr, self.crop_frames, ring, plan.slots_ptr, stride)
+            return self.launch(self.prepare(wav))
         else:
             # datasets.py:103-113: centre pad to unit_length, then random.randint unit crop
             if L < self.unit_length:
