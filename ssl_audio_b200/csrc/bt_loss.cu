@@ -496,7 +496,6 @@ struct PassCfg {
     // ---- CORR epilogue: c = (S + row_nmu[i] * col_mu[j]) * row_rho[i] * col_r[j]
     const float* row_nmu; const float* row_rho; const float* col_mu; const float* col_r;
     int accumulate_loss;
-    __half* c_out;            // row-major (rows local to row0) x D, fp16, diagonal zeroed
     float* row_sq;            // += sum_j c_ij^2 (j != i), indexed by the global row; may be null
     float* row_sum;           // HSIC only: += sum_j c_ij
     float* col_sq;            // += sum_i c_ij^2 (i != j), indexed by the global column; null when a second pass provides it
@@ -1206,14 +1205,14 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         c0.a_mn = 1; c0.row0 = R0; c0.row_end = R0 + RC; c0.a_col0 = a.xchg ? 0 : R0; c0.blocked_dr = a.xchg ? RC : 0;
         c0.row_nmu = stats + S_NMU1 * D; c0.row_rho = stats + S_RHO1 * D; c0.col_mu = stats + S_MU2 * D; c0.col_r = stats + S_R2 * D;
         if (a.zh_mode) { c0.row_nmu = stats + S_ZERO * D; c0.row_rho = stats + S_INVN * D; c0.col_mu = stats + S_ZERO * D; c0.col_r = stats + S_ONE * D; }
-        c0.accumulate_loss = 1; c0.c_out = C1;
+        c0.accumulate_loss = 1;                       // C1 / C2 are written through the TMA store maps (mc1 / mc2)
         c0.row_sq = (need & 1) ? accs + A_SQ1 * D : nullptr; c0.row_sum = accs + A_SUM1 * D;
         // (exchange mode: the column sums come from bt_colsq_kernel on the received block)
         c0.col_sq = (!a.rows_mode && (need & 2)) ? accs + A_SQ2 * D : nullptr; c0.col_sum = accs + A_SUM2 * D;
         c1 = c0;
         c1.row_nmu = stats + S_NMU2 * D; c1.row_rho = stats + S_RHO2 * D; c1.col_mu = stats + S_MU1 * D; c1.col_r = stats + S_R1 * D;
         if (a.zh_mode) { c1.row_nmu = c0.row_nmu; c1.row_rho = c0.row_rho; c1.col_mu = c0.col_mu; c1.col_r = c0.col_r; }
-        c1.accumulate_loss = 0; c1.c_out = C2;
+        c1.accumulate_loss = 0;
         c1.row_sq = accs + A_SQ2 * D; c1.row_sum = accs + A_SUM2 * D; c1.col_sq = nullptr; c1.col_sum = nullptr;
         p.pass[0] = c0; p.pass[1] = c1;
         p.pass_count = second ? 2 : 1;
