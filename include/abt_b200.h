@@ -102,8 +102,8 @@ int abt_lms_crop_norm(const float* lms, int n_clips, int n_mels, int t_full, con
                       abt_stream_t stream);
 
 /* ===================================================================================== *
- *  Views: Mixup -> RandomResizeCrop -> RandomLinearFader, one launch for all clips and views
- *  replaces MixupBYOLA.forward (augmentations.py:103-117), log_mixup_exp (:81-85),
+ *  Views: Mixup -> [MixGaussianNoise] -> RandomResizeCrop -> RandomLinearFader, one launch for all clips and views
+ *  replaces MixupBYOLA.forward (augmentations.py:103-117), log_mixup_exp (:81-85), MixGaussianNoise.forward (:133-140),
  *  RandomResizeCrop.forward (:40-55) and RandomLinearFader.forward (:69-74) as sequenced by
  *  AudioPairTransform.forward (utils/transforms.py:49-58).
  * ===================================================================================== */
@@ -113,9 +113,12 @@ typedef struct {
     float w_x, w_z;           /* fp32 weights of exp(x), exp(z): float32(1-alpha), float32(1-(1-alpha)) */
     int32_t i, j, h, w;       /* crop box on the virtual canvas (RandomResizeCrop.get_params) */
     float head, tail;         /* fader end points */
-    int32_t flags;            /* bit0: mixup on, bit1: resize-crop on, bit2: fader on */
+    int32_t flags;            /* bit0: mixup on, bit1: resize-crop on, bit2: fader on, bit3: Gaussian-noise mix on */
     int32_t out_index;        /* which output tensor of `outs` this view is written to */
-} abt_view_params;            /* 48 bytes */
+    float g_lambda;           /* MixGaussianNoise: lambd = ratio * np.random.rand() (augmentations.py:136), as float32 */
+    float g_keep;             /* float32(1 - lambd) */
+    int32_t reserved[2];
+} abt_view_params;            /* 64 bytes */
 
 typedef struct {
     int32_t n_clips, n_views; /* params has n_clips * n_views entries, clip-major */
@@ -131,6 +134,10 @@ typedef struct {
     int64_t bank_slot_stride;
     const abt_view_params* params; /* device */
     float* outs[8];           /* output tensor of view k of this launch: (n_clips, 1, out_h, out_w) contiguous */
+    const float* noise;       /* MixGaussianNoise: STANDARD normal draws, (n_clips, noise_views, in_h, in_w) fp32, view v of this launch reads
+                                 plane view_offset + v; the kernel scales them by g_lambda (torch.normal(0, lambd, shape), augmentations.py:137).
+                                 Required when a view has flag bit3, else may be NULL */
+    int32_t noise_views;
 } abt_views_args;
 
 int abt_views_fwd(const abt_views_args* args, abt_stream_t stream);
@@ -145,10 +152,18 @@ int abt_bank_push(const float* x, int64_t x_stride, int n_clips, int clip_elems,
 int abt_normalize_batch_workspace_bytes(int n_channels, size_t* bytes);
 int abt_normalize_batch(const float* x, int n_batch, int n_channels, int hw, float* out, void* workspace, abt_stream_t stream);
 
+/* RunningNorm (augmentations.py:187-210; --pre_norm, main.py:272-277): x (n_batch, elems) fp32, the samples are processed IN ORDER with
+ * the reference's running statistics (mu += (mean(x_b) - mu) / n with n the count before the update, likewise for mean((x_b - mu)^2));
+ * updates stop after max_update samples.  state3: device, 3 doubles (count, mu, s2), zero-initialised by the caller and carried from
+ * call to call.  out = (x_b - mu) / clamp(sqrt(s2), eps).  workspace: abt_running_norm_workspace_bytes(n_batch) bytes. */
+int abt_running_norm_workspace_bytes(int n_batch, size_t* bytes);
+int abt_running_norm(const float* x, int n_batch, int elems, long long max_update, double* state3, float* out, void* workspace,
+                     abt_stream_t stream);
+
 /* ===================================================================================== *
  *  Host planner [host]: replays the reference's RNG draw order (numpy legacy MT19937 global
  *  state + CPython `random` MT19937) for a whole batch and emits the parameter table.
- *  Bit-exact against np.random.* / random.randint as called at augmentations.py:34-37,70,105,108
+ *  Bit-exact against np.random.* / random.randint as called at augmentations.py:34-37,70,105,108,136
  *  and datasets.py:89,112,344.
  * ===================================================================================== */
 typedef struct abt_planner abt_planner;
@@ -166,6 +181,8 @@ typedef struct {
     int32_t local_h, local_w;     /* local_crops_size */
     double local_scale[2];        /* (0.05, 0.6) */
     double fader_gain;            /* 1.0 */
+    int32_t gnoise;               /* args.Gnoise: MixGaussianNoise between Mixup and RandomResizeCrop (utils/transforms.py:20-21) */
+    double gnoise_ratio_d;        /* 0.2 */
 } abt_plan_config;
 
 int abt_planner_create(const abt_plan_config* cfg, abt_planner** p);

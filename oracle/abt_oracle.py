@@ -186,6 +186,17 @@ def mixup_byola(x: np.ndarray, st: MixupState) -> Tuple[np.ndarray, dict]:
     return mixed.astype(np.float32), {"alpha": alpha, "bank_index": idx, "bank_len_before": len(st.bank) - 1 if idx < 0 else None}
 
 
+def mix_gaussian_noise(lms: np.ndarray, ratio: float, n: np.ndarray) -> Tuple[np.ndarray, float]:
+    """MixGaussianNoise.forward (augmentations.py:133-140): lambd = ratio * np.random.rand(); z = exp(normal(0, lambd));
+    log((1 - lambd) * exp(lms) + z + eps).  `n` are the STANDARD normal draws behind torch.normal(0, lambd, shape) -- ATen fills
+    N(0, 1) and then scales by float32(lambd) -- so passing the reference's own draws reproduces it; fp32 arithmetic throughout."""
+    lambd = ratio * np.random.rand()
+    x = np.exp(np.asarray(lms, dtype=np.float32))
+    z = np.exp((np.asarray(n, dtype=np.float32) * np.float32(lambd)).astype(np.float32))
+    mixed = np.float32(1 - lambd) * x + z + F32_EPS
+    return np.log(mixed).astype(np.float32), lambd
+
+
 def rrc_get_params(canvas_hw, in_hw, time_scale, freq_scale) -> Tuple[int, int, int, int]:
     """RandomResizeCrop.get_params: augmentations.py:30-38 (numpy uniform x2, then CPython
     random.randint only when the canvas is larger than the crop)."""
@@ -287,20 +298,24 @@ class PairTransformConfig:
     local_crops_number: int = 0
     local_crops_size: Tuple[int, int] = (16, 16)
     mixup_ratio: float = 0.2
+    gauss_noise_ratio: float = 0.2
     global_crop_scale: Tuple[float, float] = (0.6, 1.5)
     local_crop_scale: Tuple[float, float] = (0.05, 0.6)
 
 
-def global_view(x: np.ndarray, cfg: PairTransformConfig, st: MixupState) -> Tuple[np.ndarray, dict]:
-    """One pass of AudioPairTransform.global_transform: utils/transforms.py:16-34
-    (Mixup -> RRC -> RLF; Gnoise unsupported in the oracle, it needs torch's CPU generator)."""
+def global_view(x: np.ndarray, cfg: PairTransformConfig, st: MixupState, noise: Optional[np.ndarray] = None) -> Tuple[np.ndarray, dict]:
+    """One pass of AudioPairTransform.global_transform: utils/transforms.py:16-34 (Mixup -> Gnoise -> RRC -> RLF).
+    `noise`: the N(0, 1) draws of MixGaussianNoise for this view (required with cfg.Gnoise)."""
     rec = {}
     y = x
     if cfg.mixup:
         y, p = mixup_byola(y, st)
         rec.update(alpha=p["alpha"], bank_index=p["bank_index"])
     if cfg.Gnoise:
-        raise NotImplementedError("MixGaussianNoise draws from torch's CPU generator (augmentations.py:137)")
+        if noise is None:
+            raise ValueError("cfg.Gnoise needs the standard-normal draws of torch.normal (augmentations.py:137)")
+        y, lambd = mix_gaussian_noise(y, cfg.gauss_noise_ratio, noise)
+        rec.update(lambd=lambd)
     if cfg.RRC:
         y, (i, j, h, w) = random_resize_crop(y, (cfg.n_mels, cfg.crop_frames), tuple(cfg.virtual_crop_scale),
                                              cfg.global_crop_scale, cfg.global_crop_scale)
@@ -318,11 +333,12 @@ def local_view(x: np.ndarray, cfg: PairTransformConfig) -> Tuple[np.ndarray, dic
     return y, dict(i=i, j=j, h=h, w=w)
 
 
-def audio_pair_transform(x: np.ndarray, cfg: PairTransformConfig, st: MixupState) -> Tuple[List[np.ndarray], List[dict]]:
-    """AudioPairTransform.forward (multi_transform=True): utils/transforms.py:49-58."""
+def audio_pair_transform(x: np.ndarray, cfg: PairTransformConfig, st: MixupState,
+                         noise: Optional[np.ndarray] = None) -> Tuple[List[np.ndarray], List[dict]]:
+    """AudioPairTransform.forward (multi_transform=True): utils/transforms.py:49-58.  noise: (2, 1, F, T) with cfg.Gnoise."""
     outs, recs = [], []
-    for _ in range(2):
-        y, r = global_view(x, cfg, st)
+    for k in range(2):
+        y, r = global_view(x, cfg, st, None if noise is None else noise[k])
         outs.append(y)
         recs.append(r)
     for _ in range(cfg.local_crops_number):
@@ -363,6 +379,35 @@ def normalize_batch(x: np.ndarray) -> np.ndarray:
     std = x.astype(np.float64).std(axis=(0, 2, 3), ddof=1, keepdims=True)
     std = np.clip(std, F32_EPS, np.finfo(np.float32).max)
     return ((x - mean) / std).astype(np.float32)
+
+
+class RunningNormState:
+    """RunningNorm (augmentations.py:187-210) with its default axis [1, 2] on (1, F, T) samples: scalar running mean of the sample
+    means and of mean((x - mu)^2), both with the reference's RunningMean update `mu += (m - mu) / n` where n is the number of samples
+    seen BEFORE this one (augmentations.py:150-156) -- not the textbook 1/(n+1)."""
+
+    def __init__(self, epoch_samples: int, max_update_epochs: int = 10):
+        self.max_update = epoch_samples * max_update_epochs
+        self.n = 0
+        self.mu = 0.0
+        self.s2 = 0.0
+
+    def put(self, x: np.ndarray) -> np.ndarray:
+        x = np.asarray(x, dtype=np.float32)
+        if self.n < self.max_update:
+            m = float(x.astype(np.float64).mean())
+            self.mu = m if self.n == 0 else self.mu + (m - self.mu) / self.n
+            v = float(((x.astype(np.float64) - self.mu) ** 2).mean())
+            self.s2 = v if self.n == 0 else self.s2 + (v - self.s2) / self.n
+            self.n += 1
+        std = min(max(np.float32(np.sqrt(self.s2)), F32_EPS), np.finfo(np.float32).max)
+        return ((x - np.float32(self.mu)) / np.float32(std)).astype(np.float32)
+
+
+def running_norm(samples: np.ndarray, epoch_samples: int, max_update_epochs: int = 10) -> np.ndarray:
+    """A (B, 1, F, T) batch pushed through RunningNormState in sample order."""
+    st = RunningNormState(epoch_samples, max_update_epochs)
+    return np.stack([st.put(x) for x in samples])
 
 
 # --------------------------------------------------------------------------------------

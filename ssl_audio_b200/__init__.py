@@ -7,12 +7,12 @@ Host-side mirror of the reference's interfaces for the path named in BASELINE.js
 All compute runs in hand-written CUDA behind the C ABI of include/abt_b200.h; importing this package
 never falls back to PyTorch/CPU implementations.
 """
-from .augmentations import MixGaussianNoise, MixupBYOLA, NormalizeBatch, RandomLinearFader, RandomResizeCrop, log_mixup_exp
+from .augmentations import MixGaussianNoise, MixupBYOLA, NormalizeBatch, RandomLinearFader, RandomResizeCrop, RunningNorm, log_mixup_exp
 from .frontend import BatchFrontend, LogMelSpectrogram
 from .loss import BarlowTwinsLoss, bt_loss_fwd_bwd, off_diagonal
 from .transforms import AudioPairTransform
 
 __all__ = [
-    "AudioPairTransform", "RandomResizeCrop", "RandomLinearFader", "MixupBYOLA", "MixGaussianNoise", "NormalizeBatch", "log_mixup_exp",
+    "AudioPairTransform", "RandomResizeCrop", "RandomLinearFader", "MixupBYOLA", "MixGaussianNoise", "NormalizeBatch", "RunningNorm", "log_mixup_exp",
     "LogMelSpectrogram", "BatchFrontend", "BarlowTwinsLoss", "bt_loss_fwd_bwd", "off_diagonal",
 ]

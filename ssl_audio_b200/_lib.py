@@ -30,6 +30,7 @@ class ViewParams(C.Structure):
         ("z_kind", C.c_int32), ("z_index", C.c_int32), ("w_x", C.c_float), ("w_z", C.c_float),
         ("i", C.c_int32), ("j", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
         ("head", C.c_float), ("tail", C.c_float), ("flags", C.c_int32), ("out_index", C.c_int32),
+        ("g_lambda", C.c_float), ("g_keep", C.c_float), ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -40,7 +41,7 @@ class ViewsArgs(C.Structure):
         ("param_stride", C.c_int32), ("view_offset", C.c_int32),
         ("x", C.c_void_p), ("x_slot", C.c_void_p), ("x_slot_stride", C.c_int64),
         ("bank", C.c_void_p), ("bank_slot_stride", C.c_int64), ("params", C.c_void_p),
-        ("outs", C.c_void_p * 8),
+        ("outs", C.c_void_p * 8), ("noise", C.c_void_p), ("noise_views", C.c_int32),
     ]
 
 
@@ -52,6 +53,7 @@ class PlanConfig(C.Structure):
         ("freq_scale", C.c_double * 2), ("time_scale", C.c_double * 2),
         ("n_local", C.c_int32), ("local_h", C.c_int32), ("local_w", C.c_int32),
         ("local_scale", C.c_double * 2), ("fader_gain", C.c_double),
+        ("gnoise", C.c_int32), ("gnoise_ratio_d", C.c_double),
     ]
 
 
@@ -123,6 +125,8 @@ SIGNATURES = {
     "abt_bank_push": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "abt_normalize_batch_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
     "abt_normalize_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "abt_running_norm_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
+    "abt_running_norm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "abt_planner_create": (C.c_int, [C.POINTER(PlanConfig), C.POINTER(C.c_void_p)]),
     "abt_planner_destroy": (C.c_int, [C.c_void_p]),
     "abt_planner_set_numpy_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),

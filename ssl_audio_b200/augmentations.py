@@ -19,7 +19,7 @@ import torch.nn as nn
 from . import _lib
 from .planner import VIEW_DTYPE, BatchPlan, ViewPlanner
 
-__all__ = ["RandomResizeCrop", "RandomLinearFader", "MixupBYOLA", "log_mixup_exp", "MixGaussianNoise", "NormalizeBatch", "ViewEngine"]
+__all__ = ["RandomResizeCrop", "RandomLinearFader", "MixupBYOLA", "log_mixup_exp", "MixGaussianNoise", "NormalizeBatch", "RunningNorm", "ViewEngine"]
 
 
 def _as_batch(x: torch.Tensor) -> Tuple[torch.Tensor, bool]:
@@ -63,7 +63,8 @@ class ViewEngine:
 
 
 def _launch_views(lib, x_ptr: int, x_slot_ptr: int, x_slot_stride: int, ring: Optional[torch.Tensor], params_ptr: int, param_stride: int,
-                  view_offset: int, n_clips: int, n_views: int, in_hw, canvas_hw, out_hw, outs: List[torch.Tensor], device) -> None:
+                  view_offset: int, n_clips: int, n_views: int, in_hw, canvas_hw, out_hw, outs: List[torch.Tensor], device,
+                  noise: Optional[torch.Tensor] = None) -> None:
     a = _lib.ViewsArgs()
     a.n_clips, a.n_views = int(n_clips), int(n_views)
     a.in_h, a.in_w = int(in_hw[0]), int(in_hw[1])
@@ -78,22 +79,37 @@ def _launch_views(lib, x_ptr: int, x_slot_ptr: int, x_slot_stride: int, ring: Op
     a.params = params_ptr
     for k, o in enumerate(outs):
         a.outs[k] = o.data_ptr()
+    if noise is not None:
+        a.noise, a.noise_views = noise.data_ptr(), int(noise.shape[1])
     _lib.check(lib.abt_views_fwd(C.byref(a), torch.cuda.current_stream(device).cuda_stream))
 
 
 def run_views(engine: ViewEngine, x: torch.Tensor, x_slot_ptr: int, x_slot_stride: int, plan: BatchPlan,
-              n_global: int, n_local: int, global_out_hw, local_out_hw) -> List[torch.Tensor]:
-    """Run all views of a planned (and uploaded) batch: one launch for the global views, one for the local crops."""
+              n_global: int, n_local: int, global_out_hw, local_out_hw, noise: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+    """Run all views of a planned (and uploaded) batch: one launch for the global views, one for the local crops.
+    `noise` (MixGaussianNoise only): standard-normal draws (n_clips, n_global, F, T); drawn on the device when not given."""
     lib = engine._lib
     dev = x.device
     n_clips = plan.params.shape[0]
     n_views = n_global + n_local
+    if engine.planner.gnoise and n_global:
+        shape = (n_clips, n_global, engine.in_hw[0], engine.in_hw[1])
+        if noise is None:
+            # the reference draws torch.normal(0, lambd, shape) from torch's CPU generator (augmentations.py:137); here the N(0, 1)
+            # draws come from torch's CUDA generator (seeded by torch.manual_seed) and the kernel scales them by lambd
+            noise = torch.randn(shape, dtype=torch.float32, device=dev)
+        else:
+            _check_cuda_f32(noise, "noise")
+            if tuple(noise.shape) != shape or not noise.is_contiguous():
+                raise ValueError(f"noise must be contiguous with shape {shape}, got {tuple(noise.shape)}")
+    else:
+        noise = None
     outs: List[torch.Tensor] = []
     if n_global:
         g_outs = [torch.empty((n_clips, 1, global_out_hw[0], global_out_hw[1]), dtype=torch.float32, device=dev) for _ in range(n_global)]
         if n_clips:
             _launch_views(lib, x.data_ptr(), x_slot_ptr, x_slot_stride, engine.ring, plan.params_ptr, n_views, 0, n_clips, n_global,
-                          engine.in_hw, engine.canvas_hw, global_out_hw, g_outs, dev)
+                          engine.in_hw, engine.canvas_hw, global_out_hw, g_outs, dev, noise)
         outs += g_outs
     if n_local:
         l_outs = [torch.empty((n_clips, 1, local_out_hw[0], local_out_hw[1]), dtype=torch.float32, device=dev) for _ in range(n_local)]
@@ -260,16 +276,35 @@ class MixupBYOLA(_SingleStage):
         return self.__class__.__name__ + f"(ratio={self.ratio},n={self.n},log_mixup_exp={self.log_mixup_exp})"
 
 
-class MixGaussianNoise(nn.Module):
-    """reference: augmentations.py:125-140.  Not on the GPU path yet: it draws
-    its noise from torch's CPU generator, which the kernel cannot replay."""
+class MixGaussianNoise(_SingleStage):
+    """Gaussian Noise Mixer (reference: augmentations.py:125-140): `log((1 - lambd) * exp(lms) + exp(n * lambd) + eps)` with
+    `lambd = ratio * np.random.rand()` replayed from numpy's global generator and n ~ N(0, 1).
+
+    The reference takes n from torch's CPU generator (`torch.normal(0, lambd, shape)`); a GPU kernel cannot replay that stream, so
+    `forward(lms, noise=None)` takes the standard-normal draws as an optional tensor of lms's shape -- pass the reference's draws
+    (`torch.randn(shape)` after the same `torch.manual_seed`) to reproduce it exactly, or leave it out to draw from torch's CUDA
+    generator: same distribution, different stream."""
 
     def __init__(self, ratio=0.2):
         super().__init__()
         self.ratio = ratio
+        self._engine = None
 
-    def forward(self, lms):
-        raise NotImplementedError("MixGaussianNoise is outside the accelerated hot path (args.Gnoise must be False)")
+    def forward(self, lms: torch.Tensor, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _check_cuda_f32(lms, "lms")
+        x4, single = _as_batch(lms.contiguous())
+        F, T = int(x4.shape[2]), int(x4.shape[3])
+        if self._engine is None or self._engine.in_hw != (F, T):
+            pl = ViewPlanner(mixup=False, rrc=False, rlf=False, n_global=1, in_hw=(F, T), canvas_hw=(F, T), gnoise=True, gnoise_ratio=self.ratio)
+            self._engine = ViewEngine(pl, (F, T), (F, T))
+        if noise is not None:
+            noise = noise.contiguous().reshape(x4.shape)
+        plan = self._engine.planner.plan(x4.shape[0], device=x4.device)
+        out = run_views(self._engine, x4, 0, F * T, plan, 1, 0, (F, T), None, noise)[0]
+        return out[0] if single else out
+
+    def __repr__(self):
+        return self.__class__.__name__ + f"(ratio={self.ratio})"
 
 
 class NormalizeBatch(nn.Module):
@@ -304,3 +339,40 @@ class NormalizeBatch(nn.Module):
 
     def __repr__(self):
         return self.__class__.__name__ + f"(axis={self.axis})"
+
+
+class RunningNorm(nn.Module):
+    """Online normalization using running mean / std over the samples (reference: augmentations.py:187-210, --pre_norm at
+    main.py:272-277), default `axis=[1, 2]`: one scalar mean and std for the whole (1, F, T) log-mel, updated sample by sample up to
+    `epoch_samples * max_update_epochs` samples.  A batch `(B, 1, F, T)` is processed in sample order, i.e. exactly as B consecutive
+    calls of the reference module; the running state lives on the device (abt_running_norm).  x: CUDA fp32."""
+
+    def __init__(self, epoch_samples, max_update_epochs=10, axis=[1, 2]):
+        super().__init__()
+        if list(axis) != [1, 2]:
+            raise NotImplementedError("only axis=[1, 2] (the reference's only setting) is on the GPU path")
+        self.max_update = epoch_samples * max_update_epochs
+        self.axis = axis
+        self._state = None
+        self._ws = {}
+
+    def forward(self, image: torch.Tensor) -> torch.Tensor:
+        _check_cuda_f32(image, "image")
+        x4, single = _as_batch(image.contiguous())
+        B, elems = int(x4.shape[0]), int(x4.shape[2] * x4.shape[3])
+        dev = x4.device
+        if self._state is None or self._state.device != dev:
+            self._state = torch.zeros(3, dtype=torch.float64, device=dev)
+        lib = _lib.load()
+        if B not in self._ws:
+            nbytes = C.c_size_t()
+            _lib.check(lib.abt_running_norm_workspace_bytes(B, C.byref(nbytes)))
+            self._ws[B] = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        out = torch.empty_like(x4)
+        with torch.cuda.device(dev):
+            _lib.check(lib.abt_running_norm(x4.data_ptr(), B, elems, int(self.max_update), self._state.data_ptr(), out.data_ptr(),
+                                            self._ws[B].data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        return out[0] if single else out
+
+    def __repr__(self):
+        return self.__class__.__name__ + f"(max_update={self.max_update},axis={self.axis})"

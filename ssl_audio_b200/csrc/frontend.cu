@@ -303,6 +303,8 @@ __global__ void __launch_bounds__(kViewThreads) views_kernel(const abt_views_arg
     const float* z = nullptr;
     if ((p.flags & 1) && p.z_kind == 1) z = a.bank + (long long)p.z_index * a.bank_slot_stride;
     if ((p.flags & 1) && p.z_kind == 2) z = a.x + (long long)(a.x_slot ? a.x_slot[p.z_index] : p.z_index) * a.x_slot_stride;
+    // MixGaussianNoise (augmentations.py:133-140): log((1 - lambd) exp(m) + exp(lambd n) + eps) on the mixed-up clip m, n ~ N(0, 1)
+    const float* gn = ((p.flags & 8) && a.noise != nullptr) ? a.noise + ((size_t)clip * a.noise_views + a.view_offset + view) * (size_t)(a.in_h * a.in_w) : nullptr;
 
     const int y0 = (a.canvas_h - a.in_h) / 2, x0 = (a.canvas_w - a.in_w) / 2;
     const bool rrc = (p.flags & 2) != 0;
@@ -327,6 +329,13 @@ __global__ void __launch_bounds__(kViewThreads) views_kernel(const abt_views_arg
                     v.z = __logf(p.w_x * __expf(v.z) + p.w_z * __expf(zv.z) + kF32Eps);
                     v.w = __logf(p.w_x * __expf(v.w) + p.w_z * __expf(zv.w) + kF32Eps);
                 }
+                if (gn != nullptr) {
+                    const float4 nv = __ldg(reinterpret_cast<const float4*>(gn + e));
+                    v.x = __logf(p.g_keep * __expf(v.x) + __expf(p.g_lambda * nv.x) + kF32Eps);
+                    v.y = __logf(p.g_keep * __expf(v.y) + __expf(p.g_lambda * nv.y) + kF32Eps);
+                    v.z = __logf(p.g_keep * __expf(v.z) + __expf(p.g_lambda * nv.z) + kF32Eps);
+                    v.w = __logf(p.g_keep * __expf(v.w) + __expf(p.g_lambda * nv.w) + kF32Eps);
+                }
             }
             *reinterpret_cast<float4*>(canvas + r * a.canvas_w + col) = v;
         }
@@ -338,6 +347,7 @@ __global__ void __launch_bounds__(kViewThreads) views_kernel(const abt_views_arg
                 const int e = (r - y0) * a.in_w + (col - x0);
                 v = __ldg(x + e);
                 if (z != nullptr) v = __logf(p.w_x * __expf(v) + p.w_z * __expf(__ldg(z + e)) + kF32Eps);
+                if (gn != nullptr) v = __logf(p.g_keep * __expf(v) + __expf(p.g_lambda * __ldg(gn + e)) + kF32Eps);
             }
             canvas[r * a.canvas_w + col] = v;
         }
@@ -504,6 +514,62 @@ __global__ void __launch_bounds__(256) batch_norm_apply_kernel(const float* __re
         const long long o = ((i / hw) * n_ch + ch) * hw + (i % hw);
         out[o] = (__ldg(x + o) - mean) * inv;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// RunningNorm (augmentations.py:187-210; --pre_norm, main.py:272-277): online normalisation with running statistics over the
+// SAMPLES, in sample order.  Per sample b: m_b = mean(x_b), mu <- m_b (first sample) or mu + (m_b - mu) / n, v_b = mean((x_b - mu)^2),
+// s2 likewise, out_b = (x_b - mu) / clamp(sqrt(s2), eps).  (n is the count BEFORE the update, exactly as the reference's RunningMean.)
+// Three launches for a batch: per-sample sums, the sequential scalar recurrence (one thread), the elementwise normalisation.
+// state: 3 doubles on the device -- count, mu, s2 -- owned by the Python module.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sample_sums_kernel(const float* __restrict__ x, int elems, double* __restrict__ sums /* [B][2] */) {
+    __shared__ double red[2][8];
+    const float* xb = x + (size_t)blockIdx.x * elems;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i0 = threadIdx.x * 8; i0 < elems; i0 += blockDim.x * 8) {
+        float a = 0.f, q = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (i0 + k < elems) { const float v = __ldg(xb + i0 + k); a += v; q = fmaf(v, v, q); }
+        s1 += (double)a; s2 += (double)q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int w = 0; w < 8; ++w) { t1 += red[0][w]; t2 += red[1][w]; }
+        sums[2 * blockIdx.x] = t1 / elems;          // mean(x_b)
+        sums[2 * blockIdx.x + 1] = t2 / elems;      // mean(x_b^2)
+    }
+}
+
+__global__ void running_norm_scan_kernel(const double* __restrict__ sums, int n_batch, long long max_update, double* __restrict__ state,
+                                         float* __restrict__ mean_std /* [B][2]: mu_b, 1 / std_b */) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double n = state[0], mu = state[1], s2 = state[2];
+    for (int b = 0; b < n_batch; ++b) {
+        if (n < (double)max_update) {
+            const double m = sums[2 * b], q = sums[2 * b + 1];
+            mu = (n == 0.0) ? m : mu + (m - mu) / n;
+            const double v = fmax(q - 2.0 * mu * m + mu * mu, 0.0);     // mean((x - mu)^2)
+            s2 = (n == 0.0) ? v : s2 + (v - s2) / n;
+            n += 1.0;
+        }
+        mean_std[2 * b] = (float)mu;
+        mean_std[2 * b + 1] = 1.0f / fmaxf((float)sqrt(s2), kF32Eps);
+    }
+    state[0] = n; state[1] = mu; state[2] = s2;
+}
+
+__global__ void __launch_bounds__(256) sample_norm_apply_kernel(const float* __restrict__ x, float* __restrict__ out, int elems,
+                                                                const float* __restrict__ mean_std) {
+    const int b = blockIdx.y;
+    const float mu = mean_std[2 * b], inv = mean_std[2 * b + 1];
+    const size_t base = (size_t)b * elems;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += gridDim.x * blockDim.x) out[base + i] = (__ldg(x + base + i) - mu) * inv;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -729,6 +795,8 @@ extern "C" int abt_views_fwd(const abt_views_args* a, abt_stream_t stream) {
     if (a->x == nullptr || a->params == nullptr) return set_error(ABT_ERR_ARG, "null argument");
     if (a->n_clips < 0 || a->n_views < 0 || a->n_views > 8) return set_error(ABT_ERR_ARG, "bad n_clips / n_views (at most 8 views per launch)");
     if (a->param_stride < 0 || a->view_offset < 0) return set_error(ABT_ERR_ARG, "bad param_stride / view_offset");
+    if (a->noise != nullptr && a->noise_views < a->view_offset + a->n_views)
+        return set_error(ABT_ERR_ARG, "noise has %d view planes, this launch reads planes up to %d", a->noise_views, a->view_offset + a->n_views);
     if (a->in_h < 1 || a->in_w < 1 || (a->in_h * a->in_w) % 4 != 0) return set_error(ABT_ERR_ARG, "in_h * in_w must be a positive multiple of 4");
     if (a->canvas_h < a->in_h || a->canvas_w < a->in_w) return set_error(ABT_ERR_ARG, "canvas smaller than input");
     if (a->out_h < 1 || a->out_w < 1 || a->out_h + a->out_w > 256) return set_error(ABT_ERR_ARG, "out_h + out_w must be in [2, 256]");
@@ -781,6 +849,30 @@ extern "C" int abt_normalize_batch(const float* x, int n_batch, int n_channels, 
     const unsigned blocks = (unsigned)((per_ch + 1023) / 1024 < 148 * 8 ? (per_ch + 1023) / 1024 : 148 * 8);
     batch_norm_apply_kernel<<<dim3(blocks, n_channels), 256, 0, st>>>(x, out, n_batch, n_channels, hw, static_cast<const double*>(workspace), kNbBlocks);
     count_launch(2);
+    ABT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int abt_running_norm_workspace_bytes(int n_batch, size_t* bytes) {
+    if (bytes == nullptr || n_batch < 0) return set_error(ABT_ERR_ARG, "bad argument");
+    *bytes = (size_t)n_batch * (2 * sizeof(double) + 2 * sizeof(float)) + 256;
+    return 0;
+}
+
+extern "C" int abt_running_norm(const float* x, int n_batch, int elems, long long max_update, double* state3, float* out, void* workspace,
+                                abt_stream_t stream) {
+    if (n_batch == 0) return 0;
+    if (x == nullptr || out == nullptr || state3 == nullptr || workspace == nullptr) return set_error(ABT_ERR_ARG, "null argument");
+    if (n_batch < 0 || n_batch > 65535 || elems < 1) return set_error(ABT_ERR_ARG, "bad shape");
+    if (int rc = check_device_sm100()) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    double* sums = static_cast<double*>(workspace);
+    float* mean_std = reinterpret_cast<float*>(sums + 2 * (size_t)n_batch);
+    sample_sums_kernel<<<n_batch, 256, 0, st>>>(x, elems, sums);
+    running_norm_scan_kernel<<<1, 32, 0, st>>>(sums, n_batch, max_update, state3, mean_std);
+    const unsigned bx = (unsigned)((elems + 1023) / 1024 < 64 ? (elems + 1023) / 1024 : 64);
+    sample_norm_apply_kernel<<<dim3(bx, n_batch), 256, 0, st>>>(x, out, elems, mean_std);
+    count_launch(3);
     ABT_CUDA_OK(cudaGetLastError());
     return 0;
 }

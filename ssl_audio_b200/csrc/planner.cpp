@@ -6,6 +6,7 @@
 //   datasets.py:344  np.random.randint(l - crop_frames)            time crop of a precomputed log-mel
 //   datasets.py:112  random.randint(0, len - unit_length)          wav crop
 //   augmentations.py:105,108  np.random.random(), np.random.randint(len(bank))      Mixup
+//   augmentations.py:136      np.random.rand()                                       MixGaussianNoise (lambd)
 //   augmentations.py:34-37    np.random.uniform x2, random.randint x2 (conditional)  RandomResizeCrop
 //   augmentations.py:70       np.random.rand(2)                                      RandomLinearFader
 // The generator states are imported from / exported to the interpreter's global generators by the
@@ -210,6 +211,12 @@ extern "C" int abt_planner_plan_batch(abt_planner* p, int n_clips, int time_crop
                         vp->w_z = (float)(1.0 - a);
                     }
                     p->bank_push(uid);
+                }
+                if (c.gnoise) {
+                    const double lambd = (double)c.gnoise_ratio_d * p->np_rng.next_double();
+                    vp->g_lambda = (float)lambd;
+                    vp->g_keep = (float)(1.0 - lambd);
+                    vp->flags |= 8;
                 }
                 if (c.rrc) plan_rrc(p, vp, c.canvas_h, c.canvas_w, c.freq_scale, c.time_scale);
                 if (c.rlf) {

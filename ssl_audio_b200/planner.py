@@ -22,10 +22,11 @@ VIEW_DTYPE = np.dtype([
     ("z_kind", np.int32), ("z_index", np.int32), ("w_x", np.float32), ("w_z", np.float32),
     ("i", np.int32), ("j", np.int32), ("h", np.int32), ("w", np.int32),
     ("head", np.float32), ("tail", np.float32), ("flags", np.int32), ("out_index", np.int32),
+    ("g_lambda", np.float32), ("g_keep", np.float32), ("reserved", np.int32, (2,)),
 ])
-assert VIEW_DTYPE.itemsize == C.sizeof(_lib.ViewParams) == 48
+assert VIEW_DTYPE.itemsize == C.sizeof(_lib.ViewParams) == 64
 
-FLAG_MIXUP, FLAG_RRC, FLAG_RLF = 1, 2, 4
+FLAG_MIXUP, FLAG_RRC, FLAG_RLF, FLAG_GNOISE = 1, 2, 4, 8
 
 
 def _numpy_global_state_address() -> int:
@@ -108,7 +109,8 @@ class ViewPlanner:
                  ring_slots: Optional[int] = None, n_global: int = 2, in_hw: Tuple[int, int] = (64, 96),
                  canvas_hw: Tuple[int, int] = (64, 144), freq_scale: Sequence[float] = (0.6, 1.5),
                  time_scale: Sequence[float] = (0.6, 1.5), n_local: int = 0, local_hw: Tuple[int, int] = (16, 16),
-                 local_scale: Sequence[float] = (0.05, 0.6), fader_gain: float = 1.0):
+                 local_scale: Sequence[float] = (0.05, 0.6), fader_gain: float = 1.0, gnoise: bool = False,
+                 gnoise_ratio: float = 0.2):
         lib = _lib.load()
         cfg = _lib.PlanConfig()
         cfg.mixup, cfg.rrc, cfg.rlf = int(bool(mixup)), int(bool(rrc)), int(bool(rlf))
@@ -124,11 +126,14 @@ class ViewPlanner:
         cfg.local_h, cfg.local_w = int(local_hw[0]), int(local_hw[1])
         cfg.local_scale[0], cfg.local_scale[1] = float(local_scale[0]), float(local_scale[1])
         cfg.fader_gain = float(fader_gain)
+        cfg.gnoise = int(bool(gnoise))
+        cfg.gnoise_ratio_d = float(gnoise_ratio)
         self.cfg = cfg
         self.n_views = cfg.n_global + cfg.n_local
         self.ring_slots = cfg.ring_slots
         self.n_memory = cfg.n_memory
-        self._uses_numpy = bool(mixup or rrc or rlf or n_local)
+        self._uses_numpy = bool(mixup or rrc or rlf or n_local or gnoise)
+        self.gnoise = bool(gnoise)
         self._uses_pyrandom = bool(rrc or n_local)
         self._h = C.c_void_p()
         _lib.check(lib.abt_planner_create(C.byref(cfg), C.byref(self._h)))
@@ -188,7 +193,7 @@ class ViewPlanner:
                                                          py_addr[0] if py_addr else None, py_addr[1] if py_addr else None,
                                                          buf.ctypes.data, buf.nbytes))
         nv = self.n_views
-        params = buf[:48 * nv * n_clips].view(VIEW_DTYPE).reshape(n_clips, nv)
+        params = buf[:VIEW_DTYPE.itemsize * nv * n_clips].view(VIEW_DTYPE).reshape(n_clips, nv)
         starts = buf[off1:off1 + 4 * n_clips].view(np.int32)
         wav_starts = buf[off2:off2 + 4 * n_clips].view(np.int32)
         slots = buf[off3:off3 + 4 * n_clips].view(np.int32)

@@ -9,7 +9,7 @@ collated `(B, 1, ., .)` tensor the reference's DataLoader would have produced.
 """
 from __future__ import annotations
 
-from typing import List
+from typing import List, Optional
 
 import torch
 import torch.nn as nn
@@ -29,8 +29,8 @@ class AudioPairTransform(nn.Module):
         self.multi_transform = multi_transform
         self.local_crops_number = args.local_crops_number
         self.train_transform = train_transform
-        if train_transform is True and args.Gnoise:
-            raise NotImplementedError("args.Gnoise: MixGaussianNoise is outside the accelerated hot path (SURVEY.md section 8f)")
+        self._gnoise = bool(train_transform is True and getattr(args, "Gnoise", False))
+        self._gnoise_ratio = gauss_noise_ratio
         self._mixup = bool(train_transform is True and args.mixup)
         self._rrc = bool(train_transform is True and args.RRC)
         self._rlf = bool(train_transform is True and args.RLF)
@@ -57,7 +57,8 @@ class AudioPairTransform(nn.Module):
             pl = ViewPlanner(mixup=self._mixup, rrc=self._rrc, rlf=self._rlf, mixup_ratio=self._mixup_ratio, n_memory=2048,
                              ring_slots=2048 + self._max_batch, n_global=self._n_global, in_hw=self._in_hw,
                              canvas_hw=self._canvas_hw, freq_scale=self._global_crop_scale, time_scale=self._global_crop_scale,
-                             n_local=self._n_local, local_hw=self._local_hw, local_scale=self._local_crop_scale)
+                             n_local=self._n_local, local_hw=self._local_hw, local_scale=self._local_crop_scale,
+                             gnoise=self._gnoise, gnoise_ratio=self._gnoise_ratio)
             self._engine = ViewEngine(pl, self._in_hw, self._canvas_hw)
         return self._engine
 
@@ -69,7 +70,8 @@ class AudioPairTransform(nn.Module):
         return 0 if self._engine is None else self._engine.planner.bank_len()
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor):
+    def forward(self, x: torch.Tensor, noise: Optional[torch.Tensor] = None):
+        """`noise` (only with args.Gnoise): the N(0, 1) draws of MixGaussianNoise, (B, n_global, F, T) -- see MixGaussianNoise."""
         _check_cuda_f32(x, "x")
         x4, single = _as_batch(x.contiguous())
         if (int(x4.shape[2]), int(x4.shape[3])) != self._in_hw:
@@ -79,15 +81,16 @@ class AudioPairTransform(nn.Module):
         if self._mixup:
             eng.ensure_ring(x4.device)
         plan = eng.planner.plan(B, device=x4.device)
-        outs = self.views_from_plan(x4, 0, self._in_hw[0] * self._in_hw[1], plan)
+        outs = self.views_from_plan(x4, 0, self._in_hw[0] * self._in_hw[1], plan, noise)
         if self._mixup:
             push_bank(eng, x4, self._in_hw[0] * self._in_hw[1], plan)
         if single:
             outs = [o[0] for o in outs]
         return outs if self.multi_transform else outs[0]
 
-    def views_from_plan(self, x, x_slot_ptr, x_slot_stride, plan) -> List[torch.Tensor]:
+    def views_from_plan(self, x, x_slot_ptr, x_slot_stride, plan, noise=None) -> List[torch.Tensor]:
         """Views of an already planned batch whose clips live at x + x_slot[b] * x_slot_stride (x_slot_ptr: device pointer to
         int32 slots, 0 = identity; used by the batch frontend, which lets the log-mel kernel write the clips straight into
         the Mixup ring)."""
-        return run_views(self._engine, x, x_slot_ptr, x_slot_stride, plan, self._n_global, self._n_local, self._in_hw, self._local_hw)
+        return run_views(self._engine, x, x_slot_ptr, x_slot_stride, plan, self._n_global, self._n_local, self._in_hw, self._local_hw,
+                         noise)

@@ -33,12 +33,23 @@ def test_version_and_error_string():
     assert isinstance(lib.abt_last_error(), bytes)
 
 
-def test_struct_sizes_match_header():
-    assert C.sizeof(_lib.ViewParams) == 48
-    assert C.sizeof(_lib.MelConfig) == 40
-    assert C.sizeof(_lib.BtArgs) == 8 * 2 + 4 * 10 + 8 * 7
-    assert C.sizeof(_lib.ViewsArgs) == 4 * 10 + 8 * 6 + 8 * 8
-    assert C.sizeof(_lib.PlanConfig) == 16 + 8 + 4 * 7 + 4 + 32 + 12 + 4 + 16 + 8
+def test_struct_sizes_match_header(tmp_path):
+    """sizeof of every struct that crosses the boundary, as gcc lays it out from include/abt_b200.h, equals the ctypes mirror."""
+    import subprocess
+    pairs = {"abt_view_params": _lib.ViewParams, "abt_mel_config": _lib.MelConfig, "abt_bt_args": _lib.BtArgs,
+             "abt_views_args": _lib.ViewsArgs, "abt_plan_config": _lib.PlanConfig, "abt_bt_rows_args": _lib.BtRowsArgs,
+             "abt_bt_dist_layout": _lib.BtDistLayout, "abt_bt_dist_args": _lib.BtDistArgs, "abt_bt_dist_step_args": _lib.BtDistStepArgs}
+    src = tmp_path / "sz.c"
+    header = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "abt_b200.h")
+    body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in pairs)
+    src.write_text(f'#include <stdio.h>\n#include "{header}"\nint main(void){{{body}return 0;}}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    sizes = dict(zip(out[::2], (int(v) for v in out[1::2])))
+    for name, cls in pairs.items():
+        assert sizes[name] == C.sizeof(cls), name
+    assert sizes["abt_view_params"] == 64
 
 
 def test_argument_validation_needs_no_gpu():

@@ -295,3 +295,55 @@ def test_normalize_batch_matches_reference_golden(golden_dir):
     assert abs(float(y.mean())) < 1e-4 and abs(float(y.std()) - 1.0) < 1e-4
     with pytest.raises(RuntimeError):
         mod(torch.zeros(2, 1, 64, 96))
+
+
+def test_running_norm_matches_reference_golden(golden_dir):
+    """RunningNorm (--pre_norm, main.py:272-277) against the reference module fed sample by sample: a whole batch in one call, the same
+    sequence split over several calls (the running state is carried on the device), single (1, F, T) samples, and the frozen
+    statistics after max_update samples."""
+    import ssl_audio_b200 as S
+    g = np.load(os.path.join(golden_dir, "prenorm.npz"))
+    for tag in ("a", "b"):
+        epoch_samples, max_epochs = (int(v) for v in g[f"{tag}_cfg"])
+        x, ref = torch.from_numpy(g[f"{tag}_x"]).cuda(), g[f"{tag}_y"]
+        y = S.RunningNorm(epoch_samples, max_epochs)(x).cpu().numpy()
+        np.testing.assert_allclose(y, ref, rtol=0, atol=2e-5, err_msg=tag)
+        np.testing.assert_allclose(y, O.running_norm(g[f"{tag}_x"], epoch_samples, max_epochs), rtol=0, atol=2e-5)
+        mod = S.RunningNorm(epoch_samples, max_epochs)
+        parts = [mod(x[:3]), mod(x[3]).unsqueeze(0), mod(x[4:])]
+        np.testing.assert_allclose(torch.cat(parts).cpu().numpy(), ref, rtol=0, atol=2e-5, err_msg=tag + " split")
+    with pytest.raises(RuntimeError):
+        S.RunningNorm(10)(torch.zeros(2, 1, 64, 96))
+
+
+def test_mix_gaussian_noise_matches_reference_golden(golden_dir):
+    """MixGaussianNoise (args.Gnoise): the bare module and the whole Mixup -> Gnoise -> RRC -> RLF chain against the reference, fed the
+    reference's own N(0, 1) draws; then the default path, whose draws come from torch's CUDA generator, against the oracle fed the
+    same draws."""
+    import ssl_audio_b200 as S
+    g = np.load(os.path.join(golden_dir, "gnoise.npz"))
+    np.random.seed(41)
+    mod = S.MixGaussianNoise(ratio=0.2)
+    y = mod(torch.from_numpy(g["m_x"]).cuda(), torch.from_numpy(g["m_n"]).cuda()).cpu().numpy()
+    assert np.abs(y - g["m_y"]).max() < TOL
+    seed = int(g["seed"])
+    x, noise = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["noise"]).cuda()
+    np.random.seed(seed); random.seed(seed)
+    v = S.AudioPairTransform(_args(Gnoise=True))(x, noise)
+    got = torch.stack(v, 1).cpu().numpy()
+    assert np.abs(got - g["views"]).max() < TOL, np.abs(got - g["views"]).max()
+    np.random.seed(seed); random.seed(seed)
+    tf = S.AudioPairTransform(_args(Gnoise=True))
+    for b in range(6):                                         # sample by sample, like Dataset.__getitem__
+        crops = tf(x[b], noise[b:b + 1])
+        assert np.abs(torch.stack(crops).cpu().numpy() - g["views"][b]).max() < TOL
+    # default: noise drawn on the device
+    np.random.seed(7); torch.manual_seed(7)
+    y = S.MixGaussianNoise(0.2)(x[0])
+    torch.manual_seed(7)
+    n = torch.randn(1, 1, 64, 96, device="cuda").cpu().numpy()[0]
+    np.random.seed(7)
+    ref, _ = O.mix_gaussian_noise(g["x"][0], 0.2, n)
+    assert tuple(y.shape) == (1, 64, 96) and np.abs(y.cpu().numpy() - ref).max() < TOL
+    with pytest.raises(ValueError):
+        S.AudioPairTransform(_args(Gnoise=True))(x, noise[:3])

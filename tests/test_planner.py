@@ -122,3 +122,29 @@ def test_rrc_ranges_property():
     assert (p["i"] >= 0).all() and (p["i"] + p["h"] <= 64).all()
     assert (p["j"] >= 0).all() and (p["j"] + p["w"] <= 144).all()
     assert 0.45 < (p["h"] == 64).mean() < 0.65          # P(h = 64) ~ 55.8 %
+
+
+def test_gaussian_noise_draw_order(golden_dir):
+    """args.Gnoise adds one np.random.rand() per global view between the Mixup and the RandomResizeCrop draws
+    (augmentations.py:136, utils/transforms.py:18-34): lambd and everything drawn after it must match the oracle replay."""
+    g = np.load(os.path.join(golden_dir, "gnoise.npz"))
+    seed = int(g["seed"])
+    np.random.seed(seed); random.seed(seed)
+    pl = ViewPlanner(mixup=True, rrc=True, rlf=True, gnoise=True)
+    p = pl.plan(6).params
+    after = (np.random.random(), random.random())
+    np.random.seed(seed); random.seed(seed)
+    st_, cfg = O.MixupState(), O.PairTransformConfig(Gnoise=True)
+    for b in range(6):
+        _, recs = O.audio_pair_transform(g["x"][b], cfg, st_, g["noise"][b][:, None])
+        for v, r in enumerate(recs):
+            pv = p[b, v]
+            assert pv["flags"] == 15
+            assert pv["g_lambda"] == np.float32(r["lambd"]) and pv["g_keep"] == np.float32(1 - r["lambd"])
+            assert (pv["i"], pv["j"], pv["h"], pv["w"]) == (r["i"], r["j"], r["h"], r["w"])
+            assert pv["head"] == np.float32(r["head"]) and pv["tail"] == np.float32(r["tail"])
+    assert after == (np.random.random(), random.random())
+    # without the flag nothing changes: no draw, no flag
+    np.random.seed(3); random.seed(3)
+    q = ViewPlanner(mixup=True, rrc=True, rlf=True).plan(2).params
+    assert (q["flags"] == 7).all() and (q["g_lambda"] == 0).all()
