@@ -10,7 +10,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libabt_b200.so")
+LIB_PATH = os.environ.get("ABT_LIB") or os.path.join(_HERE, "libabt_b200.so")     # ABT_LIB: A/B timing of two builds on one box
 
 ABT_ERR_ARG = -1
 

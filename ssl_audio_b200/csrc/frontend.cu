@@ -42,7 +42,7 @@ constexpr int kNfft = 1024;
 constexpr int kMels = 64;
 constexpr int kTileFrames = 32;
 constexpr int kWarps = 8;
-constexpr int kScratchFloats = 2 * 32 * 33;   // per warp
+constexpr int kScratchFloats = 2 * 32 * 33 + 2;   // per warp; the +2 staggers the warps' power spectra over the banks for the mel pass
 constexpr float kF32Eps = 1.1920928955078125e-07f;
 
 struct LogmelArgs {
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
             }
             fft32(re, im);   // register p: Y[n1 = lane][k2 = bitrev(p)]
             // twiddle W1024^(n1 k2) and transpose through shared memory (64-bit accesses, conflict-free with the 33-stride)
-            __syncwarp();    // the previous round's mel reads of this scratch are complete
+            __syncwarp();
 #pragma unroll
             for (int p = 0; p < 32; ++p) {
                 const int k2 = bitrev5(p);
@@ -184,7 +184,6 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
             const int lp = (32 - lane) & 31;
 #pragma unroll
             for (int k1 = 0; k1 < 16; ++k1) {
-                constexpr int dummy = 0; (void)dummy;
                 const int p = bitrev5(k1), pq = bitrev5(31 - k1), pq0 = bitrev5((32 - k1) & 31);
                 float qr = __shfl_sync(0xffffffffu, re[pq], lp), qi = __shfl_sync(0xffffffffu, im[pq], lp);
                 if (lane == 0) { qr = re[pq0]; qi = im[pq0]; }
@@ -196,42 +195,35 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
                 const int p16 = bitrev5(16);
                 sc[512] = make_float2(4.0f * re[p16] * re[p16], 4.0f * im[p16] * im[p16]);
             }
-            __syncwarp();
-            // sparse mel projection: this lane owns bands `lane` and `63 - lane` of both frames
+        }
+        // ---- sparse mel projection of the round's 16 frames, across the warps: thread = (frame f, band group g).  The 16 lanes of a
+        // half-warp read the same weight (broadcast) and 16 different frames' power -- frame f = 2 * warp + {0, 1} sits at float offset
+        // warp * kScratchFloats + 2 k + {0, 1}, i.e. bank (f + 2 k) mod 32: conflict-free.  Band lengths grow with the band index, so a
+        // thread takes bands g, 31 - g, 32 + g, 63 - g: about 61 of the 970 non-zero weights each.
+        __syncthreads();
+        if ((f_first + round * 2 * kWarps) < a.n_frames_total && (tile * kTileFrames + round * 2 * kWarps) < a.n_frames_out) {   // block-uniform
+            const int f = tid & 15, g = tid >> 4;
+            const float* pf = s_scratch + (f >> 1) * kScratchFloats + (f & 1);
 #pragma unroll
-            for (int hm = 0; hm < 2; ++hm) {
-                const int m = hm == 0 ? lane : (kMels - 1 - lane);
+            for (int q = 0; q < 4; ++q) {
+                const int m = (q >> 1) * 32 + ((q & 1) ? 31 - g : g);
                 const int ks = s_mel_start[m], kl = s_mel_start[kMels + m];
                 const float* w = s_melw + s_mel_start[2 * kMels + m];
-                float ma = 0.f, mb = 0.f;
-                // two bins per iteration: 16-byte read of (Pa, Pb) x 2 and 8-byte read of two weights (the host aligns every band's
-                // weight array so that even bins sit at even offsets)
-                int k = ks;
-                const int kend = ks + kl;
-                if ((k & 1) && k < kend) {
-                    const float wt = w[0];
-                    const float2 pv = sc[k];
-                    ma = fmaf(wt, pv.x, ma); mb = fmaf(wt, pv.y, mb);
-                    ++k;
-                }
+                const float* pk = pf + 2 * ks;
+                float m0 = 0.f, m1 = 0.f;
+                int k = 0;
 #pragma unroll 2
-                for (; k + 1 < kend; k += 2) {
-                    const float2 wt = *reinterpret_cast<const float2*>(w + (k - ks));
-                    const float4 pv = *reinterpret_cast<const float4*>(sc + k);
-                    ma = fmaf(wt.x, pv.x, ma); mb = fmaf(wt.x, pv.y, mb);
-                    ma = fmaf(wt.y, pv.z, ma); mb = fmaf(wt.y, pv.w, mb);
+                for (; k + 1 < kl; k += 2) {
+                    m0 = fmaf(w[k], pk[2 * k], m0);
+                    m1 = fmaf(w[k + 1], pk[2 * k + 2], m1);
                 }
-                if (k < kend) {
-                    const float wt = w[k - ks];
-                    const float2 pv = sc[k];
-                    ma = fmaf(wt, pv.x, ma); mb = fmaf(wt, pv.y, mb);
-                }
-                float la = __logf(ma + kF32Eps), lb = __logf(mb + kF32Eps);      // lg2.approx * ln 2: |err| ~ 1e-6, far inside the 1e-3 log-mel tolerance
-                if (a.apply_norm) { la = (la - a.norm_mean) * a.inv_std; lb = (lb - a.norm_mean) * a.inv_std; }
-                s_out[m * (kTileFrames + 1) + fa] = la;
-                s_out[m * (kTileFrames + 1) + fb] = lb;
+                if (k < kl) m0 = fmaf(w[k], pk[2 * k], m0);
+                float l = __logf(m0 + m1 + kF32Eps);      // lg2.approx * ln 2: |err| ~ 1e-6, far inside the 1e-3 log-mel tolerance
+                if (a.apply_norm) l = (l - a.norm_mean) * a.inv_std;
+                s_out[m * (kTileFrames + 1) + round * 2 * kWarps + f] = l;
             }
         }
+        if (round + 1 < kTileFrames / (2 * kWarps)) __syncthreads();      // the next round's transposes reuse the scratch
     }
     __syncthreads();
     // ---- coalesced store: rows of up to 32 consecutive frames per mel band
