@@ -14,7 +14,7 @@
 //     warp transposes through a padded (bank-conflict-free) shared tile, each lane runs a second
 //     32-point FFT;  X[k] and X[1024-k] are recombined into the two power spectra;
 //   * the mel projection uses the filterbank's sparsity (<= 2 filters per bin, 970 non-zeros of
-//     32832): each lane gathers two mel bands from the shared power spectrum (CSR);
+//     32832), as a block-wide pass over the 16 frames of a round: thread = (frame, band group), CSR weights;
 //   * log, z-score, and a staged, time-contiguous (coalesced) store.
 #include "abt_internal.h"
 #include "fft32_gen.cuh"

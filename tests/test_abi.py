@@ -65,6 +65,14 @@ def test_argument_validation_needs_no_gpu():
     cfg = _lib.MelConfig(16000, 512, 512, 160, 64, 60.0, 7800.0, 0, 0.0, 1.0)
     h = C.c_void_p()
     assert lib.abt_logmel_plan_create(C.byref(cfg), C.byref(h)) == _lib.ABT_ERR_ARG   # n_fft must be 1024
+    assert lib.abt_running_norm_workspace_bytes(-1, C.byref(nbytes)) == _lib.ABT_ERR_ARG
+    assert lib.abt_running_norm_workspace_bytes(8, C.byref(nbytes)) == 0 and nbytes.value >= 8 * 24
+    assert lib.abt_running_norm(None, 4, 6144, 10, None, None, None, None) == _lib.ABT_ERR_ARG
+    va = _lib.ViewsArgs()
+    va.n_clips, va.n_views, va.in_h, va.in_w, va.canvas_h, va.canvas_w, va.out_h, va.out_w = 2, 2, 64, 96, 64, 144, 64, 96
+    va.x, va.params, va.noise, va.noise_views = 1 << 20, 1 << 20, 1 << 20, 1        # (never dereferenced: validation fails first)
+    assert lib.abt_views_fwd(C.byref(va), None) == _lib.ABT_ERR_ARG
+    assert b"noise" in lib.abt_last_error()
 
 
 def test_no_cpu_fallback():
