@@ -272,6 +272,25 @@ __device__ __forceinline__ float cubic2(float x) {   // 1 < |x| < 2
 
 constexpr int kViewThreads = 384;
 
+// exp / log on the special-function unit (ex2 / lg2, relative error ~1e-6, far inside the 1e-3 tolerance of the views).  The .ftz forms
+// skip the denormal range checks nvcc wraps around __expf / __logf (4 extra instructions per call); flushing is harmless here: every
+// sum below carries + eps, so a flushed exp() term is below half an ulp of the result either way.
+__device__ __forceinline__ float exp_sfu(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+__device__ __forceinline__ float lds_f32(unsigned addr) {     // volatile asm: never moved across the __syncthreads between the passes
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float log_sfu(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y * 0.6931471805599453f;
+}
+
 // One CTA per (clip, view).  Three phases over shared memory:
 //   1. the crop rows of the virtual canvas: log-mixup-exp of x with its partner inside the pasted region, zeros outside
 //      (every canvas element the taps can touch is written exactly once; float4 global loads);
@@ -315,18 +334,17 @@ __global__ void __launch_bounds__(kViewThreads) views_kernel(const abt_views_arg
                 v = __ldg(reinterpret_cast<const float4*>(x + e));
                 if (z != nullptr) {
                     const float4 zv = __ldg(reinterpret_cast<const float4*>(z + e));
-                    // fast exp2/log2 (MUFU): relative error ~1e-6, far inside the 1e-3 tolerance of the views
-                    v.x = __logf(p.w_x * __expf(v.x) + p.w_z * __expf(zv.x) + kF32Eps);
-                    v.y = __logf(p.w_x * __expf(v.y) + p.w_z * __expf(zv.y) + kF32Eps);
-                    v.z = __logf(p.w_x * __expf(v.z) + p.w_z * __expf(zv.z) + kF32Eps);
-                    v.w = __logf(p.w_x * __expf(v.w) + p.w_z * __expf(zv.w) + kF32Eps);
+                    v.x = log_sfu(p.w_x * exp_sfu(v.x) + p.w_z * exp_sfu(zv.x) + kF32Eps);
+                    v.y = log_sfu(p.w_x * exp_sfu(v.y) + p.w_z * exp_sfu(zv.y) + kF32Eps);
+                    v.z = log_sfu(p.w_x * exp_sfu(v.z) + p.w_z * exp_sfu(zv.z) + kF32Eps);
+                    v.w = log_sfu(p.w_x * exp_sfu(v.w) + p.w_z * exp_sfu(zv.w) + kF32Eps);
                 }
                 if (gn != nullptr) {
                     const float4 nv = __ldg(reinterpret_cast<const float4*>(gn + e));
-                    v.x = __logf(p.g_keep * __expf(v.x) + __expf(p.g_lambda * nv.x) + kF32Eps);
-                    v.y = __logf(p.g_keep * __expf(v.y) + __expf(p.g_lambda * nv.y) + kF32Eps);
-                    v.z = __logf(p.g_keep * __expf(v.z) + __expf(p.g_lambda * nv.z) + kF32Eps);
-                    v.w = __logf(p.g_keep * __expf(v.w) + __expf(p.g_lambda * nv.w) + kF32Eps);
+                    v.x = log_sfu(p.g_keep * exp_sfu(v.x) + exp_sfu(p.g_lambda * nv.x) + kF32Eps);
+                    v.y = log_sfu(p.g_keep * exp_sfu(v.y) + exp_sfu(p.g_lambda * nv.y) + kF32Eps);
+                    v.z = log_sfu(p.g_keep * exp_sfu(v.z) + exp_sfu(p.g_lambda * nv.z) + kF32Eps);
+                    v.w = log_sfu(p.g_keep * exp_sfu(v.w) + exp_sfu(p.g_lambda * nv.w) + kF32Eps);
                 }
             }
             *reinterpret_cast<float4*>(canvas + r * a.canvas_w + col) = v;
@@ -338,8 +356,8 @@ __global__ void __launch_bounds__(kViewThreads) views_kernel(const abt_views_arg
             if (r >= y0 && r < y0 + a.in_h && col >= x0 && col < x0 + a.in_w) {
                 const int e = (r - y0) * a.in_w + (col - x0);
                 v = __ldg(x + e);
-                if (z != nullptr) v = __logf(p.w_x * __expf(v) + p.w_z * __expf(__ldg(z + e)) + kF32Eps);
-                if (gn != nullptr) v = __logf(p.g_keep * __expf(v) + __expf(p.g_lambda * __ldg(gn + e)) + kF32Eps);
+                if (z != nullptr) v = log_sfu(p.w_x * exp_sfu(v) + p.w_z * exp_sfu(__ldg(z + e)) + kF32Eps);
+                if (gn != nullptr) v = log_sfu(p.g_keep * exp_sfu(v) + exp_sfu(p.g_lambda * __ldg(gn + e)) + kF32Eps);
             }
             canvas[r * a.canvas_w + col] = v;
         }
@@ -359,7 +377,7 @@ __global__ void __launch_bounds__(kViewThreads) views_kernel(const abt_views_arg
         for (int k = 0; k < 4; ++k) {
             int sk = base - 1 + k;
             sk = sk < 0 ? 0 : (sk > n_in_ax - 1 ? n_in_ax - 1 : sk);
-            sidx[k] = sk + (is_x ? cj : 0);          // x taps in canvas columns, y taps relative to the crop's first row
+            sidx[k] = is_x ? sk + cj : sk * a.out_w * 4;   // x taps: canvas columns; y taps: BYTE offsets of the hbuf rows (relative to the crop's first row)
         }
         tap[tid] = make_int4(sidx[0], sidx[1], sidx[2], sidx[3]);
         coef[tid] = make_float4(cubic2(t + 1.0f), cubic1(t), cubic1(1.0f - t), cubic2(2.0f - t));
@@ -372,10 +390,14 @@ __global__ void __launch_bounds__(kViewThreads) views_kernel(const abt_views_arg
     if (active) {
         const int4 tx = tap[ox];
         const float4 cx = coef[ox];
-        for (int yy = grp; yy < chh; yy += n_groups) {
-            const float* row = canvas + (ci + yy) * a.canvas_w;
-            hbuf[yy * a.out_w + ox] = row[tx.x] * cx.x + row[tx.y] * cx.y + row[tx.z] * cx.z + row[tx.w] * cx.w;
-        }
+        // shared-memory byte addresses: the four taps of this thread's column in row ci + grp, advanced by n_groups rows per iteration
+        const unsigned row0 = static_cast<unsigned>(__cvta_generic_to_shared(canvas + (ci + grp) * a.canvas_w));
+        unsigned t0 = row0 + tx.x * 4, t1 = row0 + tx.y * 4, t2 = row0 + tx.z * 4, t3 = row0 + tx.w * 4;
+        const unsigned row_step = (unsigned)(n_groups * a.canvas_w) * 4u;
+        float* hdst = hbuf + grp * a.out_w + ox;
+        const int hstep = n_groups * a.out_w;
+        for (int yy = grp; yy < chh; yy += n_groups, t0 += row_step, t1 += row_step, t2 += row_step, t3 += row_step, hdst += hstep)
+            *hdst = lds_f32(t0) * cx.x + lds_f32(t1) * cx.y + lds_f32(t2) * cx.z + lds_f32(t3) * cx.w;
     }
     __syncthreads();
     // ---- phase 3: vertical pass + fader (torch.linspace(head, tail, T) evaluated from both ends with one rounding)
@@ -383,16 +405,21 @@ __global__ void __launch_bounds__(kViewThreads) views_kernel(const abt_views_arg
         const bool fade = (p.flags & 4) != 0;
         const float step = a.out_w > 1 ? (p.tail - p.head) / (float)(a.out_w - 1) : 0.f;
         const float fv = !fade ? 0.f : ((ox < a.out_w / 2) ? fmaf(step, (float)ox, p.head) : fmaf(-step, (float)(a.out_w - 1 - ox), p.tail));
-        float* out = a.outs[view] + (size_t)clip * a.out_h * a.out_w;
-        for (int oy = grp; oy < a.out_h; oy += n_groups) {
-            const int4 ty = tap[a.out_w + oy];
-            const float4 cy = coef[a.out_w + oy];
+        // everything that changes per row advances by a constant: the table pointers, the output pointer; the taps are byte offsets
+        float* out = a.outs[view] + (size_t)clip * a.out_h * a.out_w + (size_t)grp * a.out_w + ox;
+        const size_t out_step = (size_t)n_groups * a.out_w;
+        const unsigned hcol = static_cast<unsigned>(__cvta_generic_to_shared(hbuf + ox));
+        const int4* tp = tap + a.out_w + grp;
+        const float4* cp = coef + a.out_w + grp;
+        for (int oy = grp; oy < a.out_h; oy += n_groups, tp += n_groups, cp += n_groups, out += out_step) {
+            const int4 ty = *tp;
+            const float4 cy = *cp;
             float acc = 0.f;
-            acc += hbuf[ty.x * a.out_w + ox] * cy.x;
-            acc += hbuf[ty.y * a.out_w + ox] * cy.y;
-            acc += hbuf[ty.z * a.out_w + ox] * cy.z;
-            acc += hbuf[ty.w * a.out_w + ox] * cy.w;
-            out[oy * a.out_w + ox] = fade ? acc + fv : acc;
+            acc += lds_f32(hcol + ty.x) * cy.x;
+            acc += lds_f32(hcol + ty.y) * cy.y;
+            acc += lds_f32(hcol + ty.z) * cy.z;
+            acc += lds_f32(hcol + ty.w) * cy.w;
+            *out = fade ? acc + fv : acc;
         }
     }
 }
