@@ -49,12 +49,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(bdir, exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(bdir, src.rsplit(".", 1)[0] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
+        if src.endswith(".cpp"):      # host-only source: straight to the host compiler (function multi-versioning does not survive cudafe)
+            cmd = [os.environ.get("CXX") or shutil.which("g++") or "g++", "-O3", "-std=c++17", "-fPIC", "-c", os.path.join(CSRC, src), "-o", obj]
+        else:
+            cmd = [nvcc, *NVCC_FLAGS, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+            raise RuntimeError(f"compiling {src} failed:\n{r.stdout}\n{r.stderr}")
         if verbose:
             sys.stderr.write(r.stderr)
         objs.append(obj)
