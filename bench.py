@@ -321,18 +321,23 @@ def run_ours(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    h0 = time.perf_counter()
-    probe = min(args.steps, 32)        # host time to ENQUEUE a step, taken over the first steps only: later the launch queue is full and the
-    host_ms = 0.0                      # enqueueing thread is paced by the device, so a whole-loop average would just repeat ms_per_step
-    for i in range(args.steps):
+    for _ in range(args.steps):
         out = step(wav, z1, z2)
-        if i == probe - 1:
-            host_ms = (time.perf_counter() - h0) * 1e3 / probe
     e1.record()
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     launches = int(lib.abt_debug_launch_count(0))
+    # host time to ENQUEUE one step, each step timed alone with the device idle before it: inside the loop above the enqueueing thread
+    # is paced by the device (launch queue, plan staging ring), so its wall time there would only repeat ms_per_step
+    host_samples = []
+    for _ in range(12):
+        sync_all()
+        h0 = time.perf_counter()
+        step(wav, z1, z2)
+        host_samples.append(time.perf_counter() - h0)
+    sync_all()
+    host_ms = sorted(host_samples)[len(host_samples) // 2] * 1e3
     loss_val = float(out[1].detach())
 
     # loss-only pass with per-launch CUDA events on the launching stream (the roofline numbers: in the step above the tensor-core
