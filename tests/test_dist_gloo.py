@@ -1,4 +1,4 @@
-"""World-size-2 test of the multi-GPU objective's host logic (ssl_audio_b200/dist.py) on CPUs with gloo: dimension
+"""World-size-2 and -4 tests of the multi-GPU objective's host logic (ssl_audio_b200/dist.py) on CPUs with gloo: dimension
 partition, all-gather order, gradient all-to-all and loss reduction.  The three compute stages are injected as a
 numpy backend here (test infrastructure); on a GPU box the same choreography drives abt_bt_dist_stats_local /
 abt_bt_dist_normalize / abt_bt_dist_rows_fwd_bwd (tests/test_gpu_dist.py)."""
@@ -107,13 +107,12 @@ def _worker(rank, world, port, hsic, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("hsic", [False, True])
-def test_global_objective_world2_gloo(hsic):
-    world = 2
+@pytest.mark.parametrize("world,hsic", [(2, False), (2, True), (4, False)])
+def test_global_objective_gloo(world, hsic):
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), hsic, out), nprocs=world, join=True)
-    assert dict(out) == {0: True, 1: True}
+    assert dict(out) == {r: True for r in range(world)}
 
 
 def test_row_block_partition():
