@@ -39,14 +39,18 @@ def _args_ns(dim):
                                  unit_sec=0.95, projector_out_dim=dim, HSIC=False, alpha=1.0, lmbda=0.005)
 
 
-def _traffic():
-    """DRAM bytes (read + write) of the CORR + GRAD launches of one step, from the committed `ncu --set full` capture."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        with open(path) as f:
-            return json.load(f)["umma_dram_bytes_per_step"]
-    except Exception:
-        return None
+def _traffic(key="umma_dram_bytes_per_step"):
+    """DRAM bytes (read + write) per launch of a kernel, from the committed `ncu --set full` captures (profiles/r2_traffic.json, else
+    round 1's); None when that kernel has no capture."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                v = json.load(f).get(key)
+            if v is not None:
+                return v
+        except Exception:
+            pass
+    return None
 
 
 def _peaks():
@@ -165,29 +169,38 @@ def run_reference(args):
     torch.set_num_threads(cores)
     B, D, L = args.batch, args.dim, int(args.clip_seconds * 16000)
     workers = cores
-    sample_clips = max(workers, min(B, workers * args.ref_clips_per_worker))
-    # every "step" of this arm is a bounded CPU sample (about a second); cap the count so the run ends within a few minutes
-    args.steps = min(args.steps, 20)
-    args.warmup = min(args.warmup, 3)
-    n_steps = args.steps + args.warmup
+    host = P.host_description()
+    n_steps = args.steps + args.warmup                                      # --steps and --warmup are honoured as given
+    # A step = the FULL workload (all B clips through the per-sample frontend on `workers` single-threaded processes + the loss
+    # fwd/bwd on all B rows).  Only if K + W full steps would not end within the time budget is the frontend timed on a bounded
+    # sample of the clips; the loss always runs at full size (its D x D passes do not scale with the row count).
+    t0 = time.perf_counter()
+    fe_rate = P.time_frontend(B, L, workers)
+    loss_s = P.time_loss(B, D)
+    first_s = time.perf_counter() - t0
+    clips = B
+    if first_s * n_steps > args.ref_budget_s and n_steps > 1:
+        fe_budget = max(0.05, (args.ref_budget_s - first_s) / (n_steps - 1) - loss_s)
+        clips = int(min(B, max(workers, fe_budget * fe_rate)))
+        clips = max(workers, clips // workers * workers)
     vals = []
-    fe_rate = loss_s = None
     for s in range(n_steps):
-        fe_rate = P.time_frontend(sample_clips, L, workers)                # clips/s on `workers` processes
-        loss_s = P.time_loss(min(B, args.ref_loss_rows), D)                # seconds for fwd+bwd on the row sample
-        loss_s_full = loss_s * (B / min(B, args.ref_loss_rows))            # the GEMMs are linear in the row count
-        step_s = B / fe_rate + loss_s_full
+        if s > 0:
+            fe_rate = P.time_frontend(clips, L, workers)                    # clips/s on `workers` processes
+            loss_s = P.time_loss(B, D) if first_s * n_steps <= args.ref_budget_s or s % 8 == 0 else loss_s
+        step_s = B / fe_rate + loss_s
         if s >= args.warmup:
             vals.append(B / step_s)
     value = sum(vals) / len(vals)
-    sample = (f"per step: frontend timed on {sample_clips} of {B} clips ({workers} single-threaded worker processes, the reference's "
-              f"DataLoader model), loss fwd+bwd timed on {min(B, args.ref_loss_rows)} of {B} rows at D={D} (fp32, {cores} threads) and scaled linearly")
+    sample = (f"per step: frontend timed on {clips} of {B} clips ({workers} single-threaded worker processes, the reference's DataLoader "
+              f"model); loss fwd+bwd on all {B} rows at D={D} (fp32, {cores} threads)" + ("" if clips == B else "; frontend sampled to keep "
+              f"{n_steps} steps within {args.ref_budget_s:.0f} s, loss re-timed every 8th step"))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * B / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": _config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "frontend_clips_per_s": fe_rate, "loss_fwd_bwd_s": loss_s},
+                         "frontend_clips_per_s": fe_rate, "loss_fwd_bwd_s": loss_s, "host": host},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -361,6 +374,10 @@ def run_ours(args):
     stats_ms, corr_ms, grad_ms, ncalls = C.c_float(), C.c_float(), C.c_float(), C.c_int()
     _lib.check(lib.abt_debug_timing_read(C.byref(stats_ms), C.byref(corr_ms), C.byref(grad_ms), C.byref(ncalls)))
     _lib.check(lib.abt_debug_timing(0))
+    # the library averages over CALLS; a multi-GPU step makes several (front / dz1 / dz2 phases): account per STEP
+    calls_per_step = ncalls.value / float(args.steps)
+    for v in (stats_ms, corr_ms, grad_ms):
+        v.value = v.value * calls_per_step
 
     # frontend-only and loss-only device times (explain `value`; not the headline)
     fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -370,6 +387,72 @@ def run_ours(args):
     fe1.record()
     torch.cuda.synchronize(dev)
     fe_ms = fe0.elapsed_time(fe1) / args.steps
+
+    # ---- mode F (BASELINE config 2 as worded): the full (B, 64, 1001) log-mel is emitted as well as the two views
+    fe_full = S.BatchFrontend(cfg, norm_stats=AS_STATS, path="lms", mode="full")
+    for _ in range(3):
+        fe_full(wav)
+    torch.cuda.synchronize(dev)
+    ff0, ff1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ff0.record()
+    for _ in range(args.steps):
+        fe_full(wav)
+    ff1.record()
+    torch.cuda.synchronize(dev)
+    fe_full_ms = ff0.elapsed_time(ff1) / args.steps
+    del fe_full
+
+    # ---- BASELINE config 3: loss fwd+bwd sweep, N = 128 rows per GPU, D = 2048 / 4096 / 8192 (global batch 128 x world).
+    # Every iteration is timed alone with CUDA events after an L2 flush (the 2 MB embeddings would otherwise sit in L2).
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sweep = []
+    for d_s in (2048, 4096, 8192):
+        gs = torch.Generator(device=dev).manual_seed(100 + rank)
+        a0 = torch.randn(128, d_s, device=dev, generator=gs)
+        b0 = (0.6 * a0 + 0.8 * torch.randn(128, d_s, device=dev, generator=gs)).bfloat16()
+        a0 = a0.bfloat16()
+        crit_s = S.BarlowTwinsLoss(_args_ns(d_s), ncrops=2).to(dev)
+
+        def one():
+            a = a0.detach().requires_grad_(True)
+            b = b0.detach().requires_grad_(True)
+            lo = crit_s(b, a, ngcrops_each=1)
+            lo.backward()
+            return lo
+        for _ in range(5):
+            one()
+        sync_all()
+        _lib.check(lib.abt_debug_timing(1))
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.sweep_iters)]
+        for e_a, e_b in evs:
+            flush.zero_()
+            e_a.record()
+            lo = one()
+            e_b.record()
+        torch.cuda.synchronize(dev)
+        st_s, co_s, gr_s, nc_s = C.c_float(), C.c_float(), C.c_float(), C.c_int()
+        _lib.check(lib.abt_debug_timing_read(C.byref(st_s), C.byref(co_s), C.byref(gr_s), C.byref(nc_s)))
+        _lib.check(lib.abt_debug_timing(0))
+        per = nc_s.value / float(args.sweep_iters)
+        times = sorted(e_a.elapsed_time(e_b) for e_a, e_b in evs)
+        sweep.append([d_s, times[len(times) // 2], (co_s.value + gr_s.value) * per, st_s.value * per, float(lo.detach())])
+        del crit_s
+    del flush
+
+    # ---- sustained loop (>= 2 s of back-to-back steps, clocks sampled throughout): the burst number above is 12 ms of work
+    sus_steps = int(max(args.steps, min(20000, args.sustained_s / max(ms / args.steps * 1e-3, 1e-5))))
+    sampler2 = ClockSampler(local_rank)
+    sync_all()
+    if rank == 0:
+        sampler2.start()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    for _ in range(sus_steps):
+        step(wav, z1, z2)
+    u1.record()
+    sync_all()
+    clocks_sus = sampler2.stop() if rank == 0 else None
+    sus_ms = u0.elapsed_time(u1) / sus_steps
 
     # ---- e2e: HOST buffers (pinned), through the public API.  Per step, inside the timed region: the frontend reads the
     # waveforms straight from pinned host memory (crop-first: only the cropped spans cross PCIe), the embeddings are
@@ -426,10 +509,21 @@ def run_ours(args):
     d2h = 4
 
     # ---- reduce over ranks (max time)
-    tt = torch.tensor([ms, e2e_s, corr_ms.value, grad_ms.value, fe_ms, loss_ms, stats_ms.value], dtype=torch.float64, device=dev)
+    base = [ms, e2e_s, corr_ms.value, grad_ms.value, fe_ms, loss_ms, stats_ms.value, fe_full_ms, sus_ms]
+    tt = torch.tensor(base + [v for row in sweep for v in row[1:4]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms, e2e_s, corr, grad, fe_ms, loss_ms, st_ms = (float(v) for v in tt.cpu())
+    vals = [float(v) for v in tt.cpu()]
+    ms, e2e_s, corr, grad, fe_ms, loss_ms, st_ms, fe_full_ms, sus_ms = vals[:9]
+    for k, row in enumerate(sweep):
+        row[1:4] = vals[9 + 3 * k: 12 + 3 * k]
+    # every rank must have arrived at the same global loss (multi-GPU: a cheap invariant of the exchange; single GPU: trivially true)
+    lv = torch.tensor([loss_val] + [row[4] for row in sweep] + [-loss_val] + [-row[4] for row in sweep], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(lv, op=dist.ReduceOp.MAX)
+    lv = [float(v) for v in lv.cpu()]
+    nl = 1 + len(sweep)
+    loss_spread = max(abs(lv[k] + lv[nl + k]) / max(abs(lv[k]), 1e-30) for k in range(nl))      # (max - min) / max over ranks
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -439,7 +533,22 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = B * world / (ms_per_step * 1e-3)
     e2e_value = B * world * e2e_steps / e2e_s
-    flops = 6.0 * B * D * D                                   # algorithmic FLOPs of one loss term, per GPU
+    if world > 1 and loss_spread > 1e-6:
+        raise RuntimeError(f"ranks disagree on the global loss (relative spread {loss_spread:.2e}): the multi-GPU exchange is broken")
+    flops = 6.0 * B * D * D                                   # algorithmic FLOPs of one loss term, per GPU = 6 N_g D^2 / R
+    sweep_out = []
+    for d_s, call_ms, kern_ms, stat_ms_s, lo_s in sweep:
+        fl = 6.0 * 128 * d_s * d_s                             # per GPU; the global batch is 128 x world rows
+        ach = fl / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
+        sweep_out.append({
+            "D": d_s, "rows_per_gpu": 128, "global_rows": 128 * world, "ms": call_ms, "clips_per_s": 128 * world / (call_ms * 1e-3), "loss_value": lo_s,
+            "roofline": {"bound": "tensor", "kernel": "bt_fused_ts_kernel (one launch: S -> loss, P -> gradients, batch-norm backward)" if world == 1
+                         else "bt_umma_kernel (CORR + GRAD launches of the row-block step)",
+                         "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tf_burst"],
+                         "traffic": _traffic(f"fused_dram_bytes_n128_d{d_s}") if world == 1 else None,
+                         "algorithmic_flops": fl, "algorithmic_bytes": 6.0 * 128 * d_s * 2, "kernel_ms": kern_ms, "stats_ms": stat_ms_s,
+                         "frac_whole_call": fl / (call_ms * 1e-3) / 1e12 / peaks["tf_burst"],
+                         "executed_flops": (8.0 if world == 1 else 6.0) * 128 * d_s * d_s}})
     tc_ms = corr + grad
     achieved = flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     fe_bytes = B * (64896 + 49152 + 49152 + 24576)            # mode C algorithmic bytes per clip
@@ -455,9 +564,21 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": "bt_umma_kernel (CORR + GRAD launches)", "achieved": achieved, "peak": peaks["tf_burst"],
                      "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"], "traffic": _traffic(),
                      "algorithmic_flops_per_step": flops, "corr_ms": corr, "grad_ms": grad, "stats_ms": st_ms, "loss_fwd_bwd_ms": loss_ms,
-                     "measured": "CUDA events around the CORR and GRAD launches on the launching stream, loss-only pass of the same bench run",
+                     "measured": "CUDA events around the CORR and GRAD launches on the launching stream, loss-only pass of the same bench run, summed per step",
+                     "launch_groups_per_step": calls_per_step,
                      "frac_of_sustained_peak": achieved / peaks["tf_sustained"],
                      "peak_source": peaks["source"] + " (bf16_tflops burst figure: the launches are timed alone, in short bursts at boost clocks)"},
+        "loss_sweep": {"workload": "BASELINE config 3: Barlow Twins loss fwd+bwd, 128 rows per GPU (global batch 128 x n_gpus), bf16 in, "
+                                   "every iteration timed alone with CUDA events after an L2 flush; ms = median whole call (statistics + tensor-core "
+                                   "launches + autograd glue), max over ranks",
+                       "iters": args.sweep_iters, "points": sweep_out},
+        "sustained": {"steps": sus_steps, "ms_per_step": sus_ms, "value": B * world / (sus_ms * 1e-3), "clocks": clocks_sus,
+                      "note": "same step, back to back for >= %.1f s" % args.sustained_s},
+        "loss_spread_over_ranks": loss_spread,
+        "frontend_full": {"mode": "F (full log-mel emitted + two views)", "ms_per_step": fe_full_ms, "clips_per_s": B / (fe_full_ms * 1e-3),
+                          "algorithmic_bytes_per_step": B * 1019136, "achieved_gbs": B * 1019136 / (fe_full_ms * 1e-3) / 1e9,
+                          "hbm_frac": B * 1019136 / (fe_full_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                          "algorithmic_fp32_tflops": B * 29.6e6 / (fe_full_ms * 1e-3) / 1e12, "fp32_peak_tflops": 74.4},
         "frontend": {"ms_per_step": fe_ms, "clips_per_s": B / (fe_ms * 1e-3), "algorithmic_bytes_per_step": fe_bytes,
                      "achieved_gbs": fe_bytes / (fe_ms * 1e-3) / 1e9, "hbm_frac": fe_bytes / (fe_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                      "algorithmic_fp32_tflops": B * 2.84e6 / (fe_ms * 1e-3) / 1e12, "fp32_peak_tflops": 74.4,
@@ -474,20 +595,23 @@ def run_ours(args):
 
 
 def cpu_baseline(args):
+    """The CPU port of the reference path on the host cores, FULL workload (no sampling), plus the variants BASELINE.md section 4 lists."""
     import torch
     from oracle import torch_port as P
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B, D, L = args.batch, args.dim, int(args.clip_seconds * 16000)
-    sample_clips = max(cores, min(B, cores * args.ref_clips_per_worker))
-    fe_rate = P.time_frontend(sample_clips, L, cores)
-    rows = min(B, args.ref_loss_rows)
-    loss_s = P.time_loss(rows, D)
-    step_s = B / fe_rate + loss_s * (B / rows)
+    fe_rate = P.time_frontend(B, L, cores)
+    loss_s = P.time_loss(B, D)
+    step_s = B / fe_rate + loss_s
+    batched = P.time_frontend_batched(min(B, 128), L)
+    sweep = {str(d): P.time_loss(128, d) for d in (2048, 4096, 8192)}
     return {"value": B / step_s, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"frontend: {sample_clips} of {B} clips over {cores} single-threaded worker processes; loss fwd+bwd: {rows} of {B} rows at D={D}, "
-                      f"fp32, {cores} threads, scaled linearly in rows",
-            "frontend_clips_per_s": fe_rate, "loss_fwd_bwd_s": loss_s}
+            "sample": f"full workload, one pass: frontend on all {B} clips over {cores} single-threaded worker processes (the reference's DataLoader model); "
+                      f"loss fwd+bwd on all {B} rows at D={D}, fp32, {cores} threads",
+            "frontend_clips_per_s": fe_rate, "loss_fwd_bwd_s": loss_s,
+            "frontend_batched_clips_per_s": batched, "frontend_batched_note": f"single process, one batched MelSpectrogram call on {min(B, 128)} clips + per-sample views, {cores} intra-op threads",
+            "loss_fwd_bwd_s_n128": sweep, "host": P.host_description()}
 
 
 def main():
@@ -500,8 +624,9 @@ def main():
     ap.add_argument("--dim", type=int, default=8192, help="projector_out_dim")
     ap.add_argument("--clip-seconds", type=float, default=10.0)
     ap.add_argument("--e2e-steps", type=int, default=20)
-    ap.add_argument("--ref-clips-per-worker", type=int, default=32)
-    ap.add_argument("--ref-loss-rows", type=int, default=256)
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="reference arm: wall-clock budget of the whole K + W step run")
+    ap.add_argument("--sweep-iters", type=int, default=30, help="timed iterations per point of the N = 128 loss sweep (BASELINE config 3)")
+    ap.add_argument("--sustained-s", type=float, default=2.5, help="length of the sustained-clock loop reported beside the burst number")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -470,6 +470,39 @@ def bt_loss_forward_backward(z1: np.ndarray, z2: np.ndarray, alpha=1.0, lmbda=0.
     return loss, bn_bwd(gh1, h1, r1), bn_bwd(gh2, h2, r2), c
 
 
+def bt_loss_forward_backward_blocked(z1: np.ndarray, z2: np.ndarray, alpha=1.0, lmbda=0.005, hsic=False, eps=1e-5,
+                                     block: int = 1024, dtype=np.float64):
+    """Same closed form as bt_loss_forward_backward (utils/loss.py:15-30 + its autograd graph), evaluated one
+    row block of C at a time so that D = 8192 never holds a D x D float64 matrix.  Returns (loss, dz1, dz2)."""
+    z1 = z1.astype(dtype)
+    z2 = z2.astype(dtype)
+    n, d = z1.shape
+    h1, _, _, r1 = batchnorm_train(z1, eps)
+    h2, _, _, r2 = batchnorm_train(z2, eps)
+    shift = 1.0 if hsic else 0.0
+    on = 0.0
+    off = 0.0
+    gh1 = np.empty_like(h1)
+    gh2 = np.zeros_like(h2)
+    for s in range(0, d, block):
+        e = min(s + block, d)
+        c = h1[:, s:e].T @ h2 / n                      # rows s..e of C
+        idx = np.arange(s, e)
+        dg = c[idx - s, idx].copy()
+        on += ((dg - 1.0) ** 2).sum()
+        cs = c + shift
+        off += (cs ** 2).sum() - ((dg + shift) ** 2).sum()
+        g = 2.0 * lmbda * cs
+        g[idx - s, idx] = 2.0 * alpha * (dg - 1.0)
+        gh1[:, s:e] = h2 @ g.T / n
+        gh2 += h1[:, s:e] @ g / n
+
+    def bn_bwd(gh, h, r):
+        return (gh - gh.mean(axis=0) - h * (gh * h).mean(axis=0)) * r
+
+    return alpha * on + lmbda * off, bn_bwd(gh1, h1, r1), bn_bwd(gh2, h2, r2)
+
+
 def bn_running_update(running_mean, running_var, z, momentum=0.1):
     """BatchNorm1d running-stat update (unbiased variance), applied z1 then z2: utils/loss.py:17."""
     n = z.shape[0]

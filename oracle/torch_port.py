@@ -155,3 +155,41 @@ def time_loss(n: int, d: int, repeats: int = 1) -> float:
         z1.grad = None
         z2.grad = None
     return best
+
+
+def time_frontend_batched(n_clips: int, n_samples: int, norm_stats=(-0.8294, 4.6230)) -> float:
+    """Clips/s of the single-process variant: ONE batched torchaudio MelSpectrogram call over
+    the whole (B, L) batch with all intra-op threads, then the reference's per-sample crop / z-score / two-view loop."""
+    import time
+    np.random.seed(2000)
+    random.seed(2000)
+    g = torch.Generator().manual_seed(2000)
+    wav = torch.clamp(0.1 * torch.randn(n_clips, n_samples, generator=g), -1, 1)
+    mel = make_melspec()
+    tfm = PortPairTransform()
+    t0 = time.perf_counter()
+    lms = log_mel(mel, wav)
+    for b in range(n_clips):
+        clip_lms_path(lms[b], norm_stats, tfm)
+    return n_clips / (time.perf_counter() - t0)
+
+
+def host_description() -> dict:
+    """CPU model string, core / thread counts and library versions (printed beside every CPU number)."""
+    import os
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    try:
+        import torchaudio
+        ta = torchaudio.__version__
+    except Exception:
+        ta = "unavailable"
+    return {"cpu_model": model, "os_cpu_count": os.cpu_count(), "torch_num_threads": torch.get_num_threads(),
+            "torch": torch.__version__, "torchaudio": ta}

@@ -108,6 +108,9 @@ template <> __device__ __forceinline__ void load8<float>(const float* p, float (
 }
 template <typename T> struct NeedsRound { static constexpr bool value = true; };
 template <> struct NeedsRound<__nv_bfloat16> { static constexpr bool value = false; };     // already bf16: rounding is the identity
+template <> struct NeedsRound<__half> { static constexpr bool value = false; };            // fp16 embeddings feed the tensor cores as fp16 (kind::f16, no re-rounding)
+// the value the tensor cores see for an input element: fp32 inputs are rounded to bf16, 16-bit inputs are used as they are
+template <typename T> __device__ __forceinline__ float in_round(float x) { return NeedsRound<T>::value ? bf16_round(x) : x; }
 
 constexpr int kStatVec = 4;                       // statistics kernel: 4 columns per thread (8-byte loads keep it at ~50 registers, 5 blocks / SM)
 constexpr int kStatCols = 32 * kStatVec;          // 128 columns per block
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(kColThreads) bt_colstat_kernel(const T* __rest
             for (int k = 0; k < 5; ++k) t[k] += __ldcg(partials + ((size_t)sp * 5 + k) * D + gc);
         const float invN = 1.0f / (float)N;
         const float2 f1 = Ld2<T>::ld(z1 + (gc & ~1)), f2 = Ld2<T>::ld(z2 + (gc & ~1));
-        const float sh1 = bf16_round((gc & 1) ? f1.y : f1.x), sh2 = bf16_round((gc & 1) ? f2.y : f2.x);
+        const float sh1 = in_round<T>((gc & 1) ? f1.y : f1.x), sh2 = in_round<T>((gc & 1) ? f2.y : f2.x);
         const float m1 = t[0] * invN, m2 = t[2] * invN;
         const float var1 = fmaxf(t[1] * invN - m1 * m1, 0.f), var2 = fmaxf(t[3] * invN - m2 * m2, 0.f);
         const float cov = t[4] * invN - m1 * m2;
@@ -290,13 +293,105 @@ __global__ void __launch_bounds__(kColThreads) bt_normalize_kernel(const T* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// 1s. small batches (N <= 128, the one-launch objective): statistics AND standardisation in ONE pass.  A block owns 64 columns,
+//     keeps its N x 64 slice of both views in registers (thread = row group x column pair, <= 16 rows each), reduces the shifted
+//     sums through shared memory, and writes the fp16 standardised embeddings from the registers: z is read once, no partial-sum
+//     round trip, no arrival counters.  The on-diagonal loss leaves as one float per block (summed by the consumer), and block 0
+//     clears the accumulators of the tensor-core kernel, so the call needs no memset either.
+// ------------------------------------------------------------------------------------------
+constexpr int kSmallCols = 64;
+template <typename T>
+__global__ void __launch_bounds__(kColThreads) bt_stat_norm_small_kernel(const T* __restrict__ z1, const T* __restrict__ z2, int N, int D, float eps,
+                                                                         float momentum, float* __restrict__ stats, float* __restrict__ running_mean,
+                                                                         float* __restrict__ running_var, __half* __restrict__ zh1,
+                                                                         __half* __restrict__ zh2, float* __restrict__ ondiag_part,
+                                                                         double* __restrict__ loss_acc, unsigned int* __restrict__ done_counter) {
+    __shared__ float red[kRowGroups][10][32];
+    __shared__ float colstat[4][kSmallCols];
+    __shared__ float on_red[2];
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int col = blockIdx.x * kSmallCols + lane * 2;           // D is a multiple of 64: always in range
+    if (blockIdx.x == 0 && threadIdx.x == 0) { loss_acc[0] = 0.0; loss_acc[1] = 0.0; *done_counter = 0u; }
+    const float2 k1 = Ld2<T>::ld(z1 + col), k2 = Ld2<T>::ld(z2 + col);
+    const float sh1x = in_round<T>(k1.x), sh1y = in_round<T>(k1.y), sh2x = in_round<T>(k2.x), sh2y = in_round<T>(k2.y);
+    float va[16][2], vb[16][2];
+    float acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int n = rg + kRowGroups * k;
+        float2 a = make_float2(sh1x, sh1y), b = make_float2(sh2x, sh2y);
+        if (n < N) { a = Ld2<T>::ld(z1 + (size_t)n * D + col); b = Ld2<T>::ld(z2 + (size_t)n * D + col); }
+        va[k][0] = in_round<T>(a.x) - sh1x; va[k][1] = in_round<T>(a.y) - sh1y;       // shifted data (rows >= N contribute zero)
+        vb[k][0] = in_round<T>(b.x) - sh2x; vb[k][1] = in_round<T>(b.y) - sh2y;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            acc[c] += va[k][c]; acc[2 + c] = fmaf(va[k][c], va[k][c], acc[2 + c]);
+            acc[4 + c] += vb[k][c]; acc[6 + c] = fmaf(vb[k][c], vb[k][c], acc[6 + c]);
+            acc[8 + c] = fmaf(va[k][c], vb[k][c], acc[8 + c]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) red[rg][k][lane] = acc[k];
+    __syncthreads();
+    float on = 0.f;
+    if (threadIdx.x < kSmallCols) {
+        const int c = threadIdx.x & 1, ln = threadIdx.x >> 1, gc = blockIdx.x * kSmallCols + threadIdx.x;     // column ln * 2 + c
+        float t[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int g = 0; g < kRowGroups; ++g)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) t[k] += red[g][2 * k + c][ln];
+        const float invN = 1.0f / (float)N;
+        const float2 f1 = Ld2<T>::ld(z1 + (gc & ~1)), f2 = Ld2<T>::ld(z2 + (gc & ~1));
+        const float sh1 = in_round<T>(c ? f1.y : f1.x), sh2 = in_round<T>(c ? f2.y : f2.x);
+        const float m1 = t[0] * invN, m2 = t[2] * invN;
+        const float var1 = fmaxf(t[1] * invN - m1 * m1, 0.f), var2 = fmaxf(t[3] * invN - m2 * m2, 0.f);
+        const float cov = t[4] * invN - m1 * m2;
+        const float mu1 = sh1 + m1, mu2 = sh2 + m2;
+        const float r1 = rsqrtf(var1 + eps), r2 = rsqrtf(var2 + eps);
+        const float r1n = r1 * (1.5f - 0.5f * (var1 + eps) * r1 * r1), r2n = r2 * (1.5f - 0.5f * (var2 + eps) * r2 * r2);
+        const float cd = cov * r1n * r2n;
+        stats[S_MU1 * D + gc] = mu1; stats[S_R1 * D + gc] = r1n;
+        stats[S_MU2 * D + gc] = mu2; stats[S_R2 * D + gc] = r2n;
+        stats[S_CDIAG * D + gc] = cd;
+        colstat[0][threadIdx.x] = m1; colstat[1][threadIdx.x] = r1n; colstat[2][threadIdx.x] = m2; colstat[3][threadIdx.x] = r2n;
+        on = (cd - 1.0f) * (cd - 1.0f);
+        if (running_mean != nullptr) {
+            const float unb = (N > 1) ? (float)N / (float)(N - 1) : 1.0f;
+            float rm = running_mean[gc], rv = running_var[gc];
+            rm = (1.f - momentum) * rm + momentum * mu1; rv = (1.f - momentum) * rv + momentum * var1 * unb;
+            rm = (1.f - momentum) * rm + momentum * mu2; rv = (1.f - momentum) * rv + momentum * var2 * unb;
+            running_mean[gc] = rm; running_var[gc] = rv;
+        }
+        on = warp_sum(on);
+        if (lane == 0) on_red[threadIdx.x >> 5] = on;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) ondiag_part[blockIdx.x] = on_red[0] + on_red[1];
+    // standardise from the registers (the values are already shifted: subtract the shifted mean)
+    const float m1x = colstat[0][lane * 2], m1y = colstat[0][lane * 2 + 1], r1x = colstat[1][lane * 2], r1y = colstat[1][lane * 2 + 1];
+    const float m2x = colstat[2][lane * 2], m2y = colstat[2][lane * 2 + 1], r2x = colstat[3][lane * 2], r2y = colstat[3][lane * 2 + 1];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int n = rg + kRowGroups * k;
+        if (n < N) {
+            Ld2<__half>::st(zh1 + (size_t)n * D + col, (va[k][0] - m1x) * r1x, (va[k][1] - m1y) * r1y);
+            Ld2<__half>::st(zh2 + (size_t)n * D + col, (vb[k][0] - m2x) * r2x, (vb[k][1] - m2y) * r2y);
+        }
+    }
+}
+
 // row sums of the standardised embeddings (HSIC only): R[n] = sum_j zh[n, j]
-__global__ void __launch_bounds__(256) bt_rowsum_kernel(const __nv_bfloat16* __restrict__ z, int N, int D, const float* __restrict__ mu,
+template <typename T16>
+__global__ void __launch_bounds__(256) bt_rowsum_kernel(const T16* __restrict__ z, int N, int D, const float* __restrict__ mu,
                                                         const float* __restrict__ r, float* __restrict__ out) {
     __shared__ float red[8];
     const int n = blockIdx.x;
     float acc = 0.f;
-    for (int c = threadIdx.x; c < D; c += blockDim.x) acc += (__bfloat162float(z[(size_t)n * D + c]) - mu[c]) * r[c];
+    for (int c = threadIdx.x; c < D; c += blockDim.x) acc += ((float)z[(size_t)n * D + c] - mu[c]) * r[c];
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
@@ -359,8 +454,8 @@ __global__ void __launch_bounds__(256) bt_stat_pack_kernel(const T* __restrict__
         pack[(size_t)k * D + c] = t;
     }
     const float2 a = Ld2<T>::ld(z1 + (c & ~1)), b = Ld2<T>::ld(z2 + (c & ~1));
-    pack[(size_t)5 * D + c] = bf16_round((c & 1) ? a.y : a.x);
-    pack[(size_t)6 * D + c] = bf16_round((c & 1) ? b.y : b.x);
+    pack[(size_t)5 * D + c] = in_round<T>((c & 1) ? a.y : a.x);
+    pack[(size_t)6 * D + c] = in_round<T>((c & 1) ? b.y : b.x);
 }
 
 // packs: [world][7][D].  Combines the per-rank shifted sums in double (exact re-centring), writes the statistics arrays, the
@@ -433,9 +528,9 @@ __global__ void __launch_bounds__(kColThreads) bt_normalize_global_kernel(const 
         for (int n = n0 + rg; n < n1; n += kRowGroups) {
             const size_t o = (size_t)n * D + col;
             const float2 a2 = Ld2<T>::ld(z1 + o), b2 = Ld2<T>::ld(z2 + o);
-            const float h0 = (bf16_round(a2.x) - m1[0]) * q1r[0], h1 = (bf16_round(a2.y) - m1[1]) * q1r[1];
+            const float h0 = (in_round<T>(a2.x) - m1[0]) * q1r[0], h1 = (in_round<T>(a2.y) - m1[1]) * q1r[1];
             Ld2<__half>::st(zh1 + o, h0, h1);
-            Ld2<__half>::st(zh2 + o, (bf16_round(b2.x) - m2[0]) * q2r[0], (bf16_round(b2.y) - m2[1]) * q2r[1]);
+            Ld2<__half>::st(zh2 + o, (in_round<T>(b2.x) - m2[0]) * q2r[0], (in_round<T>(b2.y) - m2[1]) * q2r[1]);
             // [dimension owner q][local row][Dr]: the slice every other rank needs as the A operand of its CORR tiles, contiguous
             if (zh1_blk != nullptr) Ld2<__half>::st(zh1_blk + ((size_t)(col / dr) * n_local + n) * dr + (col % dr), h0, h1);
         }
@@ -529,7 +624,7 @@ struct UmmaParams {
     double* loss_acc;
     // GRAD
     int io_dtype;                      // abt_dtype of dz
-    int zfmt;                          // format of PassCfg::z_self / z_other: 0 raw bf16, 1 standardised fp16
+    int zfmt;                          // format of PassCfg::z_self / z_other: 0 raw bf16, 1 standardised fp16, 2 raw fp16
     const float* stats;                // StatSlot arrays
     const float* rs1; const float* rs2;   // HSIC: row sums of zh1 / zh2 over all dimensions
     float alpha, lambda, grad_scale;
@@ -593,8 +688,10 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&acc)[32], const Umma
             const int t = h * 16 + u;
             if (t < n_valid) {
                 const size_t n = (size_t)(n_base + t);
-                const float zhs = p.zfmt ? __half2float(__ushort_as_half(zs_raw[u])) : (__uint_as_float((uint32_t)zs_raw[u] << 16) - mu_s) * r_s;
-                const float zho = p.zfmt ? __half2float(__ushort_as_half(zo_raw[u])) : (__uint_as_float((uint32_t)zo_raw[u] << 16) - mu_o) * r_o;
+                float zhs, zho;
+                if (p.zfmt == 1) { zhs = __half2float(__ushort_as_half(zs_raw[u])); zho = __half2float(__ushort_as_half(zo_raw[u])); }
+                else if (p.zfmt == 2) { zhs = (__half2float(__ushort_as_half(zs_raw[u])) - mu_s) * r_s; zho = (__half2float(__ushort_as_half(zo_raw[u])) - mu_o) * r_o; }
+                else { zhs = (__uint_as_float((uint32_t)zs_raw[u] << 16) - mu_s) * r_s; zho = (__uint_as_float((uint32_t)zo_raw[u] << 16) - mu_o) * r_o; }
                 float g = fmaf(hs, __uint_as_float(acc[t]), gd * zho);
                 if (p.hsic) g = fmaf(hs, rsv[u] - zho, g);
                 store_out<T>(dz + n * pc.ld_dz, (g - zhs * b) * rg);
@@ -942,6 +1039,10 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
 }
 
+}  // namespace abt
+#include "bt_fused.cuh"
+namespace abt {
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -996,6 +1097,9 @@ struct WsLayout {
     size_t zero_bytes;   // misc + acc: cleared at the start of every call
 };
 
+static int g_fused = 2;         // single-GPU, N <= 128: the one-launch kernels of bt_fused.cuh; 2 = operands in TMEM, 1 = in shared memory, 0 = off (abt_debug_set key 9)
+static bool fused_applies(int N, bool rows_mode, int world) { return g_fused != 0 && world == 0 && !rows_mode && N <= FB; }
+
 static WsLayout ws_layout(int N, int D, int rows, int dtype, bool two_c, int world = 0) {
     WsLayout L{};
     size_t off = 0;
@@ -1010,27 +1114,28 @@ static WsLayout ws_layout(int N, int D, int rows, int dtype, bool two_c, int wor
     L.pack_all = off; if (world > 0) off = align_up(off + sizeof(float) * 7 * (size_t)D * world, 256);
     L.rs1 = off; off = align_up(off + sizeof(float) * (size_t)N, 256);
     L.rs2 = off; off = align_up(off + sizeof(float) * (size_t)N, 256);
-    L.zb1 = off; if (dtype != ABT_DTYPE_BF16) off = align_up(off + 2 * (size_t)N * D, 256);
-    L.zb2 = off; if (dtype != ABT_DTYPE_BF16) off = align_up(off + 2 * (size_t)N * D, 256);
+    L.zb1 = off; if (dtype == ABT_DTYPE_F32) off = align_up(off + 2 * (size_t)N * D, 256);       // bf16 copies of fp32 embeddings
+    L.zb2 = off; if (dtype == ABT_DTYPE_F32) off = align_up(off + 2 * (size_t)N * D, 256);
     L.zh1 = off; off = align_up(off + 2 * (size_t)N * D, 256);
     L.zh2 = off; off = align_up(off + 2 * (size_t)N * D, 256);
     L.zs1 = off; if (world > 0) off = align_up(off + 2 * (size_t)N * rows, 256);          // (N_g, Dr): view-1 columns of this rank's dimensions, all samples
     L.zh1_blk = off; if (world > 0) off = align_up(off + 2 * (size_t)(N / world) * D, 256);  // (world, n_local, Dr): send buffer of that exchange
-    L.c1 = off; off = align_up(off + 2 * (size_t)rows * D, 256);
+    L.c1 = off; if (!fused_applies(N, two_c, world)) off = align_up(off + 2 * (size_t)rows * D, 256);     // the fused kernel keeps C on chip
     L.c2 = off; if (two_c) off = align_up(off + 2 * (size_t)rows * D, 256);
     L.total = off;
     return L;
 }
 
-static int g_num_sms = 0;
 static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+    static int cached[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (cached[dev] <= 0) cached[dev] = 148;
     }
-    return g_num_sms;
+    return cached[dev];
 }
 
 // ABT_DEBUG_SYNC=1: synchronise after every stage of a loss evaluation and report which one failed
@@ -1047,13 +1152,18 @@ static int g_cta_group = 2;     // 2 = CTA-pair kernel (default), 1 = single-CTA
 static bool g_tail_split = true; // GRAD: split the last partial wave into half-width items (abt_debug_set key 8)
 static int g_dist_xchg = -1;    // multi-GPU exchange schedule: -1 = auto (4 ranks and more), 0 = never, 1 = whenever possible (abt_debug_set key 7)
 
+// cudaFuncSetAttribute is per device: keep one flag per device ordinal
 static int ensure_umma_attr() {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(bt_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
         if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     return 0;
 }
@@ -1125,11 +1235,13 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
     __half* C2 = reinterpret_cast<__half*>(ws + L.c2);
     __half* zh1 = reinterpret_cast<__half*>(ws + L.zh1);
     __half* zh2 = reinterpret_cast<__half*>(ws + L.zh2);
-    const bool is_bf16 = (a.dtype == ABT_DTYPE_BF16);
-    __nv_bfloat16* zb1 = is_bf16 ? nullptr : reinterpret_cast<__nv_bfloat16*>(ws + L.zb1);
-    __nv_bfloat16* zb2 = is_bf16 ? nullptr : reinterpret_cast<__nv_bfloat16*>(ws + L.zb2);
-    const __nv_bfloat16* zq1 = is_bf16 ? static_cast<const __nv_bfloat16*>(a.z1) : zb1;
-    const __nv_bfloat16* zq2 = is_bf16 ? static_cast<const __nv_bfloat16*>(a.z2) : zb2;
+    // 16-bit embeddings feed the tensor cores as they are (bf16 or fp16, kind::f16 takes both); fp32 ones get a bf16 copy
+    const bool is_16 = (a.dtype != ABT_DTYPE_F32);
+    const bool raw_f16 = (a.dtype == ABT_DTYPE_F16) && !a.zh_mode;
+    __nv_bfloat16* zb1 = is_16 ? nullptr : reinterpret_cast<__nv_bfloat16*>(ws + L.zb1);
+    __nv_bfloat16* zb2 = is_16 ? nullptr : reinterpret_cast<__nv_bfloat16*>(ws + L.zb2);
+    const void* zq1 = is_16 ? a.z1 : static_cast<const void*>(zb1);
+    const void* zq2 = is_16 ? a.z2 : static_cast<const void*>(zb2);
     const int need = a.need & 3;
     const int col_blocks = (D + kColsPerBlock - 1) / kColsPerBlock;
     if (int rc = ensure_umma_attr()) return rc;
@@ -1141,6 +1253,46 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
     const int pmask = a.xchg ? (a.phase & 7) : (a.phase == 0 ? 7 : (a.phase == 1 ? 3 : 4));
     const bool front = (pmask & 1) != 0;
     __half* ZS1 = reinterpret_cast<__half*>(ws + L.zs1);
+    if (fused_applies(N, a.rows_mode, a.zh_mode ? 1 : 0) && need != 0) {
+        // ---- small batch: statistics + standardisation in one pass, then ONE tensor-core launch
+        //      (S tiles -> loss + fp16 P on chip -> gradient accumulators in TMEM -> batch-norm backward); no memset, no D x D matrix
+        float* ondiag_part = partials;
+        bt_stat_norm_small_kernel<T><<<D / kSmallCols, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, a.eps,
+                                                                                 a.momentum, stats, a.running_mean, a.running_var, zh1, zh2, ondiag_part,
+                                                                                 loss_acc, reinterpret_cast<unsigned int*>(ws + L.misc + 64));
+        count_launch();
+        if (int rc = debug_sync(stream, "statistics")) return rc;
+        if (a.hsic) {
+            bt_rowsum_zh_kernel<<<N, 256, 0, stream>>>(zh1, N, D, rs1);
+            bt_rowsum_zh_kernel<<<N, 256, 0, stream>>>(zh2, N, D, rs2);
+            count_launch(2);
+        }
+        if (timed) { cudaEventRecord(tev[1], stream); cudaEventRecord(tev[2], stream); }
+        FusedParams p{};
+        p.D = D; p.N = N; p.n_pad = (N + 15) / 16 * 16;
+        p.n_blocks = (D + FB - 1) / FB;
+        p.pass_count = need == 3 ? 2 : 1;
+        p.pass_side[0] = (need & 1) ? 0 : 1; p.pass_side[1] = 1;
+        p.hsic = a.hsic; p.io_dtype = a.dtype;
+        p.alpha = a.alpha; p.lambda = a.lambda; p.grad_scale = a.grad_scale;
+        p.stats = stats; p.rs1 = rs1; p.rs2 = rs2;
+        p.dz1 = a.dz1; p.dz2 = a.dz2;
+        p.loss_acc = loss_acc; p.done_counter = reinterpret_cast<unsigned int*>(ws + L.misc + 64); p.loss_out = a.loss_out;
+        p.ondiag_part = ondiag_part; p.n_parts = D / kSmallCols;
+        CUtensorMap mz1, mz2;
+        if (int rc = make_map_16(&mz1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh1, N, D, 64, p.n_pad)) return rc;
+        if (int rc = make_map_16(&mz2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh2, N, D, 64, p.n_pad)) return rc;
+        const int units = p.n_blocks * p.pass_count;
+        const int grid = units < num_sms() ? units : num_sms();
+        if (g_fused == 1) bt_fused_kernel<<<grid, kNumThreads, kFSmemBytes, stream>>>(mz1, mz2, p);
+        else bt_fused_ts_kernel<<<grid, kTThreads, kTSmemBytes, stream>>>(mz1, mz2, p);
+        count_launch();
+        if (int rc = debug_sync(stream, "FUSED")) return rc;
+        if (timed) { cudaEventRecord(tev[3], stream); ++g_timing.count; }
+        cudaError_t fe = cudaGetLastError();
+        if (fe != cudaSuccess) return set_error(ABT_ERR_CUDA, "bt_fused_kernel launch: %s", cudaGetErrorString(fe));
+        return 0;
+    }
     if (front) cudaMemsetAsync(ws + L.misc, 0, L.zero_bytes, stream);     // loss partial sums + row / column accumulators
     // ---- statistics
     if (!front) {
@@ -1162,8 +1314,13 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         count_launch(2);
         if (int rc = debug_sync(stream, "statistics")) return rc;
         if (a.hsic && need != 0) {
-            bt_rowsum_kernel<<<N, 256, 0, stream>>>(zq1, N, D, stats + S_MU1 * D, stats + S_R1 * D, rs1);
-            bt_rowsum_kernel<<<N, 256, 0, stream>>>(zq2, N, D, stats + S_MU2 * D, stats + S_R2 * D, rs2);
+            if (raw_f16) {
+                bt_rowsum_kernel<__half><<<N, 256, 0, stream>>>(static_cast<const __half*>(zq1), N, D, stats + S_MU1 * D, stats + S_R1 * D, rs1);
+                bt_rowsum_kernel<__half><<<N, 256, 0, stream>>>(static_cast<const __half*>(zq2), N, D, stats + S_MU2 * D, stats + S_R2 * D, rs2);
+            } else {
+                bt_rowsum_kernel<__nv_bfloat16><<<N, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(zq1), N, D, stats + S_MU1 * D, stats + S_R1 * D, rs1);
+                bt_rowsum_kernel<__nv_bfloat16><<<N, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(zq2), N, D, stats + S_MU2 * D, stats + S_R2 * D, rs2);
+            }
             count_launch(2);
         }
     } else {
@@ -1187,14 +1344,14 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
     if (timed) cudaEventRecord(tev[1], stream);
     if (front) {
         CUtensorMap m1, m2;
-        const CUtensorMapDataType odt = a.zh_mode ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        const CUtensorMapDataType odt = (a.zh_mode || raw_f16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
         if (a.xchg) { if (int rc = make_map_16(&m1, odt, ZS1, N, RC, 64, 64)) return rc; }
         else if (int rc = make_map_16(&m1, odt, a.zh_mode ? a.z1 : zq1, N, D, 64, 64)) return rc;
         if (int rc = make_map_16(&m2, odt, a.zh_mode ? a.z2 : zq2, N, D, 64, 64)) return rc;
         UmmaParams p{};
         p.dc = g_desc;
         p.mode = 0; p.D = D; p.N = N;
-        p.bn = 256; p.ab_format = a.zh_mode ? 0 : 1;
+        p.bn = 256; p.ab_format = (a.zh_mode || raw_f16) ? 0 : 1;
         p.tiles_m = row_tiles; p.tiles_n = (D + p.bn - 1) / p.bn;
         p.kblocks = (N + BK - 1) / BK;
         p.split_from = 1 << 30;                                 // set below once the pass count is known
@@ -1262,9 +1419,9 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         p.hsic = a.hsic; p.write_c = 0;
         p.loss_acc = loss_acc;
         p.io_dtype = a.dtype; p.stats = stats; p.rs1 = rs1; p.rs2 = rs2;
-        p.zfmt = a.zh_mode ? 1 : 0;
-        const uint16_t* Z1 = static_cast<const uint16_t*>(a.zh_mode ? a.z1 : static_cast<const void*>(zq1));      // epilogue reads (16-bit elements)
-        const uint16_t* Z2 = static_cast<const uint16_t*>(a.zh_mode ? a.z2 : static_cast<const void*>(zq2));
+        p.zfmt = a.zh_mode ? 1 : (raw_f16 ? 2 : 0);
+        const uint16_t* Z1 = static_cast<const uint16_t*>(a.zh_mode ? a.z1 : zq1);      // epilogue reads (16-bit elements)
+        const uint16_t* Z2 = static_cast<const uint16_t*>(a.zh_mode ? a.z2 : zq2);
         p.alpha = a.alpha; p.lambda = a.lambda; p.grad_scale = a.grad_scale; p.loss_out = a.loss_out;
         PassCfg d1{}, d2{};
         d1.a_mn = 0; d1.row0 = R0; d1.row_end = R0 + RC; d1.side = 0; d1.dz = a.dz1; d1.ld_dz = a.ld_dz;
@@ -1361,6 +1518,7 @@ extern "C" int abt_debug_set(int key, int value) {
     if (key == 6) { g_cta_group = value == 1 ? 1 : 2; return 0; }
     if (key == 8) { g_tail_split = value != 0; return 0; }
     if (key == 7) { g_dist_xchg = value < 0 ? -1 : (value != 0 ? 1 : 0); return 0; }
+    if (key == 9) { g_fused = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }
     if (key < 0 || key >= 6) return set_error(ABT_ERR_ARG, "unknown debug key %d", key);
     *f[key] = value;
     return 0;

@@ -25,6 +25,11 @@ __all__ = ["BarlowTwinsLoss", "off_diagonal", "bt_loss_fwd_bwd"]
 
 _DTYPES = {torch.bfloat16: _lib.DTYPE_BF16, torch.float16: _lib.DTYPE_F16, torch.float32: _lib.DTYPE_F32}
 
+# fp16 embeddings (the reference's AMP mode is fp16 autocast + GradScaler, main.py:84,137): the library writes the gradients in
+# the input dtype during forward, BEFORE autograd hands over the loss scale, so small d loss / d z (< 6e-5) would be fp16
+# subnormals.  They are therefore stored pre-multiplied by a power of two and backward divides it back out of grad_output.
+_FP16_PRESCALE = 4096.0
+
 
 def off_diagonal(x: torch.Tensor) -> torch.Tensor:
     """Flattened view of the off-diagonal elements of a square matrix (reference: utils/utils.py:23-27)."""
@@ -101,16 +106,20 @@ class _BTLossFn(torch.autograd.Function):
         rv = bn.running_var if track else None
         if rm is not None and (rm.device != z1.device or rm.dtype != torch.float32):
             raise RuntimeError("BarlowTwinsLoss buffers must be fp32 on the embeddings' device (call .cuda() as main.py:422 does)")
+        if track and bn.momentum is None:
+            raise NotImplementedError("BatchNorm1d(momentum=None) (cumulative moving average) is not supported; the reference uses the default 0.1")
+        momentum = bn.momentum if bn.momentum is not None else 0.1
+        pre = _FP16_PRESCALE if z1.dtype == torch.float16 else 1.0
         from . import dist as _dist
         if _dist.is_active():
+            gs = module.grad_scale if module.grad_scale is not None else float(torch.distributed.get_world_size())
             loss, dz1, dz2 = _dist.bt_loss_fwd_bwd_global(z1.detach(), z2.detach(), cfg.alpha, cfg.lmbda, cfg.HSIC, eps=bn.eps,
-                                                          momentum=bn.momentum if bn.momentum is not None else 0.1,
-                                                          running_mean=rm, running_var=rv, need_dz1=need1, need_dz2=need2,
-                                                          grad_scale=module.grad_scale, overlap_hook=module.comm_overlap_hook)
+                                                          momentum=momentum, running_mean=rm, running_var=rv, need_dz1=need1, need_dz2=need2,
+                                                          grad_scale=gs * pre, overlap_hook=module.comm_overlap_hook)
         else:
-            loss, dz1, dz2 = bt_loss_fwd_bwd(z1.detach(), z2.detach(), cfg.alpha, cfg.lmbda, cfg.HSIC, eps=bn.eps,
-                                             momentum=bn.momentum if bn.momentum is not None else 0.1,
-                                             running_mean=rm, running_var=rv, need_dz1=need1, need_dz2=need2)
+            loss, dz1, dz2 = bt_loss_fwd_bwd(z1.detach(), z2.detach(), cfg.alpha, cfg.lmbda, cfg.HSIC, eps=bn.eps, momentum=momentum,
+                                             running_mean=rm, running_var=rv, need_dz1=need1, need_dz2=need2, grad_scale=pre)
+        ctx.prescale = pre
         if track:
             module._pending_batches += 2    # BatchNorm is applied to z1 and then to z2 (utils/loss.py:17); flushed lazily
         ctx.save_for_backward(dz1 if dz1 is not None else torch.empty(0, device=z1.device),
@@ -131,6 +140,8 @@ class _BTLossFn(torch.autograd.Function):
         ref = g1 if g1 is not None else g2
         if ref is not None:
             scale = grad_out.detach().to(torch.float32).contiguous()
+            if ctx.prescale != 1.0:
+                scale = scale / ctx.prescale
             with torch.cuda.device(ref.device):
                 _lib.check(_lib.load().abt_scale_inplace(g1.data_ptr() if g1 is not None else None, g2.data_ptr() if g2 is not None else None,
                                                          ref.numel(), _DTYPES[ref.dtype], scale.data_ptr(),
@@ -155,6 +166,8 @@ class BarlowTwinsLoss(nn.Module):
         # buffer when somebody looks at it (state_dict / explicit flush) instead of launching a kernel every step
         self._pending_batches = 0
         self.register_state_dict_pre_hook(lambda module, prefix, keep_vars: module.flush_counters())
+        # a checkpoint's counter replaces (not adds to) the steps taken before it was loaded
+        self.register_load_state_dict_pre_hook(lambda module, *a, **k: setattr(module, "_pending_batches", 0))
 
     def flush_counters(self) -> None:
         if self._pending_batches:
@@ -164,9 +177,9 @@ class BarlowTwinsLoss(nn.Module):
     def forward_loss(self, z1, z2):
         if z1.shape[-1] != self.cfg.projector_out_dim:
             raise ValueError(f"expected embeddings with {self.cfg.projector_out_dim} dims, got {z1.shape[-1]}")
-        if not self.bn.training:
-            raise NotImplementedError("eval-mode BatchNorm (running statistics) is not part of the accelerated path; "
-                                      "the reference never switches the loss module to eval")
+        if not self.bn.training and self.bn.track_running_stats:
+            raise NotImplementedError("eval-mode BatchNorm (normalising with the running statistics) is not part of the accelerated path; "
+                                      "the reference never switches the loss module to eval (main.py:84-139 trains only)")
         return _BTLossFn.apply(z1, z2, self)
 
     def forward(self, student_output, teacher_output, ngcrops_each=1):

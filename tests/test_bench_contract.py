@@ -13,17 +13,18 @@ def _run(*args):
 
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
-    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-clips-per-worker", "2", "--ref-loss-rows", "16")
+    r = _run("--impl", "reference", "--steps", "2", "--warmup", "1", "--batch", "16", "--dim", "256", "--clip-seconds", "1")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "two_view_clips_per_sec" and d["unit"] == "clips/s"
-    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0 and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["higher_is_better"] is True       # --steps / --warmup honoured
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert cb["host"]["cpu_model"] and cb["host"]["torch_num_threads"] >= 1 and cb["host"]["torchaudio"]
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
 

@@ -1,7 +1,12 @@
 """GPU parity of the Barlow Twins objective (through the C ABI) against the numpy oracle and the
 reference-generated golden fixtures.  Tolerances are those of BASELINE.json:north_star: loss and
 gradients within 1e-3 relative (gradients: Frobenius-norm relative error) for bf16 inputs with
-fp32 accumulation; the oracle consumes the same bf16-rounded values in float64."""
+fp32 accumulation; the oracle consumes the same bf16-rounded values in float64.
+
+16-bit outputs: a gradient written in bf16 carries the bf16 rounding quantum (~1.6e-3 Frobenius), which is larger than the
+tolerance itself.  Instead of widening the tolerance, the 16-bit tests (a) hold the SAME kernel with fp32 outputs to the true
+1e-3 against the oracle and (b) require the 16-bit output to be the correctly rounded fp32 one (`ROUND_TOL`: at most a few
+one-ulp flips, which only the float atomics of the N > 128 path can cause)."""
 import os
 import types
 
@@ -14,6 +19,23 @@ pytestmark = pytest.mark.gpu
 from oracle import abt_oracle as O  # noqa: E402
 
 TOL = 1e-3
+ROUND_TOL = 2e-4        # || out16 - round16(out32) || / || out32 ||: zero when deterministic, ~1e-5 with float-atomic reordering
+
+
+def _round_like(x, dtype):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dtype).float().numpy()
+
+
+def _check_16bit(z1, z2, dtype, r1, r2, rl, **kw):
+    """Parity of a 16-bit run: fp32-output run of the same kernels within TOL of the oracle, 16-bit outputs = its rounding."""
+    loss32, a1, a2, _ = _run(z1, z2, torch.float32, **kw)
+    loss16, b1, b2, _ = _run(z1, z2, dtype, **kw)
+    assert abs(loss32 - rl) <= TOL * abs(rl) and abs(loss16 - rl) <= TOL * abs(rl), (loss32, loss16, rl)
+    for a, b, r in ((a1, b1, r1), (a2, b2, r2)):
+        if a is None:
+            continue
+        assert _rel(a, r) < TOL, _rel(a, r)
+        assert _rel(b, _round_like(a, dtype).astype(np.float64)) < ROUND_TOL, _rel(b, _round_like(a, dtype).astype(np.float64))
 
 
 def _cfg(d, hsic=False, alpha=1.0, lmbda=0.005):
@@ -40,12 +62,36 @@ def _run(z1, z2, dtype, hsic=False, alpha=1.0, lmbda=0.005, need=(True, True)):
 @pytest.mark.parametrize("n,d", [(32, 64), (128, 256), (48, 320), (128, 2048), (256, 1024), (100, 512)])
 def test_bf16_matches_oracle(n, d):
     z1, z2 = O.synth_embeddings(n, d, seed=n + d)
-    loss, g1, g2, _ = _run(z1, z2, torch.bfloat16)
     rl, r1, r2, _ = O.bt_loss_forward_backward(z1, z2)
-    assert abs(loss - rl) <= TOL * abs(rl), (loss, rl)
-    # outputs are rounded to bf16 (gradients in the input dtype): allow the bf16 quantum on top
-    assert _rel(g1, r1) < TOL + 4e-3, _rel(g1, r1)
-    assert _rel(g2, r2) < TOL + 4e-3, _rel(g2, r2)
+    _check_16bit(z1, z2, torch.bfloat16, r1, r2, rl)
+
+
+@pytest.mark.parametrize("n,d,hsic", [(128, 2048, False), (64, 512, True), (16, 128, False), (100, 448, False), (8, 64, False)])
+def test_single_launch_kernel_matches_two_launch_path(n, d, hsic):
+    """N <= 128 runs the one-launch kernel (bt_fused.cuh); abt_debug_set(9, 0) routes the same inputs through CORR + GRAD.
+    Both must agree with the oracle, and with each other far inside the tolerance."""
+    from ssl_audio_b200 import _lib, loss as L
+    z1, z2 = O.synth_embeddings(n, d, seed=3 * n + d)
+    rl, r1, r2, _ = O.bt_loss_forward_backward(z1, z2, hsic=hsic)
+    lf, f1, f2, _ = _run(z1, z2, torch.float32, hsic=hsic)
+    try:
+        _lib.load().abt_debug_set(9, 0)
+        L._WS._buf.clear()                       # the two-launch path needs the D x D workspace
+        lt, t1, t2, _ = _run(z1, z2, torch.float32, hsic=hsic)
+    finally:
+        _lib.load().abt_debug_set(9, 2)
+        L._WS._buf.clear()
+    for loss, g1, g2 in ((lf, f1, f2), (lt, t1, t2)):
+        assert abs(loss - rl) <= TOL * abs(rl), (loss, rl)
+        assert _rel(g1, r1) < TOL and _rel(g2, r2) < TOL, (_rel(g1, r1), _rel(g2, r2))
+    assert _rel(f1, t1.astype(np.float64)) < 5e-4 and _rel(f2, t2.astype(np.float64)) < 5e-4
+
+
+def test_single_launch_kernel_is_deterministic():
+    z1, z2 = O.synth_embeddings(128, 1024, seed=21)
+    _, a1, a2, _ = _run(z1, z2, torch.bfloat16)
+    _, b1, b2, _ = _run(z1, z2, torch.bfloat16)
+    assert np.array_equal(a1, b1) and np.array_equal(a2, b2)
 
 
 @pytest.mark.parametrize("n,d,hsic", [(64, 256, False), (64, 256, True), (128, 1024, False)])
@@ -108,16 +154,37 @@ def test_byol_pairing_two_terms(golden_dir):
     assert _rel(t.grad.cpu().numpy(), g["byol_dteacher"].astype(np.float64)) < TOL
 
 
-def test_grad_output_scaling_and_fp16():
-    z1, z2 = O.synth_embeddings(64, 256, seed=9)
+@pytest.mark.parametrize("n,d", [(64, 256), (192, 512)])
+def test_fp16_embeddings_are_not_rerounded(n, d):
+    """fp16 inputs (the reference's AMP mode, main.py:84) feed the tensor cores as fp16: inputs with a full 11-bit mantissa."""
+    rng = np.random.default_rng(5)
+    z1 = rng.standard_normal((n, d)).astype(np.float16).astype(np.float32)
+    z2 = (0.6 * z1 + 0.8 * rng.standard_normal((n, d))).astype(np.float16).astype(np.float32)
+    assert not np.array_equal(z1, O.round_bf16(z1))
+    rl, r1, r2, _ = O.bt_loss_forward_backward(z1, z2)
+    loss, g1, g2, _ = _run(z1, z2, torch.float16)
+    assert abs(loss - rl) <= TOL * abs(rl)
+    # fp16 outputs: 11-bit mantissa, quantum ~2e-4
+    assert _rel(g1, r1) < TOL and _rel(g2, r2) < TOL, (_rel(g1, r1), _rel(g2, r2))
+
+
+@pytest.mark.parametrize("n,d", [(64, 256), (192, 512)])
+def test_grad_scaler_small_gradients_fp16(n, d):
+    """GradScaler: the loss scale arrives in backward, after the gradients were produced.  With lambda tiny the off-diagonal part of
+    d loss / d z is ~1e-7 -- far below fp16's smallest normal (6e-5) -- and must survive until the scale (65536) is applied."""
     import ssl_audio_b200 as S
+    rng = np.random.default_rng(9)
+    z1 = rng.standard_normal((n, d)).astype(np.float16).astype(np.float32)
+    z2 = (0.6 * z1 + 0.8 * rng.standard_normal((n, d))).astype(np.float16).astype(np.float32)
+    alpha, lmbda, scale = 1e-3, 5e-6, 65536.0
     t1 = torch.from_numpy(z1).cuda().half().requires_grad_(True)
     t2 = torch.from_numpy(z2).cuda().half().requires_grad_(True)
-    mod = S.BarlowTwinsLoss(_cfg(256), ncrops=2).cuda()
-    (mod.forward_loss(t1, t2) * 128.0).backward()     # GradScaler-style scaling
-    _, r1, r2, _ = O.bt_loss_forward_backward(z1, z2)
-    assert _rel(t1.grad.float().cpu().numpy() / 128.0, r1) < 5e-3
-    assert _rel(t2.grad.float().cpu().numpy() / 128.0, r2) < 5e-3
+    mod = S.BarlowTwinsLoss(_cfg(d, alpha=alpha, lmbda=lmbda), ncrops=2).cuda()
+    (mod.forward_loss(t1, t2) * scale).backward()
+    _, r1, r2, _ = O.bt_loss_forward_backward(z1, z2, alpha=alpha, lmbda=lmbda)
+    assert np.abs(r1).max() < 6.1e-5                      # every unscaled gradient is an fp16 subnormal
+    assert _rel(t1.grad.float().cpu().numpy() / scale, r1) < TOL
+    assert _rel(t2.grad.float().cpu().numpy() / scale, r2) < TOL
 
 
 def test_error_conventions():
@@ -133,78 +200,23 @@ def test_error_conventions():
         S.off_diagonal(torch.zeros(3, 4))
 
 
+@pytest.mark.parametrize("n,d", [(128, 4096), (128, 8192), (1024, 8192), (256, 4096)])
+def test_full_size_fp32_and_bf16_against_blocked_oracle(n, d):
+    """BASELINE config 3 (N = 128, D = 4096 / 8192) and the bench workload (N = 1024, D = 8192) at FULL size: loss and both complete
+    gradients within 1e-3 of the float64 oracle (evaluated one row block of C at a time), fp32 outputs; bf16 outputs = their rounding."""
+    z1, z2 = O.synth_embeddings(n, d, seed=n + d)
+    rl, r1, r2 = O.bt_loss_forward_backward_blocked(z1, z2)
+    _check_16bit(z1, z2, torch.bfloat16, r1, r2, rl)
+
+
 def test_full_size_properties_d8192():
-    """BASELINE config 3 at full size (N=128, D=8192): properties that need no O(D^2) oracle --
-    loss(z, z) has a vanishing on-diagonal term, the loss is symmetric in its arguments, gradients
-    are orthogonal to the batch-norm null space (column sums and column projections on zh vanish)."""
+    """Size-independent properties at N = 128, D = 8192: the loss is symmetric under swapping the views (and the gradients swap with
+    them), gradients are orthogonal to the batch-norm null space (column sums vanish)."""
     n, d = 128, 8192
     z1, z2 = O.synth_embeddings(n, d, seed=1)
-    loss12, g1, g2, _ = _run(z1, z2, torch.bfloat16)
-    loss21, h2, h1, _ = _run(z2, z1, torch.bfloat16)
+    loss12, g1, g2, _ = _run(z1, z2, torch.float32)
+    loss21, h2, h1, _ = _run(z2, z1, torch.float32)
     assert abs(loss12 - loss21) <= 1e-5 * abs(loss12)
-    assert _rel(g1, h1.astype(np.float64)) < 1e-2 and _rel(g2, h2.astype(np.float64)) < 1e-2
-    col_sum = np.abs(g1.astype(np.float64).sum(0)).max()
-    assert col_sum < 1e-2 * np.abs(g1).sum(0).max()
-    # spot-check 64 columns of dz1 against the closed form evaluated only for those columns
-    rl, r1, _, _ = O.bt_loss_forward_backward(z1[:, :], z2[:, :]) if False else (None, None, None, None)
-    h1z, _, _, rr1 = O.batchnorm_train(z1.astype(np.float64))
-    h2z, _, _, _ = O.batchnorm_train(z2.astype(np.float64))
-    cols = np.arange(0, d, d // 64)
-    c_rows = h1z[:, cols].T @ h2z / n                                   # (64, D) rows of C
-    G = 2 * 0.005 * c_rows
-    G[np.arange(len(cols)), cols] = 2 * (c_rows[np.arange(len(cols)), cols] - 1.0)
-    gh = h2z @ G.T / n                                                   # (N, 64)
-    hz = h1z[:, cols]
-    ref = (gh - gh.mean(0) - hz * (gh * hz).mean(0)) * rr1[cols]
-    assert _rel(g1[:, cols], ref) < TOL + 4e-3
-    # loss against a float64 evaluation that never forms more than a row block of C
-    on = 0.0
-    off = 0.0
-    for s in range(0, d, 1024):
-        blk = h1z[:, s:s + 1024].T @ h2z / n
-        idx = np.arange(s, min(s + 1024, d))
-        dg = blk[idx - s, idx]
-        on += ((dg - 1) ** 2).sum()
-        off += (blk ** 2).sum() - (dg ** 2).sum()
-    ref_loss = on + 0.005 * off
-    assert abs(loss12 - ref_loss) <= TOL * ref_loss, (loss12, ref_loss)
-
-
-def test_bench_size_properties_n1024_d8192():
-    """The bench workload (N = 1024 rows, D = 8192, bf16): same size-independent checks as above -- symmetry of the loss under swapping the
-    views, gradients in the batch-norm null space, 64 spot-checked gradient columns of BOTH views against the closed form, and the loss
-    against a float64 evaluation done row block by row block."""
-    n, d = 1024, 8192
-    z1, z2 = O.synth_embeddings(n, d, seed=2)
-    loss12, g1, g2, _ = _run(z1, z2, torch.bfloat16)
-    loss21, h2, h1, _ = _run(z2, z1, torch.bfloat16)
-    assert abs(loss12 - loss21) <= 1e-5 * abs(loss12)
-    assert _rel(g1, h1.astype(np.float64)) < 1e-2 and _rel(g2, h2.astype(np.float64)) < 1e-2
-    assert np.abs(g1.astype(np.float64).sum(0)).max() < 1e-2 * np.abs(g1).sum(0).max()
-    h1z, _, _, rr1 = O.batchnorm_train(z1.astype(np.float64))
-    h2z, _, _, rr2 = O.batchnorm_train(z2.astype(np.float64))
-    cols = np.arange(3, d, d // 64)
-    ar = np.arange(len(cols))
-    # dz1[:, cols]: rows `cols` of C
-    c_rows = h1z[:, cols].T @ h2z / n
-    G = 2 * 0.005 * c_rows
-    G[ar, cols] = 2 * (c_rows[ar, cols] - 1.0)
-    gh = h2z @ G.T / n
-    ref1 = (gh - gh.mean(0) - h1z[:, cols] * (gh * h1z[:, cols]).mean(0)) * rr1[cols]
-    assert _rel(g1[:, cols], ref1) < TOL + 4e-3
-    # dz2[:, cols]: columns `cols` of C
-    c_cols = h1z.T @ h2z[:, cols] / n
-    G = 2 * 0.005 * c_cols
-    G[cols, ar] = 2 * (c_cols[cols, ar] - 1.0)
-    gh = h1z @ G / n
-    ref2 = (gh - gh.mean(0) - h2z[:, cols] * (gh * h2z[:, cols]).mean(0)) * rr2[cols]
-    assert _rel(g2[:, cols], ref2) < TOL + 4e-3
-    on = off = 0.0
-    for s in range(0, d, 1024):
-        blk = h1z[:, s:s + 1024].T @ h2z / n
-        idx = np.arange(s, min(s + 1024, d))
-        dg = blk[idx - s, idx]
-        on += ((dg - 1) ** 2).sum()
-        off += (blk ** 2).sum() - (dg ** 2).sum()
-    ref_loss = on + 0.005 * off
-    assert abs(loss12 - ref_loss) <= TOL * ref_loss, (loss12, ref_loss)
+    assert _rel(g1, h1.astype(np.float64)) < TOL and _rel(g2, h2.astype(np.float64)) < TOL
+    assert np.abs(g1.astype(np.float64).sum(0)).max() < 1e-3 * np.abs(g1).sum(0).max()
+    assert np.abs(g2.astype(np.float64).sum(0)).max() < 1e-3 * np.abs(g2).sum(0).max()
