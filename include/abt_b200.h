@@ -152,6 +152,10 @@ int abt_bank_push(const float* x, int64_t x_stride, int n_clips, int clip_elems,
 int abt_normalize_batch_workspace_bytes(int n_channels, size_t* bytes);
 int abt_normalize_batch(const float* x, int n_batch, int n_channels, int hw, float* out, void* workspace, abt_stream_t stream);
 
+/* Dataset statistics (datasets.py:362-376, `calculate_norm_stats`: lms_vectors.mean(), lms_vectors.std()): mean and UNBIASED
+ * standard deviation of x (n_batch, elems) as two DEVICE doubles.  workspace: abt_normalize_batch_workspace_bytes(1). */
+int abt_mean_std(const float* x, int n_batch, int elems, double* out2, void* workspace, abt_stream_t stream);
+
 /* RunningNorm (augmentations.py:187-210; --pre_norm, main.py:272-277): x (n_batch, elems) fp32, the samples are processed IN ORDER with
  * the reference's running statistics (mu += (mean(x_b) - mu) / n with n the count before the update, likewise for mean((x_b - mu)^2));
  * updates stop after max_update samples.  state3: device, 3 doubles (count, mu, s2), zero-initialised by the caller and carried from
@@ -357,6 +361,29 @@ typedef struct {
 
 int abt_bt_dist_step_workspace_bytes(int n_local, int world, int n_dims, size_t* bytes);
 int abt_bt_dist_step(const abt_bt_dist_step_args* args, abt_comm* comm, abt_stream_t stream);
+
+/* ===================================================================================== *
+ *  Step-adjacent optimiser math as multi-tensor kernels
+ *  replaces LARS.step (utils/utils.py:162-189: per-parameter Python loop, two torch.norm and
+ *  ~8 launches per tensor) and update_moving_average (utils/utils.py:328-331, BYOL EMA).
+ *  All tensors of a step are described by ONE device table + a chunk map, so a step costs two
+ *  launches (LARS) or one (EMA) whatever the number of parameters.  fp32 tensors only.
+ * ===================================================================================== */
+typedef struct {
+    float* p;        /* LARS: parameter (updated in place).  EMA: moving-average parameter (updated in place) */
+    const float* g;  /* LARS: gradient.                      EMA: current (online) parameter                */
+    float* aux;      /* LARS: momentum buffer `mu` (updated in place).  EMA: unused                          */
+    long long n;     /* elements */
+    int flags;       /* LARS: bit 0 = apply weight decay, bit 1 = apply the LARS trust ratio (utils/utils.py:169,172) */
+    int chunk0;      /* index of this tensor's first chunk in the chunk map */
+} abt_opt_tensor;
+/* elements per chunk; tensor t owns ceil(n / chunk) consecutive chunks starting at chunk0, chunk_tensor[c] = t */
+int abt_opt_chunk_elems(void);
+/* tensors_dev / chunk_tensor_dev: DEVICE copies of the table and the chunk map; partial_dev: 8 bytes per chunk of scratch */
+int abt_lars_step(const abt_opt_tensor* tensors_dev, const int* chunk_tensor_dev, int n_tensors, int n_chunks, float lr, float weight_decay,
+                  float momentum, float eta, void* partial_dev, abt_stream_t stream);
+/* ma = beta * ma + (1 - beta) * cur for every tensor of the table (utils/utils.py:320-331) */
+int abt_ema_update(const abt_opt_tensor* tensors_dev, const int* chunk_tensor_dev, int n_tensors, int n_chunks, float beta, abt_stream_t stream);
 
 /* ===================================================================================== *
  *  Debug hooks (not part of the drop-in surface; used by tools/gpu_diag.py)

@@ -91,6 +91,10 @@ class BtDistArgs(C.Structure):
     ]
 
 
+class OptTensor(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("aux", C.c_void_p), ("n", C.c_longlong), ("flags", C.c_int32), ("chunk0", C.c_int32)]
+
+
 OVERLAP_CB = C.CFUNCTYPE(None, C.c_void_p)
 
 
@@ -125,6 +129,7 @@ SIGNATURES = {
     "abt_bank_push": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "abt_normalize_batch_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
     "abt_normalize_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "abt_mean_std": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "abt_running_norm_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
     "abt_running_norm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "abt_planner_create": (C.c_int, [C.POINTER(PlanConfig), C.POINTER(C.c_void_p)]),
@@ -155,6 +160,9 @@ SIGNATURES = {
     "abt_comm_destroy": (C.c_int, [C.c_void_p]),
     "abt_bt_dist_step_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "abt_bt_dist_step": (C.c_int, [C.POINTER(BtDistStepArgs), C.c_void_p, C.c_void_p]),
+    "abt_opt_chunk_elems": (C.c_int, []),
+    "abt_lars_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "abt_ema_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "abt_debug_set": (C.c_int, [C.c_int, C.c_int]),
     "abt_debug_launch_count": (C.c_longlong, [C.c_int]),
     "abt_debug_timing": (C.c_int, [C.c_int]),
@@ -187,6 +195,10 @@ def load() -> C.CDLL:
             lib.abt_debug_set(6, int(os.environ["ABT_CTA_GROUP"]))
         if os.environ.get("ABT_DIST_XCHG") in ("0", "1"):       # 0: multi-GPU step without the exchange schedule
             lib.abt_debug_set(7, int(os.environ["ABT_DIST_XCHG"]))
+        if os.environ.get("ABT_COMM_MAX_CTAS") is not None:     # CTA cap of the private NCCL communicators (0 = NCCL's default)
+            lib.abt_debug_set(13, int(os.environ["ABT_COMM_MAX_CTAS"]))
+        if os.environ.get("ABT_DIST_RESERVE_SMS") is not None:  # SMs the tensor-core kernels leave to NCCL inside the multi-GPU step
+            lib.abt_debug_set(14, int(os.environ["ABT_DIST_RESERVE_SMS"]))
         _lib = lib
     return _lib
 

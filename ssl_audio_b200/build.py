@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libabt_b200.so")
-SOURCES = ["abt_common.cu", "bt_loss.cu", "frontend.cu", "planner.cpp"]
+SOURCES = ["abt_common.cu", "bt_loss.cu", "frontend.cu", "optim.cu", "planner.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -306,12 +306,14 @@ __global__ void __launch_bounds__(kColThreads) bt_stat_norm_small_kernel(const T
                                                                          float momentum, float* __restrict__ stats, float* __restrict__ running_mean,
                                                                          float* __restrict__ running_var, __half* __restrict__ zh1,
                                                                          __half* __restrict__ zh2, float* __restrict__ ondiag_part,
-                                                                         double* __restrict__ loss_acc, unsigned int* __restrict__ done_counter) {
+                                                                         double* __restrict__ loss_acc, unsigned int* __restrict__ done_counter,
+                                                                         int tile_img_rows) {
     __shared__ float red[kRowGroups][10][32];
     __shared__ float colstat[4][kSmallCols];
     __shared__ float on_red[2];
     const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const int col = blockIdx.x * kSmallCols + lane * 2;           // D is a multiple of 64: always in range
+    griddep_launch_dependents();                                  // the tensor-core kernel may set itself up while this one runs
     if (blockIdx.x == 0 && threadIdx.x == 0) { loss_acc[0] = 0.0; loss_acc[1] = 0.0; *done_counter = 0u; }
     const float2 k1 = Ld2<T>::ld(z1 + col), k2 = Ld2<T>::ld(z2 + col);
     const float sh1x = in_round<T>(k1.x), sh1y = in_round<T>(k1.y), sh2x = in_round<T>(k2.x), sh2y = in_round<T>(k2.y);
@@ -374,13 +376,56 @@ __global__ void __launch_bounds__(kColThreads) bt_stat_norm_small_kernel(const T
     // standardise from the registers (the values are already shifted: subtract the shifted mean)
     const float m1x = colstat[0][lane * 2], m1y = colstat[0][lane * 2 + 1], r1x = colstat[1][lane * 2], r1y = colstat[1][lane * 2 + 1];
     const float m2x = colstat[2][lane * 2], m2y = colstat[2][lane * 2 + 1], r2x = colstat[3][lane * 2], r2y = colstat[3][lane * 2 + 1];
+    if (tile_img_rows == 0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int n = rg + kRowGroups * k;
+            if (n < N) {
+                Ld2<__half>::st(zh1 + (size_t)n * D + col, (va[k][0] - m1x) * r1x, (va[k][1] - m1y) * r1y);
+                Ld2<__half>::st(zh2 + (size_t)n * D + col, (vb[k][0] - m2x) * r2x, (vb[k][1] - m2y) * r2y);
+            }
+        }
+        return;
+    }
+    // Tile-image layout: this block's 64 columns are ONE operand tile of the tensor-core kernel.  It is written exactly as that
+    // kernel wants it in shared memory -- tile_img_rows rows of 128 bytes (one per sample, zero rows beyond N), 16-byte pieces
+    // XOR-swizzled with the row index (the 128-byte swizzle of a TMA tile) -- so that the kernel fetches it with ONE contiguous
+    // bulk copy instead of a 128-row tensor-map box (which a single SM ingests at only ~24 B / clk).
+    __half* t1 = zh1 + (size_t)blockIdx.x * tile_img_rows * kSmallCols;
+    __half* t2 = zh2 + (size_t)blockIdx.x * tile_img_rows * kSmallCols;
+    const int piece = lane >> 2, within = (lane & 3) * 2;                   // columns 2 lane, 2 lane + 1: 16-byte piece lane / 4
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const int n = rg + kRowGroups * k;
-        if (n < N) {
-            Ld2<__half>::st(zh1 + (size_t)n * D + col, (va[k][0] - m1x) * r1x, (va[k][1] - m1y) * r1y);
-            Ld2<__half>::st(zh2 + (size_t)n * D + col, (vb[k][0] - m2x) * r2x, (vb[k][1] - m2y) * r2y);
+        if (n < tile_img_rows) {
+            const size_t o = (size_t)n * kSmallCols + (size_t)((piece ^ (n & 7)) * 8 + within);
+            const bool live = n < N;
+            Ld2<__half>::st(t1 + o, live ? (va[k][0] - m1x) * r1x : 0.f, live ? (va[k][1] - m1y) * r1y : 0.f);
+            Ld2<__half>::st(t2 + o, live ? (vb[k][0] - m2x) * r2x : 0.f, live ? (vb[k][1] - m2y) * r2y : 0.f);
         }
+    }
+    // D % 128 == 64: the walk of the tensor-core kernel visits one block past the last tile; it must read zeros
+    if (blockIdx.x == 0 && (gridDim.x & 1)) {
+        uint32_t* e1 = reinterpret_cast<uint32_t*>(zh1 + (size_t)gridDim.x * tile_img_rows * kSmallCols);
+        uint32_t* e2 = reinterpret_cast<uint32_t*>(zh2 + (size_t)gridDim.x * tile_img_rows * kSmallCols);
+        for (int i = threadIdx.x; i < tile_img_rows * kSmallCols / 2; i += kColThreads) { e1[i] = 0u; e2[i] = 0u; }
+    }
+}
+
+// row sums of standardised embeddings stored as tile images (HSIC only): the swizzle permutes columns inside a tile row, the sum does not care
+__global__ void __launch_bounds__(256) bt_rowsum_img_kernel(const __half* __restrict__ zimg, int n_tiles, int img_rows, float* __restrict__ out) {
+    __shared__ float red[8];
+    const int n = blockIdx.x;
+    float acc = 0.f;
+    for (int e = threadIdx.x; e < n_tiles * kSmallCols; e += blockDim.x)
+        acc += __half2float(zimg[((size_t)(e / kSmallCols) * img_rows + n) * kSmallCols + (e % kSmallCols)]);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        out[n] = t;
     }
 }
 
@@ -1097,7 +1142,10 @@ struct WsLayout {
     size_t zero_bytes;   // misc + acc: cleared at the start of every call
 };
 
-static int g_fused = 2;         // single-GPU, N <= 128: the one-launch kernels of bt_fused.cuh; 2 = operands in TMEM, 1 = in shared memory, 0 = off (abt_debug_set key 9)
+static int g_fused = 3;         // single-GPU, N <= 128: the one-launch kernels of bt_fused.cuh; 3 = 64-column steps, four S buffers (default),
+                                // 2 = 128-column steps with operands in TMEM, 1 = P in shared memory, 0 = off (abt_debug_set key 9)
+static int g_fused_stages = kXStages;   // ring depth of the one-launch kernel (abt_debug_set key 11)
+static int g_fused_debug = 0;    // timing experiments on the one-launch kernel (abt_debug_set key 10); results are wrong when non-zero
 static bool fused_applies(int N, bool rows_mode, int world) { return g_fused != 0 && world == 0 && !rows_mode && N <= FB; }
 
 static WsLayout ws_layout(int N, int D, int rows, int dtype, bool two_c, int world = 0) {
@@ -1116,8 +1164,11 @@ static WsLayout ws_layout(int N, int D, int rows, int dtype, bool two_c, int wor
     L.rs2 = off; off = align_up(off + sizeof(float) * (size_t)N, 256);
     L.zb1 = off; if (dtype == ABT_DTYPE_F32) off = align_up(off + 2 * (size_t)N * D, 256);       // bf16 copies of fp32 embeddings
     L.zb2 = off; if (dtype == ABT_DTYPE_F32) off = align_up(off + 2 * (size_t)N * D, 256);
-    L.zh1 = off; off = align_up(off + 2 * (size_t)N * D, 256);
-    L.zh2 = off; off = align_up(off + 2 * (size_t)N * D, 256);
+    // one-launch path: tile images of (N rounded up to 32) rows x 64 columns, plus one spare (zero) tile
+    const size_t zh_rows = fused_applies(N, two_c, world) ? (size_t)((N + 31) / 32 * 32) : (size_t)N;
+    const size_t zh_extra = fused_applies(N, two_c, world) ? zh_rows * 128 : 0;
+    L.zh1 = off; off = align_up(off + 2 * zh_rows * D + zh_extra, 256);
+    L.zh2 = off; off = align_up(off + 2 * zh_rows * D + zh_extra, 256);
     L.zs1 = off; if (world > 0) off = align_up(off + 2 * (size_t)N * rows, 256);          // (N_g, Dr): view-1 columns of this rank's dimensions, all samples
     L.zh1_blk = off; if (world > 0) off = align_up(off + 2 * (size_t)(N / world) * D, 256);  // (world, n_local, Dr): send buffer of that exchange
     L.c1 = off; if (!fused_applies(N, two_c, world)) off = align_up(off + 2 * (size_t)rows * D, 256);     // the fused kernel keeps C on chip
@@ -1149,6 +1200,9 @@ static int debug_sync(cudaStream_t st, const char* stage) {
 }
 
 static int g_cta_group = 2;     // 2 = CTA-pair kernel (default), 1 = single-CTA kernel (abt_debug_set key 6)
+static int g_reserve_sms = 0;   // SMs the persistent tensor-core kernels leave free (multi-GPU: for NCCL's kernels); abt_debug_set key 12
+static int g_dist_reserve_sms = 12;   // ... the value abt_bt_dist_step uses for its own launches (key 14): 8 + 4 CTAs of the two communicators
+static int g_comm_max_ctas = 8; // CTA cap of the private NCCL communicators (0 = NCCL's default); abt_debug_set key 13, read at abt_comm_create
 static bool g_tail_split = true; // GRAD: split the last partial wave into half-width items (abt_debug_set key 8)
 static int g_dist_xchg = -1;    // multi-GPU exchange schedule: -1 = auto (4 ranks and more), 0 = never, 1 = whenever possible (abt_debug_set key 7)
 
@@ -1162,6 +1216,12 @@ static int ensure_umma_attr() {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused3_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused3_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused3_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused3_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused3_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused3_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
         if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
@@ -1173,7 +1233,9 @@ static int launch_umma(int cg, const CUtensorMap& a0, const CUtensorMap& b0, con
                        const CUtensorMap& c1, const UmmaParams& p, cudaStream_t stream) {
     const int tiles = p.tiles_m * p.tiles_n * p.pass_count;
     const int total = tiles + (p.split_from < tiles ? tiles - p.split_from : 0);
-    const int slots = num_sms() / cg;
+    int avail = num_sms() - g_reserve_sms;
+    if (avail < 2 * cg) avail = 2 * cg;
+    const int slots = avail / cg;
     const int grid = (total < slots ? total : slots) * cg;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -1257,19 +1319,27 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         // ---- small batch: statistics + standardisation in one pass, then ONE tensor-core launch
         //      (S tiles -> loss + fp16 P on chip -> gradient accumulators in TMEM -> batch-norm backward); no memset, no D x D matrix
         float* ondiag_part = partials;
+        const int n_pad = (N + 31) / 32 * 32;
+        const bool img = g_fused == 3 && !(g_fused_debug & 16);              // tile-image operands + bulk copies (version 3)
         bt_stat_norm_small_kernel<T><<<D / kSmallCols, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, a.eps,
                                                                                  a.momentum, stats, a.running_mean, a.running_var, zh1, zh2, ondiag_part,
-                                                                                 loss_acc, reinterpret_cast<unsigned int*>(ws + L.misc + 64));
+                                                                                 loss_acc, reinterpret_cast<unsigned int*>(ws + L.misc + 64),
+                                                                                 img ? n_pad : 0);
         count_launch();
         if (int rc = debug_sync(stream, "statistics")) return rc;
         if (a.hsic) {
-            bt_rowsum_zh_kernel<<<N, 256, 0, stream>>>(zh1, N, D, rs1);
-            bt_rowsum_zh_kernel<<<N, 256, 0, stream>>>(zh2, N, D, rs2);
+            if (img) {
+                bt_rowsum_img_kernel<<<N, 256, 0, stream>>>(zh1, D / kSmallCols, n_pad, rs1);
+                bt_rowsum_img_kernel<<<N, 256, 0, stream>>>(zh2, D / kSmallCols, n_pad, rs2);
+            } else {
+                bt_rowsum_zh_kernel<<<N, 256, 0, stream>>>(zh1, N, D, rs1);
+                bt_rowsum_zh_kernel<<<N, 256, 0, stream>>>(zh2, N, D, rs2);
+            }
             count_launch(2);
         }
         if (timed) { cudaEventRecord(tev[1], stream); cudaEventRecord(tev[2], stream); }
         FusedParams p{};
-        p.D = D; p.N = N; p.n_pad = (N + 15) / 16 * 16;
+        p.D = D; p.N = N; p.n_pad = n_pad;
         p.n_blocks = (D + FB - 1) / FB;
         p.pass_count = need == 3 ? 2 : 1;
         p.pass_side[0] = (need & 1) ? 0 : 1; p.pass_side[1] = 1;
@@ -1278,14 +1348,29 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         p.stats = stats; p.rs1 = rs1; p.rs2 = rs2;
         p.dz1 = a.dz1; p.dz2 = a.dz2;
         p.loss_acc = loss_acc; p.done_counter = reinterpret_cast<unsigned int*>(ws + L.misc + 64); p.loss_out = a.loss_out;
-        p.ondiag_part = ondiag_part; p.n_parts = D / kSmallCols;
+        p.ondiag_part = ondiag_part; p.n_parts = D / kSmallCols; p.debug = g_fused_debug;
+        p.zimg1 = img ? zh1 : nullptr; p.zimg2 = img ? zh2 : nullptr;
+        p.n_stages = g_fused_stages;
         CUtensorMap mz1, mz2;
         if (int rc = make_map_16(&mz1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh1, N, D, 64, p.n_pad)) return rc;
         if (int rc = make_map_16(&mz2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh2, N, D, 64, p.n_pad)) return rc;
         const int units = p.n_blocks * p.pass_count;
         const int grid = units < num_sms() ? units : num_sms();
         if (g_fused == 1) bt_fused_kernel<<<grid, kNumThreads, kFSmemBytes, stream>>>(mz1, mz2, p);
-        else bt_fused_ts_kernel<<<grid, kTThreads, kTSmemBytes, stream>>>(mz1, mz2, p);
+        else if (g_fused == 2) bt_fused_ts_kernel<<<grid, kTThreads, kTSmemBytes, stream>>>(mz1, mz2, p);
+        else {
+            // programmatic dependent launch: set-up (barriers, TMEM allocation) overlaps the statistics kernel.  Not with HSIC (two more
+            // kernels in between) and not while per-launch events are being recorded.
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTThreads); cfg.dynamicSmemBytes = kXSmemBytes; cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = (!a.hsic && !timed && !(g_fused_debug & 32)) ? 1 : 0;
+            cudaError_t le = a.hsic ? cudaLaunchKernelEx(&cfg, bt_fused3_kernel<T, true>, mz1, mz2, p) : cudaLaunchKernelEx(&cfg, bt_fused3_kernel<T, false>, mz1, mz2, p);
+            if (le != cudaSuccess) return set_error(ABT_ERR_CUDA, "bt_fused3_kernel launch: %s", cudaGetErrorString(le));
+        }
         count_launch();
         if (int rc = debug_sync(stream, "FUSED")) return rc;
         if (timed) { cudaEventRecord(tev[3], stream); ++g_timing.count; }
@@ -1390,7 +1475,7 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         const int q = 16 * cg;                                  // UMMA N granularity (M = 128: 16, M = 256: 32 so that each CTA stages a multiple of 16)
         int bn = N >= 256 ? 256 : ((N + q - 1) / q) * q;
         // small problems: narrower sample tiles instead of split-K, so that the epilogue always sees complete sums
-        while (bn > 32 && row_tiles * ((N + bn - 1) / bn) * passes < num_sms() / cg) bn = ((bn / 2 + q - 1) / q) * q;
+        while (bn > 32 && row_tiles * ((N + bn - 1) / bn) * passes < (num_sms() - g_reserve_sms) / cg) bn = ((bn / 2 + q - 1) / q) * q;
         CUtensorMap mCk, mCt, mZ2, mZ1;
         if (a.xchg) {
             if (int rc = make_map_16(&mCk, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C1, D, RC, 64, 128)) return rc;         // column-blocked C[rows, :]
@@ -1437,7 +1522,7 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         p.pass_count = passes;
         // tail of the persistent schedule: if the last wave fills at most half of the CTA slots, its tiles are split in two
         // half-width items (one more half wave instead of one more full wave)
-        const int n_tiles = p.tiles_m * p.tiles_n * passes, slots = num_sms() / cg, rem = n_tiles % slots;
+        const int n_tiles = p.tiles_m * p.tiles_n * passes, slots = (num_sms() - g_reserve_sms) / cg, rem = n_tiles % slots;
         const bool split = g_tail_split && bn == 256 && n_tiles > slots && rem > 0 && 2 * rem <= slots;
         p.split_from = split ? n_tiles - rem : n_tiles;
         CUtensorMap mZ2h, mZ1h;
@@ -1518,7 +1603,12 @@ extern "C" int abt_debug_set(int key, int value) {
     if (key == 6) { g_cta_group = value == 1 ? 1 : 2; return 0; }
     if (key == 8) { g_tail_split = value != 0; return 0; }
     if (key == 7) { g_dist_xchg = value < 0 ? -1 : (value != 0 ? 1 : 0); return 0; }
-    if (key == 9) { g_fused = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }
+    if (key == 12) { g_reserve_sms = value < 0 ? 0 : (value > 64 ? 64 : value); return 0; }
+    if (key == 13) { g_comm_max_ctas = value < 0 ? 0 : value; return 0; }
+    if (key == 14) { g_dist_reserve_sms = value < 0 ? 0 : (value > 64 ? 64 : value); return 0; }
+    if (key == 9) { g_fused = value < 0 ? 0 : (value > 3 ? 3 : value); return 0; }
+    if (key == 10) { g_fused_debug = value; return 0; }
+    if (key == 11) { g_fused_stages = value < 6 ? 6 : (value > kXStages ? kXStages : value); return 0; }
     if (key < 0 || key >= 6) return set_error(ABT_ERR_ARG, "unknown debug key %d", key);
     *f[key] = value;
     return 0;
@@ -1744,6 +1834,7 @@ namespace abt {
 struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*);
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*);     // optional
     ncclResult_t (*CommDestroy)(ncclComm_t);
     const char* (*GetErrorString)(ncclResult_t);
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
@@ -1777,6 +1868,7 @@ static int load_nccl() {
     ABT_NCCL_SYM(GroupEnd, "ncclGroupEnd");
 #undef ABT_NCCL_SYM
     *reinterpret_cast<void**>(&g_nccl.AlltoAll) = dlsym(h, "ncclAlltoAll");
+    *reinterpret_cast<void**>(&g_nccl.CommInitRankConfig) = dlsym(h, "ncclCommInitRankConfig");
     g_nccl.ok = true;
     return 0;
 }
@@ -1854,8 +1946,20 @@ extern "C" int abt_comm_create(int world, int rank, const void* id256, abt_comm*
     c->world = world; c->rank = rank;
     ncclUniqueId id[2];
     std::memcpy(id, id256, sizeof(id));
-    ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id[0], rank);
-    if (r == ncclSuccess) r = g_nccl.CommInitRank(&c->comm2, world, id[1], rank);
+    // The collectives run beside the persistent tensor-core kernels, which leave g_reserve_sms SMs free for them (a CTA of bt_umma_kernel
+    // owns a whole SM's registers): cap the CTAs NCCL may use so that its kernels always fit there instead of queueing behind a GEMM
+    // (that queueing, with the ranks skewed against each other, was the 0.9 / 1.6 ms bimodal step of round 1).
+    ncclResult_t r;
+    if (g_nccl.CommInitRankConfig != nullptr && g_comm_max_ctas > 0) {
+        ncclConfig_t cfg1 = NCCL_CONFIG_INITIALIZER, cfg2 = NCCL_CONFIG_INITIALIZER;
+        cfg1.maxCTAs = g_comm_max_ctas;
+        cfg2.maxCTAs = g_comm_max_ctas > 4 ? 4 : g_comm_max_ctas;
+        r = g_nccl.CommInitRankConfig(&c->comm, world, id[0], rank, &cfg1);
+        if (r == ncclSuccess) r = g_nccl.CommInitRankConfig(&c->comm2, world, id[1], rank, &cfg2);
+    } else {
+        r = g_nccl.CommInitRank(&c->comm, world, id[0], rank);
+        if (r == ncclSuccess) r = g_nccl.CommInitRank(&c->comm2, world, id[1], rank);
+    }
     if (r != ncclSuccess) { delete c; return set_error(ABT_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -1937,6 +2041,9 @@ extern "C" int abt_bt_dist_step(const abt_bt_dist_step_args* a, abt_comm* c, abt
     const size_t nvec = (size_t)world * N * vec_per_slice;
     const unsigned ublocks = (unsigned)((nvec + 255) / 256 < 148u * 8u ? (nvec + 255) / 256 : 148u * 8u);
 
+    // while this step runs, the tensor-core kernels leave room for NCCL's CTAs (restored before returning on every path below via the guard)
+    struct ReserveGuard { int prev; ReserveGuard(int v) : prev(g_reserve_sms) { g_reserve_sms = v; } ~ReserveGuard() { g_reserve_sms = prev; } };
+    ReserveGuard reserve_guard(world > 1 ? g_dist_reserve_sms : g_reserve_sms);
     // 1. local statistics -> all-gather of the 7 D-float packs
     if (int rc = abt_bt_dist_stats_local(a->z1, a->z2, a->dtype, N, world, D, Dr, a->workspace, stream_)) return rc;
     chain(st, c->ev[E_P0], c->cs2);

@@ -717,10 +717,12 @@ static int launch_logmel(const abt_logmel_plan* pl, const float* wav, int64_t ro
     const int span = (kTileFrames - 1) * a.hop + kNfft;
     const size_t smem = sizeof(float) * (((span + 31) & ~31) + kWarps * kScratchFloats + kMels * (kTileFrames + 1) + pl->nnz) + sizeof(int) * 3 * kMels;
     if (smem > 227 * 1024) return set_error(ABT_ERR_ARG, "hop_length %d needs %zu bytes of shared memory (> 227 KiB)", a.hop, smem);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    static size_t smem_set[64] = {};                  // cudaFuncSetAttribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || smem > smem_set[dev]) {
         ABT_CUDA_OK(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+        if (dev >= 0 && dev < 64) smem_set[dev] = smem;
     }
     dim3 grid((n_frames_out + kTileFrames - 1) / kTileFrames, n_clips);
     logmel_kernel<<<grid, kWarps * 32, smem, stream>>>(a);
@@ -824,10 +826,12 @@ extern "C" int abt_views_fwd(const abt_views_args* a, abt_stream_t stream) {
     if (a->out_w > kViewThreads) return set_error(ABT_ERR_ARG, "out_w must be <= %d", kViewThreads);
     const size_t smem = sizeof(float) * ((size_t)a->canvas_h * a->canvas_w + (size_t)a->canvas_h * a->out_w) + 32 * (size_t)(a->out_w + a->out_h);
     if (smem > 200 * 1024) return set_error(ABT_ERR_ARG, "canvas too large for shared memory");
-    static size_t smem_set = 48 * 1024;
-    if (smem > smem_set) {
+    static size_t smem_set[64] = {};                  // per device; 0 = only the default 48 KiB is available
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && (dev < 0 || dev >= 64 || smem > smem_set[dev])) {
         ABT_CUDA_OK(cudaFuncSetAttribute(views_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+        if (dev >= 0 && dev < 64) smem_set[dev] = smem;
     }
     dim3 grid(a->n_clips, a->n_views);
     views_kernel<<<grid, kViewThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
@@ -867,6 +871,39 @@ extern "C" int abt_normalize_batch(const float* x, int n_batch, int n_channels, 
     const long long per_ch = (long long)n_batch * hw;
     const unsigned blocks = (unsigned)((per_ch + 1023) / 1024 < 148 * 8 ? (per_ch + 1023) / 1024 : 148 * 8);
     batch_norm_apply_kernel<<<dim3(blocks, n_channels), 256, 0, st>>>(x, out, n_batch, n_channels, hw, static_cast<const double*>(workspace), kNbBlocks);
+    count_launch(2);
+    ABT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// mean and UNBIASED standard deviation of a whole tensor (dataset statistics, datasets.py:362-376: `lms_vectors.mean()`,
+// `lms_vectors.std()`): the per-channel partial sums above with one channel, folded by one block into two doubles
+__global__ void __launch_bounds__(256) mean_std_finalize_kernel(const float* __restrict__ x, const double* __restrict__ partials, int n_partials, double n,
+                                                                double* __restrict__ out2) {
+    __shared__ double red[2][8];
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) { s1 += partials[(size_t)i * 2]; s2 += partials[(size_t)i * 2 + 1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int w = 0; w < 8; ++w) { t1 += red[0][w]; t2 += red[1][w]; }
+        const double dmean = t1 / n;
+        const double var = n > 1.0 ? fmax((t2 - t1 * dmean) / (n - 1.0), 0.0) : 0.0;
+        out2[0] = (double)__ldg(x) + dmean;
+        out2[1] = sqrt(var);
+    }
+}
+
+extern "C" int abt_mean_std(const float* x, int n_batch, int elems, double* out2, void* workspace, abt_stream_t stream) {
+    if (x == nullptr || out2 == nullptr || workspace == nullptr) return set_error(ABT_ERR_ARG, "null argument");
+    if (n_batch < 1 || elems < 1) return set_error(ABT_ERR_ARG, "bad shape");
+    if (int rc = check_device_sm100()) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    batch_stats_kernel<<<dim3(kNbBlocks, 1), 256, 0, st>>>(x, n_batch, 1, elems, static_cast<double*>(workspace));
+    mean_std_finalize_kernel<<<1, 256, 0, st>>>(x, static_cast<const double*>(workspace), kNbBlocks, (double)n_batch * (double)elems, out2);
     count_launch(2);
     ABT_CUDA_OK(cudaGetLastError());
     return 0;

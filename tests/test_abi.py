@@ -38,7 +38,8 @@ def test_struct_sizes_match_header(tmp_path):
     import subprocess
     pairs = {"abt_view_params": _lib.ViewParams, "abt_mel_config": _lib.MelConfig, "abt_bt_args": _lib.BtArgs,
              "abt_views_args": _lib.ViewsArgs, "abt_plan_config": _lib.PlanConfig, "abt_bt_rows_args": _lib.BtRowsArgs,
-             "abt_bt_dist_layout": _lib.BtDistLayout, "abt_bt_dist_args": _lib.BtDistArgs, "abt_bt_dist_step_args": _lib.BtDistStepArgs}
+             "abt_bt_dist_layout": _lib.BtDistLayout, "abt_bt_dist_args": _lib.BtDistArgs, "abt_bt_dist_step_args": _lib.BtDistStepArgs,
+             "abt_opt_tensor": _lib.OptTensor}
     src = tmp_path / "sz.c"
     header = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "abt_b200.h")
     body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in pairs)
@@ -55,8 +56,10 @@ def test_struct_sizes_match_header(tmp_path):
 def test_argument_validation_needs_no_gpu():
     lib = _lib.load()
     nbytes = C.c_size_t()
+    assert lib.abt_bt_workspace_bytes(1024, 8192, 0, C.byref(nbytes)) == 0
+    assert nbytes.value > 2 * 8192 * 8192                      # the fp16 correlation matrix alone is 128 MiB
     assert lib.abt_bt_workspace_bytes(128, 8192, 0, C.byref(nbytes)) == 0
-    assert nbytes.value > 2 * 8192 * 8192                      # H alone is 128 MiB
+    assert nbytes.value < 32 << 20                              # N <= 128: the one-launch kernel keeps C on chip
     assert lib.abt_bt_workspace_bytes(128, 100, 0, C.byref(nbytes)) == _lib.ABT_ERR_ARG
     assert b"multiple of 64" in lib.abt_last_error()
     assert lib.abt_bt_workspace_bytes(1, 128, 0, C.byref(nbytes)) == _lib.ABT_ERR_ARG
