@@ -1142,10 +1142,8 @@ struct WsLayout {
     size_t zero_bytes;   // misc + acc: cleared at the start of every call
 };
 
-static int g_fused = 3;         // single-GPU, N <= 128: the one-launch kernels of bt_fused.cuh; 3 = 64-column steps, four S buffers (default),
-                                // 2 = 128-column steps with operands in TMEM, 1 = P in shared memory, 0 = off (abt_debug_set key 9)
-static int g_fused_stages = kXStages;   // ring depth of the one-launch kernel (abt_debug_set key 11)
-static int g_fused_debug = 0;    // timing experiments on the one-launch kernel (abt_debug_set key 10); results are wrong when non-zero
+static int g_fused = 1;         // single-GPU, N <= 128: the one-launch kernel of bt_fused.cuh (abt_debug_set key 9: 0 = use CORR + GRAD instead)
+static int g_fused_pdl = 1;     // programmatic dependent launch of that kernel behind the statistics kernel (abt_debug_set key 10)
 static bool fused_applies(int N, bool rows_mode, int world) { return g_fused != 0 && world == 0 && !rows_mode && N <= FB; }
 
 static WsLayout ws_layout(int N, int D, int rows, int dtype, bool two_c, int world = 0) {
@@ -1206,6 +1204,30 @@ static int g_comm_max_ctas = 8; // CTA cap of the private NCCL communicators (0 
 static bool g_tail_split = true; // GRAD: split the last partial wave into half-width items (abt_debug_set key 8)
 static int g_dist_xchg = -1;    // multi-GPU exchange schedule: -1 = auto (4 ranks and more), 0 = never, 1 = whenever possible (abt_debug_set key 7)
 
+template <typename T, bool H, int NP> static cudaError_t fused_attr_one() {
+    return cudaFuncSetAttribute(bt_fused_kernel<T, H, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
+}
+template <typename T> static cudaError_t fused_attr_type() {
+    cudaError_t e = fused_attr_one<T, false, 128>();
+    if (e == cudaSuccess) e = fused_attr_one<T, true, 128>();
+    if (e == cudaSuccess) e = fused_attr_one<T, false, 0>();
+    if (e == cudaSuccess) e = fused_attr_one<T, true, 0>();
+    return e;
+}
+static cudaError_t fused_set_attr() {
+    cudaError_t e = fused_attr_type<__nv_bfloat16>();
+    if (e == cudaSuccess) e = fused_attr_type<__half>();
+    if (e == cudaSuccess) e = fused_attr_type<float>();
+    return e;
+}
+template <typename T, bool H, int NP> static cudaError_t fused_launch_one(const cudaLaunchConfig_t& cfg, const FusedParams& p) {
+    return cudaLaunchKernelEx(&cfg, bt_fused_kernel<T, H, NP>, p);
+}
+template <typename T> static cudaError_t fused_launch(const cudaLaunchConfig_t& cfg, const FusedParams& p) {
+    if (p.n_pad == 128) return p.hsic ? fused_launch_one<T, true, 128>(cfg, p) : fused_launch_one<T, false, 128>(cfg, p);
+    return p.hsic ? fused_launch_one<T, true, 0>(cfg, p) : fused_launch_one<T, false, 0>(cfg, p);
+}
+
 // cudaFuncSetAttribute is per device: keep one flag per device ordinal
 static int ensure_umma_attr() {
     static bool attr_set[64] = {};
@@ -1214,14 +1236,7 @@ static int ensure_umma_attr() {
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(bt_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused3_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused3_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused3_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused3_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused3_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(bt_fused3_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
+        if (e == cudaSuccess) e = fused_set_attr();
         if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
@@ -1320,21 +1335,14 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         //      (S tiles -> loss + fp16 P on chip -> gradient accumulators in TMEM -> batch-norm backward); no memset, no D x D matrix
         float* ondiag_part = partials;
         const int n_pad = (N + 31) / 32 * 32;
-        const bool img = g_fused == 3 && !(g_fused_debug & 16);              // tile-image operands + bulk copies (version 3)
         bt_stat_norm_small_kernel<T><<<D / kSmallCols, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, a.eps,
                                                                                  a.momentum, stats, a.running_mean, a.running_var, zh1, zh2, ondiag_part,
-                                                                                 loss_acc, reinterpret_cast<unsigned int*>(ws + L.misc + 64),
-                                                                                 img ? n_pad : 0);
+                                                                                 loss_acc, reinterpret_cast<unsigned int*>(ws + L.misc + 64), n_pad);
         count_launch();
         if (int rc = debug_sync(stream, "statistics")) return rc;
         if (a.hsic) {
-            if (img) {
-                bt_rowsum_img_kernel<<<N, 256, 0, stream>>>(zh1, D / kSmallCols, n_pad, rs1);
-                bt_rowsum_img_kernel<<<N, 256, 0, stream>>>(zh2, D / kSmallCols, n_pad, rs2);
-            } else {
-                bt_rowsum_zh_kernel<<<N, 256, 0, stream>>>(zh1, N, D, rs1);
-                bt_rowsum_zh_kernel<<<N, 256, 0, stream>>>(zh2, N, D, rs2);
-            }
+            bt_rowsum_img_kernel<<<N, 256, 0, stream>>>(zh1, D / kSmallCols, n_pad, rs1);
+            bt_rowsum_img_kernel<<<N, 256, 0, stream>>>(zh2, D / kSmallCols, n_pad, rs2);
             count_launch(2);
         }
         if (timed) { cudaEventRecord(tev[1], stream); cudaEventRecord(tev[2], stream); }
@@ -1343,34 +1351,25 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         p.n_blocks = (D + FB - 1) / FB;
         p.pass_count = need == 3 ? 2 : 1;
         p.pass_side[0] = (need & 1) ? 0 : 1; p.pass_side[1] = 1;
-        p.hsic = a.hsic; p.io_dtype = a.dtype;
+        p.hsic = a.hsic;
         p.alpha = a.alpha; p.lambda = a.lambda; p.grad_scale = a.grad_scale;
         p.stats = stats; p.rs1 = rs1; p.rs2 = rs2;
         p.dz1 = a.dz1; p.dz2 = a.dz2;
         p.loss_acc = loss_acc; p.done_counter = reinterpret_cast<unsigned int*>(ws + L.misc + 64); p.loss_out = a.loss_out;
-        p.ondiag_part = ondiag_part; p.n_parts = D / kSmallCols; p.debug = g_fused_debug;
-        p.zimg1 = img ? zh1 : nullptr; p.zimg2 = img ? zh2 : nullptr;
-        p.n_stages = g_fused_stages;
-        CUtensorMap mz1, mz2;
-        if (int rc = make_map_16(&mz1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh1, N, D, 64, p.n_pad)) return rc;
-        if (int rc = make_map_16(&mz2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, zh2, N, D, 64, p.n_pad)) return rc;
+        p.ondiag_part = ondiag_part; p.n_parts = D / kSmallCols;
+        p.zimg1 = zh1; p.zimg2 = zh2;
         const int units = p.n_blocks * p.pass_count;
-        const int grid = units < num_sms() ? units : num_sms();
-        if (g_fused == 1) bt_fused_kernel<<<grid, kNumThreads, kFSmemBytes, stream>>>(mz1, mz2, p);
-        else if (g_fused == 2) bt_fused_ts_kernel<<<grid, kTThreads, kTSmemBytes, stream>>>(mz1, mz2, p);
-        else {
-            // programmatic dependent launch: set-up (barriers, TMEM allocation) overlaps the statistics kernel.  Not with HSIC (two more
-            // kernels in between) and not while per-launch events are being recorded.
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTThreads); cfg.dynamicSmemBytes = kXSmemBytes; cfg.stream = stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = (!a.hsic && !timed && !(g_fused_debug & 32)) ? 1 : 0;
-            cudaError_t le = a.hsic ? cudaLaunchKernelEx(&cfg, bt_fused3_kernel<T, true>, mz1, mz2, p) : cudaLaunchKernelEx(&cfg, bt_fused3_kernel<T, false>, mz1, mz2, p);
-            if (le != cudaSuccess) return set_error(ABT_ERR_CUDA, "bt_fused3_kernel launch: %s", cudaGetErrorString(le));
-        }
+        // programmatic dependent launch: set-up (barriers, TMEM allocation) overlaps the statistics kernel.  Not with HSIC (two more
+        // kernels in between) and not while per-launch events are being recorded.
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(units < num_sms() ? units : num_sms()); cfg.blockDim = dim3(kTThreads); cfg.dynamicSmemBytes = kXSmemBytes; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = (!a.hsic && !timed && g_fused_pdl) ? 1 : 0;
+        const cudaError_t le = fused_launch<T>(cfg, p);
+        if (le != cudaSuccess) return set_error(ABT_ERR_CUDA, "bt_fused_kernel launch: %s", cudaGetErrorString(le));
         count_launch();
         if (int rc = debug_sync(stream, "FUSED")) return rc;
         if (timed) { cudaEventRecord(tev[3], stream); ++g_timing.count; }
@@ -1606,9 +1605,8 @@ extern "C" int abt_debug_set(int key, int value) {
     if (key == 12) { g_reserve_sms = value < 0 ? 0 : (value > 64 ? 64 : value); return 0; }
     if (key == 13) { g_comm_max_ctas = value < 0 ? 0 : value; return 0; }
     if (key == 14) { g_dist_reserve_sms = value < 0 ? 0 : (value > 64 ? 64 : value); return 0; }
-    if (key == 9) { g_fused = value < 0 ? 0 : (value > 3 ? 3 : value); return 0; }
-    if (key == 10) { g_fused_debug = value; return 0; }
-    if (key == 11) { g_fused_stages = value < 6 ? 6 : (value > kXStages ? kXStages : value); return 0; }
+    if (key == 9) { g_fused = value != 0; return 0; }
+    if (key == 10) { g_fused_pdl = value != 0; return 0; }
     if (key < 0 || key >= 6) return set_error(ABT_ERR_ARG, "unknown debug key %d", key);
     *f[key] = value;
     return 0;

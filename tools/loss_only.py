@@ -7,12 +7,9 @@ import ssl_audio_b200 as S
 if os.environ.get("ABT_FUSED") is not None:
     from ssl_audio_b200 import _lib as _l
     _l.load().abt_debug_set(9, int(os.environ["ABT_FUSED"]))
-if os.environ.get("ABT_FUSED_DEBUG") is not None:
+if os.environ.get("ABT_FUSED_PDL") is not None:
     from ssl_audio_b200 import _lib as _l
-    _l.load().abt_debug_set(10, int(os.environ["ABT_FUSED_DEBUG"]))
-if os.environ.get("ABT_FUSED_STAGES") is not None:
-    from ssl_audio_b200 import _lib as _l
-    _l.load().abt_debug_set(11, int(os.environ["ABT_FUSED_STAGES"]))
+    _l.load().abt_debug_set(10, int(os.environ["ABT_FUSED_PDL"]))
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
