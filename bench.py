@@ -413,16 +413,24 @@ def run_ours(args):
         a0 = a0.bfloat16()
         crit_s = S.BarlowTwinsLoss(_args_ns(d_s), ncrops=2).to(dev)
 
-        def one():
+        def one_module():
             a = a0.detach().requires_grad_(True)
             b = b0.detach().requires_grad_(True)
             lo = crit_s(b, a, ngcrops_each=1)
             lo.backward()
             return lo
+
+        def one():
+            # the library call itself (loss + both gradients in one C-ABI call); the module adds autograd glue and one scaling launch
+            if world > 1:
+                from ssl_audio_b200 import dist as _D
+                return _D.bt_loss_fwd_bwd_global(b0, a0, 1.0, 0.005, False)[0]
+            return S.bt_loss_fwd_bwd(b0, a0, 1.0, 0.005, False)[0]
         for _ in range(5):
             one()
+            one_module()
         sync_all()
-        _lib.check(lib.abt_debug_timing(1))
+        # (a) whole call, every iteration alone after an L2 flush; no per-launch events, so the launches keep their programmatic dependency
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.sweep_iters)]
         for e_a, e_b in evs:
             flush.zero_()
@@ -430,12 +438,24 @@ def run_ours(args):
             lo = one()
             e_b.record()
         torch.cuda.synchronize(dev)
+        times = sorted(e_a.elapsed_time(e_b) for e_a, e_b in evs)
+        # (b) the tensor-core launch(es) alone: CUDA events recorded by the library around them on the launching stream
+        _lib.check(lib.abt_debug_timing(1))
+        for _ in range(args.sweep_iters):
+            one()
+        torch.cuda.synchronize(dev)
         st_s, co_s, gr_s, nc_s = C.c_float(), C.c_float(), C.c_float(), C.c_int()
         _lib.check(lib.abt_debug_timing_read(C.byref(st_s), C.byref(co_s), C.byref(gr_s), C.byref(nc_s)))
         _lib.check(lib.abt_debug_timing(0))
         per = nc_s.value / float(args.sweep_iters)
-        times = sorted(e_a.elapsed_time(e_b) for e_a, e_b in evs)
-        sweep.append([d_s, times[len(times) // 2], (co_s.value + gr_s.value) * per, st_s.value * per, float(lo.detach())])
+        # (c) through the module (BarlowTwinsLoss + backward): the same call plus autograd glue -- host-bound at this size
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for _ in range(args.sweep_iters):
+            one_module()
+        m1.record()
+        torch.cuda.synchronize(dev)
+        sweep.append([d_s, times[len(times) // 2], (co_s.value + gr_s.value) * per, st_s.value * per, float(lo.detach()), m0.elapsed_time(m1) / args.sweep_iters])
         del crit_s
     del flush
 
@@ -537,12 +557,13 @@ def run_ours(args):
         raise RuntimeError(f"ranks disagree on the global loss (relative spread {loss_spread:.2e}): the multi-GPU exchange is broken")
     flops = 6.0 * B * D * D                                   # algorithmic FLOPs of one loss term, per GPU = 6 N_g D^2 / R
     sweep_out = []
-    for d_s, call_ms, kern_ms, stat_ms_s, lo_s in sweep:
+    for d_s, call_ms, kern_ms, stat_ms_s, lo_s, mod_ms in sweep:
         fl = 6.0 * 128 * d_s * d_s                             # per GPU; the global batch is 128 x world rows
         ach = fl / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
         sweep_out.append({
             "D": d_s, "rows_per_gpu": 128, "global_rows": 128 * world, "ms": call_ms, "clips_per_s": 128 * world / (call_ms * 1e-3), "loss_value": lo_s,
-            "roofline": {"bound": "tensor", "kernel": "bt_fused_ts_kernel (one launch: S -> loss, P -> gradients, batch-norm backward)" if world == 1
+            "module_ms": mod_ms,
+            "roofline": {"bound": "tensor", "kernel": "bt_fused_kernel (one launch: S -> loss, P -> gradients, batch-norm backward)" if world == 1
                          else "bt_umma_kernel (CORR + GRAD launches of the row-block step)",
                          "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tf_burst"],
                          "traffic": _traffic(f"fused_dram_bytes_n128_d{d_s}") if world == 1 else None,
@@ -569,8 +590,10 @@ def run_ours(args):
                      "frac_of_sustained_peak": achieved / peaks["tf_sustained"],
                      "peak_source": peaks["source"] + " (bf16_tflops burst figure: the launches are timed alone, in short bursts at boost clocks)"},
         "loss_sweep": {"workload": "BASELINE config 3: Barlow Twins loss fwd+bwd, 128 rows per GPU (global batch 128 x n_gpus), bf16 in, "
-                                   "every iteration timed alone with CUDA events after an L2 flush; ms = median whole call (statistics + tensor-core "
-                                   "launches + autograd glue), max over ranks",
+                                   "ms = median device time of the library call (loss + both gradients: statistics + tensor-core launch(es)), every "
+                                   "iteration timed alone with CUDA events after an L2 flush, max over ranks; module_ms = mean per call through "
+                                   "BarlowTwinsLoss + backward, back to back (adds autograd glue and one scaling launch; host-bound at this size); "
+                                   "roofline.frac = the tensor-core launch(es) alone (library events, a second loop), frac_whole_call = the same FLOP over ms",
                        "iters": args.sweep_iters, "points": sweep_out},
         "sustained": {"steps": sus_steps, "ms_per_step": sus_ms, "value": B * world / (sus_ms * 1e-3), "clocks": clocks_sus,
                       "note": "same step, back to back for >= %.1f s" % args.sustained_s},
