@@ -379,6 +379,19 @@ def run_ours(args):
     for v in (stats_ms, corr_ms, grad_ms):
         v.value = v.value * calls_per_step
 
+    if args.quick:
+        tq = torch.tensor([ms, loss_ms, corr_ms.value, grad_ms.value, stats_ms.value], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            v = [float(x) for x in tq.cpu()]
+            print(json.dumps({"quick": True, "n_gpus": world, "ms_per_step": v[0] / args.steps, "value": B * world / (v[0] / args.steps * 1e-3),
+                              "loss_fwd_bwd_ms": v[1], "corr_ms": v[2], "grad_ms": v[3], "stats_ms": v[4], "host_enqueue_ms": host_ms,
+                              "env": {k: os.environ.get(k) for k in ("ABT_DIST_CE", "ABT_COMM_MAX_CTAS", "ABT_DIST_RESERVE_SMS", "ABT_DIST_XCHG")}}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # frontend-only and loss-only device times (explain `value`; not the headline)
     fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fe0.record()
@@ -461,6 +474,10 @@ def run_ours(args):
 
     # ---- sustained loop (>= 2 s of back-to-back steps, clocks sampled throughout): the burst number above is 12 ms of work
     sus_steps = int(max(args.steps, min(20000, args.sustained_s / max(ms / args.steps * 1e-3, 1e-5))))
+    if world > 1:       # every rank must run the same number of (collective) steps: take rank 0's count
+        ns = torch.tensor([sus_steps], dtype=torch.int64, device=dev)
+        dist.broadcast(ns, 0)
+        sus_steps = int(ns.item())
     sampler2 = ClockSampler(local_rank)
     sync_all()
     if rank == 0:
@@ -651,6 +668,7 @@ def main():
     ap.add_argument("--sweep-iters", type=int, default=30, help="timed iterations per point of the N = 128 loss sweep (BASELINE config 3)")
     ap.add_argument("--sustained-s", type=float, default=2.5, help="length of the sustained-clock loop reported beside the burst number")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--quick", action="store_true", help="tuning aid, not a bench line: only the timed step and the loss-only pass, printed as a short JSON line")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                         # timing rule: at least 3 warm-up steps (also warms the Mixup ring)

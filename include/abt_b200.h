@@ -357,9 +357,21 @@ typedef struct {
     size_t workspace_bytes;
     abt_overlap_cb overlap_cb;
     void* overlap_user;
+    /* Optional copy-engine embedding exchange.  Instead of two NCCL all-gathers (SM kernels that compete with the tensor-core kernels
+     * and the frontend), every rank PULLS the other ranks' standardised rows out of peer-mapped exchange buffers with cudaMemcpyAsync:
+     * the copies run on the copy engines, NVLink is driven without a single SM.  exchange_peers: [host] array of `world` device
+     * pointers, entry q = rank q's exchange buffer mapped into this process (torch symmetric memory, cudaIpc*, ...), entry `rank` = this
+     * rank's own; every buffer holds abt_bt_dist_exchange_bytes() bytes and is zero-filled once before its first use (then a
+     * cross-rank barrier).  exchange_epoch: 1, 2, 3, ... -- the number of this call among the calls that used THESE buffers, the same
+     * on every rank (the buffers are double-buffered by its parity; one flag barrier per step keeps the ranks in step).
+     * exchange_peers = NULL: NCCL all-gathers. */
+    void* const* exchange_peers;
+    size_t exchange_bytes;
+    uint32_t exchange_epoch;
 } abt_bt_dist_step_args;
 
 int abt_bt_dist_step_workspace_bytes(int n_local, int world, int n_dims, size_t* bytes);
+int abt_bt_dist_exchange_bytes(int n_local, int world, int n_dims, size_t* bytes);
 int abt_bt_dist_step(const abt_bt_dist_step_args* args, abt_comm* comm, abt_stream_t stream);
 
 /* ===================================================================================== *

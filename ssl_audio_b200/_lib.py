@@ -105,6 +105,7 @@ class BtDistStepArgs(C.Structure):
         ("grad_scale", C.c_float), ("need_grad_mask", C.c_int32), ("loss_out", C.c_void_p), ("dz1", C.c_void_p), ("dz2", C.c_void_p),
         ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("overlap_cb", OVERLAP_CB), ("overlap_user", C.c_void_p),
+        ("exchange_peers", C.c_void_p), ("exchange_bytes", C.c_size_t), ("exchange_epoch", C.c_uint32),
     ]
 
 
@@ -159,6 +160,7 @@ SIGNATURES = {
     "abt_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "abt_comm_destroy": (C.c_int, [C.c_void_p]),
     "abt_bt_dist_step_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "abt_bt_dist_exchange_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "abt_bt_dist_step": (C.c_int, [C.POINTER(BtDistStepArgs), C.c_void_p, C.c_void_p]),
     "abt_opt_chunk_elems": (C.c_int, []),
     "abt_lars_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),

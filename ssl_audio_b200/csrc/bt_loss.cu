@@ -1201,7 +1201,8 @@ static int debug_sync(cudaStream_t st, const char* stage) {
 static int g_cta_group = 2;     // 2 = CTA-pair kernel (default), 1 = single-CTA kernel (abt_debug_set key 6)
 static int g_reserve_sms = 0;   // SMs the persistent tensor-core kernels leave free (multi-GPU: for NCCL's kernels); abt_debug_set key 12
 static int g_dist_reserve_sms = 12;   // ... the value abt_bt_dist_step uses for its own launches (key 14): 8 + 4 CTAs of the two communicators
-static int g_comm_max_ctas = 8; // CTA cap of the private NCCL communicators (0 = NCCL's default); abt_debug_set key 13, read at abt_comm_create
+static int g_comm_max_ctas = 0; // CTA cap of the private NCCL communicators (0 = NCCL's default); abt_debug_set key 13, read at abt_comm_create.
+                                // Measured at 2 ranks: a cap of 8 / 16 CTAs makes the step 35 % / 27 % SLOWER (the all-to-alls starve), so the default is no cap
 static bool g_tail_split = true; // GRAD: split the last partial wave into half-width items (abt_debug_set key 8)
 static int g_dist_xchg = -1;    // multi-GPU exchange schedule: -1 = auto (4 ranks and more), 0 = never, 1 = whenever possible (abt_debug_set key 7)
 
@@ -1752,14 +1753,14 @@ extern "C" int abt_bt_dist_stats_local(const void* z1, const void* z2, int dtype
 
 template <typename T>
 static void dist_normalize(const void* z1, const void* z2, int N, int world, int rank, int D, int row_count, float eps, float momentum, float* rm,
-                           float* rv, uint8_t* ws, const WsLayout& L, cudaStream_t stream) {
+                           float* rv, uint8_t* ws, const WsLayout& L, cudaStream_t stream, __half* zh1_base = nullptr, __half* zh2_base = nullptr) {
     int splits = (N + 127) / 128;
     if (splits > 8) splits = 8;
     const int chunk = (N + splits - 1) / splits;
     splits = (N + chunk - 1) / chunk;
     const dim3 sgrid((D + kColsPerBlock - 1) / kColsPerBlock, splits);
-    __half* zh1 = reinterpret_cast<__half*>(ws + L.zh1) + (size_t)rank * N * D;     // this rank's slot of the gather buffers
-    __half* zh2 = reinterpret_cast<__half*>(ws + L.zh2) + (size_t)rank * N * D;
+    __half* zh1 = (zh1_base ? zh1_base : reinterpret_cast<__half*>(ws + L.zh1)) + (size_t)rank * N * D;     // this rank's slot of the gather buffers
+    __half* zh2 = (zh2_base ? zh2_base : reinterpret_cast<__half*>(ws + L.zh2)) + (size_t)rank * N * D;
     bt_normalize_global_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(z1), static_cast<const T*>(z2), N, world, D, chunk, eps, momentum,
                                                                      reinterpret_cast<const float*>(ws + L.pack_all), reinterpret_cast<float*>(ws + L.stats),
                                                                      zh1, zh2, reinterpret_cast<__half*>(ws + L.zh1_blk), row_count, rm, rv,
@@ -1787,12 +1788,12 @@ extern "C" int abt_bt_dist_normalize(const void* z1, const void* z2, int dtype, 
 
 static int dist_rows_call(int dtype, int n_local, int world, int n_dims, int row_begin, int row_count, float alpha, float lambda, int hsic,
                           float grad_scale, int need, int phase, double* loss_parts, void* dzr1, void* dzr2, void* workspace, cudaStream_t stream,
-                          bool xchg = false) {
+                          bool xchg = false, const void* zh1_base = nullptr, const void* zh2_base = nullptr) {
     const int ng = n_local * world;
     const WsLayout L = ws_layout(ng, n_dims, row_count, ABT_DTYPE_BF16, true, world);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     LossCall c{};
-    c.z1 = ws + L.zh1; c.z2 = ws + L.zh2; c.dtype = dtype; c.N = ng; c.D = n_dims;
+    c.z1 = zh1_base ? zh1_base : ws + L.zh1; c.z2 = zh2_base ? zh2_base : ws + L.zh2; c.dtype = dtype; c.N = ng; c.D = n_dims;
     c.row_begin = row_begin; c.row_count = row_count; c.rows_mode = true; c.zh_mode = true; c.phase = phase; c.xchg = xchg;
     c.alpha = alpha; c.lambda = lambda; c.hsic = hsic; c.eps = 0.f; c.momentum = 0.f; c.grad_scale = grad_scale;
     c.need = need; c.loss_out = nullptr; c.loss_parts_out = loss_parts;
@@ -1898,6 +1899,34 @@ __global__ void bt_dist_loss_kernel(const double* __restrict__ parts, float alph
     }
 }
 
+// Copy-engine exchange buffer (one per rank, peer-mapped): [parity 0: zh1 (N_g x D fp16) | zh2] [parity 1: ...] [flags]
+constexpr int kMaxPeers = 16;
+struct ExchLayout { size_t view_bytes, flags, total; };
+static ExchLayout exch_layout(int n_local, int world, int D) {
+    ExchLayout e{};
+    e.view_bytes = align_up((size_t)n_local * world * D * 2, 256);
+    e.flags = 4 * e.view_bytes;
+    e.total = e.flags + 4096;
+    return e;
+}
+struct PeerFlags { uint32_t* f[kMaxPeers]; };
+// One flag barrier per step: thread q tells rank q "rank `rank` has finished standardising its rows for step `epoch`" (a release store
+// into q's flag array over NVLink) and waits for the same word from q in this rank's own array.  Every rank runs one such CTA on its
+// own GPU; the spin is bounded (a lost peer traps instead of hanging the device).
+__global__ void ce_barrier_kernel(PeerFlags pf, int world, int rank, uint32_t epoch) {
+    const int q = threadIdx.x;
+    if (q >= world) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.f[q] + rank * 16), "r"(epoch) : "memory");
+    const uint32_t* mine = pf.f[rank] + q * 16;
+    uint32_t v = 0;
+    for (unsigned long long spin = 0;; ++spin) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if (v >= epoch) break;
+        if (spin > (1ull << 31)) __trap();
+    }
+}
+
 struct DistLayout {
     WsLayout L;
     size_t dzr1, dzr2, recv1, recv2, parts, total;
@@ -1925,6 +1954,9 @@ struct abt_comm {
     int world, rank;
     cudaStream_t cs, cs2;     // one communication stream per communicator
     cudaEvent_t ev[12];
+    cudaStream_t ce[4];       // copy-engine exchange: peer copies are spread over four streams
+    cudaEvent_t ce_ev[2][4];  // [view][stream]
+    cudaEvent_t ce_ready;
 };
 
 extern "C" int abt_comm_unique_id(void* id256) {
@@ -1945,9 +1977,9 @@ extern "C" int abt_comm_create(int world, int rank, const void* id256, abt_comm*
     c->world = world; c->rank = rank;
     ncclUniqueId id[2];
     std::memcpy(id, id256, sizeof(id));
-    // The collectives run beside the persistent tensor-core kernels, which leave g_reserve_sms SMs free for them (a CTA of bt_umma_kernel
-    // owns a whole SM's registers): cap the CTAs NCCL may use so that its kernels always fit there instead of queueing behind a GEMM
-    // (that queueing, with the ranks skewed against each other, was the 0.9 / 1.6 ms bimodal step of round 1).
+    // The collectives run beside the persistent tensor-core kernels, which leave g_dist_reserve_sms SMs free for them (a CTA of
+    // bt_umma_kernel owns a whole SM's registers, so a collective launched behind a GEMM otherwise waits for it to end).  An optional
+    // CTA cap for NCCL exists (key 13) but is off: it slows the all-to-alls far more than it helps.
     ncclResult_t r;
     if (g_nccl.CommInitRankConfig != nullptr && g_comm_max_ctas > 0) {
         ncclConfig_t cfg1 = NCCL_CONFIG_INITIALIZER, cfg2 = NCCL_CONFIG_INITIALIZER;
@@ -1968,6 +2000,9 @@ extern "C" int abt_comm_create(int world, int rank, const void* id256, abt_comm*
         return set_error(ABT_ERR_CUDA, "cudaStreamCreate failed");
     }
     for (auto& e : c->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto& s : c->ce) cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi);
+    for (auto& v : c->ce_ev) for (auto& e : v) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ce_ready, cudaEventDisableTiming);
     *out = c;
     return 0;
 }
@@ -1977,10 +2012,21 @@ extern "C" int abt_comm_destroy(abt_comm* c) {
     cudaStreamSynchronize(c->cs);
     cudaStreamSynchronize(c->cs2);
     for (auto& e : c->ev) cudaEventDestroy(e);
+    for (auto& s : c->ce) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    for (auto& v : c->ce_ev) for (auto& e : v) cudaEventDestroy(e);
+    cudaEventDestroy(c->ce_ready);
     cudaStreamDestroy(c->cs);
     cudaStreamDestroy(c->cs2);
     if (g_nccl.ok) { g_nccl.CommDestroy(c->comm); g_nccl.CommDestroy(c->comm2); }
     delete c;
+    return 0;
+}
+
+extern "C" int abt_bt_dist_exchange_bytes(int n_local, int world, int n_dims, size_t* bytes) {
+    if (bytes == nullptr) return set_error(ABT_ERR_ARG, "bytes is null");
+    if (world < 1 || world > kMaxPeers || n_dims % world != 0) return set_error(ABT_ERR_ARG, "world must be in [1, 16] and divide n_dims");
+    if (int rc = check_dist(n_local, world, n_dims, n_dims / world)) return rc;
+    *bytes = exch_layout(n_local, world, n_dims).total;
     return 0;
 }
 
@@ -2033,8 +2079,43 @@ extern "C" int abt_bt_dist_step(const abt_bt_dist_step_args* a, abt_comm* c, abt
 
     enum { E_P0, E_P1, E_N, E_A, E_B, E_S, E_C3, E_C, E_G1, E_D, E_G2, E_E };
     auto chain = [](cudaStream_t from, cudaEvent_t ev, cudaStream_t to) { cudaEventRecord(ev, from); cudaStreamWaitEvent(to, ev, 0); };
-    __half* zh1 = reinterpret_cast<__half*>(ws + L.zh1);
-    __half* zh2 = reinterpret_cast<__half*>(ws + L.zh2);
+    // copy-engine exchange: the gather buffers live in this rank's peer-mapped exchange buffer (double-buffered by the epoch's parity)
+    const bool ce = a->exchange_peers != nullptr && world > 1;
+    const ExchLayout xl = exch_layout(N, world, D);
+    if (ce) {
+        if (world > kMaxPeers) return set_error(ABT_ERR_ARG, "copy-engine exchange supports at most %d ranks", kMaxPeers);
+        if (a->exchange_bytes < xl.total) return set_error(ABT_ERR_ARG, "exchange buffers too small: %zu < %zu", a->exchange_bytes, xl.total);
+        if (a->exchange_epoch == 0) return set_error(ABT_ERR_ARG, "exchange_epoch starts at 1");
+        for (int q = 0; q < world; ++q)
+            if (a->exchange_peers[q] == nullptr || (reinterpret_cast<uintptr_t>(a->exchange_peers[q]) & 255) != 0)
+                return set_error(ABT_ERR_ARG, "exchange buffer of rank %d is null or not 256-byte aligned", q);
+    }
+    const size_t par_off = ce ? (size_t)(a->exchange_epoch & 1u) * 2 * xl.view_bytes : 0;
+    uint8_t* xbase = ce ? static_cast<uint8_t*>(a->exchange_peers[rank]) : nullptr;
+    __half* zh1 = ce ? reinterpret_cast<__half*>(xbase + par_off) : reinterpret_cast<__half*>(ws + L.zh1);
+    __half* zh2 = ce ? reinterpret_cast<__half*>(xbase + par_off + xl.view_bytes) : reinterpret_cast<__half*>(ws + L.zh2);
+    const void* zo1 = ce ? zh1 : nullptr;      // gather-buffer overrides of the row-block calls
+    const void* zo2 = ce ? zh2 : nullptr;
+    // all-gather of one view: NCCL, or R - 1 peer copies on the copy engines (view: 0 = zh1, 1 = zh2); completion -> `done` events
+    auto gather_view = [&](int view) -> int {
+        __half* mine = view == 0 ? zh1 : zh2;
+        if (!ce) {
+            ABT_NCCL_OK(g_nccl.AllGather(mine + (size_t)rank * N * D, mine, (size_t)N * D, ncclFloat16, c->comm, c->cs));
+            return 0;
+        }
+        const size_t slot_bytes = (size_t)N * D * 2, voff = par_off + (view == 0 ? 0 : xl.view_bytes);
+        for (int i = 1; i < world; ++i) {
+            const int q = (rank + i) % world, k = (i - 1) & 3;
+            cudaMemcpyAsync(reinterpret_cast<uint8_t*>(mine) + (size_t)q * slot_bytes,
+                            static_cast<const uint8_t*>(a->exchange_peers[q]) + voff + (size_t)q * slot_bytes, slot_bytes, cudaMemcpyDeviceToDevice, c->ce[k]);
+        }
+        for (int k = 0; k < 4; ++k) cudaEventRecord(c->ce_ev[view][k], c->ce[k]);
+        return 0;
+    };
+    auto wait_view = [&](int view, cudaEvent_t nccl_ev) {
+        if (!ce) { cudaStreamWaitEvent(st, nccl_ev, 0); return; }
+        for (int k = 0; k < 4; ++k) cudaStreamWaitEvent(st, c->ce_ev[view][k], 0);
+    };
     double* parts = reinterpret_cast<double*>(ws + dl.parts);
     const int vec_per_slice = (int)((size_t)Dr * esz / 16);
     const size_t nvec = (size_t)world * N * vec_per_slice;
@@ -2049,8 +2130,19 @@ extern "C" int abt_bt_dist_step(const abt_bt_dist_step_args* a, abt_comm* c, abt
     ABT_NCCL_OK(g_nccl.AllGather(ws + L.pack_local, ws + L.pack_all, 7 * (size_t)D, ncclFloat32, c->comm2, c->cs2));
     chain(c->cs2, c->ev[E_P1], st);
     // 2. global statistics + standardised local rows (+ the column-blocked copy of view 1)
-    if (int rc = abt_bt_dist_normalize(a->z1, a->z2, a->dtype, N, world, rank, D, Dr, a->eps, a->momentum, a->running_mean, a->running_var,
-                                       a->workspace, stream_)) return rc;
+    if (a->dtype == ABT_DTYPE_BF16) dist_normalize<__nv_bfloat16>(a->z1, a->z2, N, world, rank, D, Dr, a->eps, a->momentum, a->running_mean, a->running_var, ws, L, st, ce ? zh1 : nullptr, ce ? zh2 : nullptr);
+    else if (a->dtype == ABT_DTYPE_F16) dist_normalize<__half>(a->z1, a->z2, N, world, rank, D, Dr, a->eps, a->momentum, a->running_mean, a->running_var, ws, L, st, ce ? zh1 : nullptr, ce ? zh2 : nullptr);
+    else dist_normalize<float>(a->z1, a->z2, N, world, rank, D, Dr, a->eps, a->momentum, a->running_mean, a->running_var, ws, L, st, ce ? zh1 : nullptr, ce ? zh2 : nullptr);
+    if (ce) {
+        // every rank's rows are in its own exchange buffer once all ranks have passed this barrier; by the parity argument (see the
+        // header) it also guarantees that nobody still reads the buffers this step is about to overwrite two steps from now
+        PeerFlags pf{};
+        for (int q = 0; q < world; ++q) pf.f[q] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(a->exchange_peers[q]) + xl.flags);
+        ce_barrier_kernel<<<1, 32, 0, st>>>(pf, world, rank, a->exchange_epoch);
+        count_launch();
+        cudaEventRecord(c->ce_ready, st);
+        for (int k = 0; k < 4; ++k) cudaStreamWaitEvent(c->ce[k], c->ce_ready, 0);
+    }
     cudaEventRecord(c->ev[E_N], st);
     cudaStreamWaitEvent(c->cs, c->ev[E_N], 0);
     cudaStreamWaitEvent(c->cs2, c->ev[E_N], 0);
@@ -2061,30 +2153,30 @@ extern "C" int abt_bt_dist_step(const abt_bt_dist_step_args* a, abt_comm* c, abt
         // Exchange schedule.  View 2 is gathered first; CORR (A = the view-1 columns of this rank's dimensions, which arrive by a small
         // all-to-all) and the dz1 GEMM need nothing else and run while view 1 is still crossing NVLink.  The transposed block of C comes
         // from an all-to-all of C blocks instead of a second CORR pass (6 N D^2 executed FLOP per rank, as on one GPU).
-        ABT_NCCL_OK(g_nccl.AllGather(zh2 + (size_t)rank * N * D, zh2, (size_t)N * D, ncclFloat16, c->comm, c->cs));
+        if (int rc = gather_view(1)) return rc;
         cudaEventRecord(c->ev[E_A], c->cs);
-        ABT_NCCL_OK(g_nccl.AllGather(zh1 + (size_t)rank * N * D, zh1, (size_t)N * D, ncclFloat16, c->comm, c->cs));
+        if (int rc = gather_view(0)) return rc;
         cudaEventRecord(c->ev[E_B], c->cs);
         if (int rc = all_to_all(c, c->comm2, ws + L.zh1_blk, ws + L.zs1, (size_t)N * Dr, ABT_DTYPE_F16, c->cs2)) return rc;
         cudaEventRecord(c->ev[E_S], c->cs2);
         if (a->overlap_cb != nullptr) a->overlap_cb(a->overlap_user);
-        cudaStreamWaitEvent(st, c->ev[E_A], 0);
+        wait_view(1, c->ev[E_A]);
         cudaStreamWaitEvent(st, c->ev[E_S], 0);
         if (int rc = dist_rows_call(a->dtype, N, world, D, R0, Dr, a->alpha, a->lambda, a->hsic, a->grad_scale, need, 8 | 1, parts, ws + dl.dzr1,
-                                    ws + dl.dzr2, a->workspace, st, true)) return rc;
+                                    ws + dl.dzr2, a->workspace, st, true, zo1, zo2)) return rc;
         chain(st, c->ev[E_C3], c->cs2);
         if (int rc = all_to_all(c, c->comm2, ws + L.c1, ws + L.c2, (size_t)Dr * Dr, ABT_DTYPE_F16, c->cs2)) return rc;      // C[rows_r, cols_q] -> rank q
         cudaEventRecord(c->ev[E_C], c->cs2);
         if (int rc = dist_rows_call(a->dtype, N, world, D, R0, Dr, a->alpha, a->lambda, a->hsic, a->grad_scale, need, 8 | 2, parts, ws + dl.dzr1,
-                                    ws + dl.dzr2, a->workspace, st, true)) return rc;
+                                    ws + dl.dzr2, a->workspace, st, true, zo1, zo2)) return rc;
         chain(st, c->ev[E_G1], c->cs2);
         if (int rc = all_to_all(c, c->comm2, ws + dl.dzr1, ws + dl.recv1, slice, a->dtype, c->cs2)) return rc;
         ABT_NCCL_OK(g_nccl.AllReduce(parts, parts, 3, ncclFloat64, ncclSum, c->comm2, c->cs2));
         cudaEventRecord(c->ev[E_D], c->cs2);
-        cudaStreamWaitEvent(st, c->ev[E_B], 0);
+        wait_view(0, c->ev[E_B]);
         cudaStreamWaitEvent(st, c->ev[E_C], 0);
         if (int rc = dist_rows_call(a->dtype, N, world, D, R0, Dr, a->alpha, a->lambda, a->hsic, a->grad_scale, need, 8 | 4, parts, ws + dl.dzr1,
-                                    ws + dl.dzr2, a->workspace, st, true)) return rc;
+                                    ws + dl.dzr2, a->workspace, st, true, zo1, zo2)) return rc;
         chain(st, c->ev[E_G2], c->cs2);
         if (int rc = all_to_all(c, c->comm2, ws + dl.dzr2, ws + dl.recv2, slice, a->dtype, c->cs2)) return rc;
         cudaEventRecord(c->ev[E_E], c->cs2);
@@ -2096,16 +2188,22 @@ extern "C" int abt_bt_dist_step(const abt_bt_dist_step_args* a, abt_comm* c, abt
     } else {
         // Plain schedule: both views gathered, then the row block of C and of C^T (second CORR pass); the all-to-all of dz1 overlaps
         // the dz2 GEMM
-        ABT_NCCL_OK(g_nccl.GroupStart());
-        ABT_NCCL_OK(g_nccl.AllGather(zh1 + (size_t)rank * N * D, zh1, (size_t)N * D, ncclFloat16, c->comm, c->cs));
-        ABT_NCCL_OK(g_nccl.AllGather(zh2 + (size_t)rank * N * D, zh2, (size_t)N * D, ncclFloat16, c->comm, c->cs));
-        ABT_NCCL_OK(g_nccl.GroupEnd());
+        if (ce) {
+            if (int rc = gather_view(0)) return rc;
+            if (int rc = gather_view(1)) return rc;
+        } else {
+            ABT_NCCL_OK(g_nccl.GroupStart());
+            ABT_NCCL_OK(g_nccl.AllGather(zh1 + (size_t)rank * N * D, zh1, (size_t)N * D, ncclFloat16, c->comm, c->cs));
+            ABT_NCCL_OK(g_nccl.AllGather(zh2 + (size_t)rank * N * D, zh2, (size_t)N * D, ncclFloat16, c->comm, c->cs));
+            ABT_NCCL_OK(g_nccl.GroupEnd());
+        }
         cudaEventRecord(c->ev[E_A], c->cs);
         if (a->overlap_cb != nullptr) a->overlap_cb(a->overlap_user);
-        cudaStreamWaitEvent(st, c->ev[E_A], 0);
+        wait_view(0, c->ev[E_A]);
+        wait_view(1, c->ev[E_A]);
         const int phase_a = need == 3 ? 1 : 0;
         if (int rc = dist_rows_call(a->dtype, N, world, D, R0, Dr, a->alpha, a->lambda, a->hsic, a->grad_scale, need, phase_a, parts, ws + dl.dzr1,
-                                    ws + dl.dzr2, a->workspace, st)) return rc;
+                                    ws + dl.dzr2, a->workspace, st, false, zo1, zo2)) return rc;
         chain(st, c->ev[E_G1], c->cs2);
         if (need & 1) { if (int rc = all_to_all(c, c->comm2, ws + dl.dzr1, ws + dl.recv1, slice, a->dtype, c->cs2)) return rc; }
         if (need == 2) { if (int rc = all_to_all(c, c->comm2, ws + dl.dzr2, ws + dl.recv2, slice, a->dtype, c->cs2)) return rc; }
@@ -2113,7 +2211,7 @@ extern "C" int abt_bt_dist_step(const abt_bt_dist_step_args* a, abt_comm* c, abt
         cudaEventRecord(c->ev[E_D], c->cs2);
         if (need == 3) {
             if (int rc = dist_rows_call(a->dtype, N, world, D, R0, Dr, a->alpha, a->lambda, a->hsic, a->grad_scale, need, 2, parts, ws + dl.dzr1,
-                                        ws + dl.dzr2, a->workspace, st)) return rc;
+                                        ws + dl.dzr2, a->workspace, st, false, zo1, zo2)) return rc;
             chain(st, c->ev[E_G2], c->cs2);
             if (int rc = all_to_all(c, c->comm2, ws + dl.dzr2, ws + dl.recv2, slice, a->dtype, c->cs2)) return rc;
             cudaEventRecord(c->ev[E_E], c->cs2);

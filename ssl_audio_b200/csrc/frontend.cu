@@ -150,7 +150,9 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
         const int fb = fa + 1;
         const bool any_valid = (f_first + fa) < a.n_frames_total && (tile * kTileFrames + fa) < a.n_frames_out;
         if (any_valid) {   // warp-uniform
-            float re[32], im[32];
+            // A complex value is ONE 64-bit register pair (re, im) and all arithmetic runs on Blackwell's packed fp32x2 pipe (FADD2 /
+            // FMUL2 / FFMA2; half swaps and signs are operand modifiers): about half the FP instructions of the scalar form.
+            unsigned long long x[32];
             // frame a -> real part, frame b -> imaginary part; lane = n1, register = n2, n = n1 + 32 n2
             const float* xa = s_x + fa * a.hop;
             const float* xb = s_x + fb * a.hop;
@@ -158,42 +160,44 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
             for (int n2 = 0; n2 < 32; ++n2) {
                 const int n = lane + 32 * n2;
                 const float w = __ldg(a.window + n);
-                re[n2] = xa[n] * w;
-                im[n2] = xb[n] * w;
+                x[n2] = c2_mul(c2_pack(xa[n], xb[n]), c2_pack(w, w));
             }
-            fft32(re, im);   // register p: Y[n1 = lane][k2 = bitrev(p)]
+            fft32p(x);   // register p: Y[n1 = lane][k2 = bitrev(p)]
             // twiddle W1024^(n1 k2) and transpose through shared memory (64-bit accesses, conflict-free with the 33-stride)
             __syncwarp();
+            unsigned long long* sc64 = reinterpret_cast<unsigned long long*>(sc);
 #pragma unroll
             for (int p = 0; p < 32; ++p) {
                 const int k2 = bitrev5(p);
                 const float2 w = __ldg(a.twiddle + k2 * 32 + lane);
-                sc[lane * 33 + k2] = make_float2(re[p] * w.x - im[p] * w.y, re[p] * w.y + im[p] * w.x);
+                sc64[lane * 33 + k2] = c2_cmul(x[p], c2_pack(w.x, w.y));
             }
             __syncwarp();
 #pragma unroll
-            for (int n1 = 0; n1 < 32; ++n1) {     // lane = k2, register = n1
-                const float2 v = sc[n1 * 33 + lane];
-                re[n1] = v.x;
-                im[n1] = v.y;
-            }
-            fft32(re, im);   // register p: Z[32 k1 + k2], k1 = bitrev(p), k2 = lane
+            for (int n1 = 0; n1 < 32; ++n1) x[n1] = sc64[n1 * 33 + lane];     // lane = k2, register = n1
+            fft32p(x);   // register p: Z[32 k1 + k2], k1 = bitrev(p), k2 = lane
             __syncwarp();    // all lanes have read the transposed tile: the scratch can hold the power spectra now
             // Z = A + i B with A, B the (Hermitian) spectra of the two real frames: the partner bin Z[1024 - k] lives in lane
-            // (32 - lane) & 31, register k1' = 31 - k1 (lane 0: its own register (32 - k1) & 31) -> one shuffle per value
+            // (32 - lane) & 31, register k1' = 31 - k1 (lane 0: its own register (32 - k1) & 31) -> one 64-bit shuffle per value.
+            //   2 A[k] = (re + qr, im - qi),  2 B[k] = (im + qi, qr - re);  with U = Z + Q = (2 Re A, 2 Re B) and
+            //   V = (im - qi, qr - re) = swap(Z) (+, -) + swap(Q) (-, +) = (2 Im A, 2 Im B):  (4 |A|^2, 4 |B|^2) = U o U + V o V
             const int lp = (32 - lane) & 31;
 #pragma unroll
             for (int k1 = 0; k1 < 16; ++k1) {
                 const int p = bitrev5(k1), pq = bitrev5(31 - k1), pq0 = bitrev5((32 - k1) & 31);
-                float qr = __shfl_sync(0xffffffffu, re[pq], lp), qi = __shfl_sync(0xffffffffu, im[pq], lp);
-                if (lane == 0) { qr = re[pq0]; qi = im[pq0]; }
-                const float ar = re[p] + qr, ai = im[p] - qi;     // 2 A[k]
-                const float br = im[p] + qi, bi = qr - re[p];     // 2 B[k]
-                sc[32 * k1 + lane] = make_float2(ar * ar + ai * ai, br * br + bi * bi);      // 4 |A|^2, 4 |B|^2: the 1/4 lives in the mel weights
+                unsigned long long qv = __shfl_sync(0xffffffffu, x[pq], lp);
+                if (lane == 0) qv = x[pq0];
+                float zr, zi, qr, qi;
+                c2_unpack(x[p], zr, zi);
+                c2_unpack(qv, qr, qi);
+                const unsigned long long u = c2_add(x[p], qv);
+                const unsigned long long v = c2_add(c2_pack(zi, -zr), c2_pack(-qi, qr));
+                sc64[32 * k1 + lane] = c2_fma(u, u, c2_mul(v, v));      // 4 |A|^2, 4 |B|^2: the 1/4 lives in the mel weights
             }
             if (lane == 0) {   // k = 512 pairs with itself: Z[512] = A[512] + i B[512] with both real
                 const int p16 = bitrev5(16);
-                sc[512] = make_float2(4.0f * re[p16] * re[p16], 4.0f * im[p16] * im[p16]);
+                const unsigned long long z = x[p16];
+                sc64[512] = c2_mul(c2_mul(z, z), c2_pack(4.0f, 4.0f));
             }
         }
         // ---- sparse mel projection of the round's 16 frames, across the warps: thread = (frame f, band group g).  The 16 lanes of a

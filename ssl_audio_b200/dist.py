@@ -163,6 +163,7 @@ class NativeStep:
 
     _comms = {}
     _ws = {}
+    _exch = {}          # (device, n, world, d) -> [symmetric buffer, handle, ctypes pointer array, nbytes, epoch] or None (unavailable)
 
     @classmethod
     def comm(cls, group, device):
@@ -192,6 +193,38 @@ class NativeStep:
         return cls._ws[key]
 
     @classmethod
+    def exchange(cls, group, device, n, world, d):
+        """Peer-mapped exchange buffers for the copy-engine embedding gather (torch symmetric memory): every rank allocates one buffer,
+        the rendezvous maps all of them into every process.  Returns None when symmetric memory is unavailable (-> NCCL all-gathers) or
+        switched off (ABT_DIST_CE=0).  Collective: every rank must call it with the same arguments."""
+        key = (id(group) if group is not None else 0, device.index, n, world, d)
+        if key in cls._exch:
+            return cls._exch[key]
+        entry = None
+        if os.environ.get("ABT_DIST_CE", "1") != "0" and world <= 16:
+            ok = torch.zeros(1, dtype=torch.int32, device=device)
+            try:
+                import torch.distributed._symmetric_memory as symm
+                nbytes = C.c_size_t()
+                _lib.check(_lib.load().abt_bt_dist_exchange_bytes(n, world, d, C.byref(nbytes)))
+                pg = group if group is not None else dist.group.WORLD
+                buf = symm.empty(nbytes.value, dtype=torch.uint8, device=device)
+                hdl = symm.rendezvous(buf, pg.group_name)
+                buf.zero_()
+                ptrs = (C.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+                entry = [buf, hdl, ptrs, int(nbytes.value), 0]
+                ok.fill_(1)
+            except Exception as e:          # no symmetric memory on this system / build: keep the NCCL gathers
+                if dist.get_rank(group) == 0:
+                    print(f"ssl_audio_b200: copy-engine exchange unavailable ({type(e).__name__}: {e}); using NCCL all-gathers", flush=True)
+            torch.cuda.synchronize(device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)          # all or nothing; also the barrier after the zero-fill
+            if int(ok.item()) == 0:
+                entry = None
+        cls._exch[key] = entry
+        return entry
+
+    @classmethod
     def run(cls, z1, z2, alpha, lmbda, hsic, eps, momentum, running_mean, running_var, need_dz1, need_dz2, grad_scale, group, overlap_hook):
         lib = _lib.load()
         dev = z1.device
@@ -217,6 +250,12 @@ class NativeStep:
         a.workspace_bytes = nbytes
         cb = _lib.OVERLAP_CB(lambda _user: overlap_hook()) if overlap_hook is not None else _lib.OVERLAP_CB()
         a.overlap_cb = cb
+        ex = cls.exchange(group, dev, n, world, d)
+        if ex is not None:
+            ex[4] += 1
+            a.exchange_peers = C.cast(ex[2], C.c_void_p)
+            a.exchange_bytes = ex[3]
+            a.exchange_epoch = ex[4]
         with torch.cuda.device(dev):
             _lib.check(lib.abt_bt_dist_step(C.byref(a), comm, torch.cuda.current_stream(dev).cuda_stream))
         del cb
