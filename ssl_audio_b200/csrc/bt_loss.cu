@@ -294,73 +294,98 @@ __global__ void __launch_bounds__(kColThreads) bt_normalize_kernel(const T* __re
 }
 
 // ------------------------------------------------------------------------------------------
-// 1s. small batches (N <= 128, the one-launch objective): statistics AND standardisation in ONE pass.  A block owns 64 columns,
-//     keeps its N x 64 slice of both views in registers (thread = row group x column pair, <= 16 rows each), reduces the shifted
-//     sums through shared memory, and writes the fp16 standardised embeddings from the registers: z is read once, no partial-sum
-//     round trip, no arrival counters.  The on-diagonal loss leaves as one float per block (summed by the consumer), and block 0
-//     clears the accumulators of the tensor-core kernel, so the call needs no memset either.
+// 1s. small batches (N <= 128, the one-launch objective): statistics AND standardisation in ONE pass.  A block owns 32 columns
+//     (half an operand tile; 256 blocks at D = 8192, two resident per SM) and keeps its N x 32 slice of both views in registers:
+//     a thread holds one 16-byte piece (8 columns) of up to 2 rows of each view, so z is read with 16-byte loads and the
+//     standardised rows leave as the 16-byte pieces of the tile image.  The shifted sums are reduced through shared memory in two
+//     steps; z is read once, no partial-sum round trip, no arrival counters.  The on-diagonal loss leaves as one float per block
+//     (summed by the consumer), and block 0 clears the accumulators of the tensor-core kernel, so the call needs no memset either.
 // ------------------------------------------------------------------------------------------
-constexpr int kSmallCols = 64;
+constexpr int kSmallCols = 64;                     // columns of one tile image (one operand tile of the tensor-core kernel)
+constexpr int kSmallBlockCols = 32;                // columns per block
+constexpr int kSmallRowLanes = 64;                 // 8 warps x 8 row lanes; row n is held by row lane n % 64, slot n / 64
 template <typename T>
-__global__ void __launch_bounds__(kColThreads) bt_stat_norm_small_kernel(const T* __restrict__ z1, const T* __restrict__ z2, int N, int D, float eps,
-                                                                         float momentum, float* __restrict__ stats, float* __restrict__ running_mean,
-                                                                         float* __restrict__ running_var, __half* __restrict__ zh1,
-                                                                         __half* __restrict__ zh2, float* __restrict__ ondiag_part,
-                                                                         double* __restrict__ loss_acc, unsigned int* __restrict__ done_counter,
-                                                                         int tile_img_rows) {
-    __shared__ float red[kRowGroups][10][32];
-    __shared__ float colstat[4][kSmallCols];
-    __shared__ float on_red[2];
+__global__ void __launch_bounds__(kColThreads, 2) bt_stat_norm_small_kernel(const T* __restrict__ z1, const T* __restrict__ z2, int N, int D, float eps,
+                                                                            float momentum, float* __restrict__ stats, float* __restrict__ running_mean,
+                                                                            float* __restrict__ running_var, __half* __restrict__ zh1,
+                                                                            __half* __restrict__ zh2, float* __restrict__ ondiag_part,
+                                                                            double* __restrict__ loss_acc, unsigned int* __restrict__ done_counter,
+                                                                            int tile_img_rows) {
+    // red[row lane][sum k][position]: position h * 16 + piece * 4 + j holds local column piece * 8 + h * 4 + j (16-byte stores)
+    __shared__ __align__(16) float red[kSmallRowLanes][5][kSmallBlockCols];
+    __shared__ float red2[8][5][kSmallBlockCols];
+    __shared__ __align__(16) float colstat[4][kSmallBlockCols];
     const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    const int col = blockIdx.x * kSmallCols + lane * 2;           // D is a multiple of 64: always in range
+    const int piece = lane & 3, rl = rg * 8 + (lane >> 2);        // 16-byte piece of this block's half tile row; row lane 0..63
+    const int col = blockIdx.x * kSmallBlockCols + piece * 8;     // D is a multiple of 64: always in range
     griddep_launch_dependents();                                  // the tensor-core kernel may set itself up while this one runs
     if (blockIdx.x == 0 && threadIdx.x == 0) { loss_acc[0] = 0.0; loss_acc[1] = 0.0; *done_counter = 0u; }
-    const float2 k1 = Ld2<T>::ld(z1 + col), k2 = Ld2<T>::ld(z2 + col);
-    const float sh1x = in_round<T>(k1.x), sh1y = in_round<T>(k1.y), sh2x = in_round<T>(k2.x), sh2y = in_round<T>(k2.y);
-    float va[16][2], vb[16][2];
-    float acc[10];
+    float sh1[8], sh2[8];
+    load8<T>(z1 + col, sh1); load8<T>(z2 + col, sh2);
 #pragma unroll
-    for (int k = 0; k < 10; ++k) acc[k] = 0.f;
+    for (int c = 0; c < 8; ++c) { sh1[c] = in_round<T>(sh1[c]); sh2[c] = in_round<T>(sh2[c]); }
+    float va[2][8], vb[2][8];
+    float acc[5][8];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int n = rg + kRowGroups * k;
-        float2 a = make_float2(sh1x, sh1y), b = make_float2(sh2x, sh2y);
-        if (n < N) { a = Ld2<T>::ld(z1 + (size_t)n * D + col); b = Ld2<T>::ld(z2 + (size_t)n * D + col); }
-        va[k][0] = in_round<T>(a.x) - sh1x; va[k][1] = in_round<T>(a.y) - sh1y;       // shifted data (rows >= N contribute zero)
-        vb[k][0] = in_round<T>(b.x) - sh2x; vb[k][1] = in_round<T>(b.y) - sh2y;
+    for (int k = 0; k < 5; ++k)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            acc[c] += va[k][c]; acc[2 + c] = fmaf(va[k][c], va[k][c], acc[2 + c]);
-            acc[4 + c] += vb[k][c]; acc[6 + c] = fmaf(vb[k][c], vb[k][c], acc[6 + c]);
-            acc[8 + c] = fmaf(va[k][c], vb[k][c], acc[8 + c]);
+        for (int c = 0; c < 8; ++c) acc[k][c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int n = rl + kSmallRowLanes * k;
+        if (n < N) { load8<T>(z1 + (size_t)n * D + col, va[k]); load8<T>(z2 + (size_t)n * D + col, vb[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int n = rl + kSmallRowLanes * k;
+        if (n < N) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {                          // shifted data
+                va[k][c] = in_round<T>(va[k][c]) - sh1[c]; vb[k][c] = in_round<T>(vb[k][c]) - sh2[c];
+                acc[0][c] += va[k][c]; acc[1][c] = fmaf(va[k][c], va[k][c], acc[1][c]);
+                acc[2][c] += vb[k][c]; acc[3][c] = fmaf(vb[k][c], vb[k][c], acc[3][c]);
+                acc[4][c] = fmaf(va[k][c], vb[k][c], acc[4][c]);
+            }
         }
     }
 #pragma unroll
-    for (int k = 0; k < 10; ++k) red[rg][k][lane] = acc[k];
+    for (int k = 0; k < 5; ++k) {
+        *reinterpret_cast<float4*>(&red[rl][k][piece * 4]) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+        *reinterpret_cast<float4*>(&red[rl][k][16 + piece * 4]) = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+    }
     __syncthreads();
-    float on = 0.f;
-    if (threadIdx.x < kSmallCols) {
-        const int c = threadIdx.x & 1, ln = threadIdx.x >> 1, gc = blockIdx.x * kSmallCols + threadIdx.x;     // column ln * 2 + c
+    {   // step 1: thread (position, eighth) folds 8 row lanes of all five sums
+        const int pos = threadIdx.x & 31, part = threadIdx.x >> 5;
         float t[5] = {0, 0, 0, 0, 0};
 #pragma unroll
-        for (int g = 0; g < kRowGroups; ++g)
+        for (int g = 0; g < 8; ++g)
 #pragma unroll
-            for (int k = 0; k < 5; ++k) t[k] += red[g][2 * k + c][ln];
+            for (int k = 0; k < 5; ++k) t[k] += red[part * 8 + g][k][pos];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) red2[part][k][pos] = t[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < kSmallBlockCols) {
+        const int lc = threadIdx.x, gc = blockIdx.x * kSmallBlockCols + lc;                   // local / global column
+        const int pos = ((lc >> 2) & 1) * 16 + (lc >> 3) * 4 + (lc & 3);
+        float t[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            t[k] = ((red2[0][k][pos] + red2[1][k][pos]) + (red2[2][k][pos] + red2[3][k][pos])) + ((red2[4][k][pos] + red2[5][k][pos]) + (red2[6][k][pos] + red2[7][k][pos]));
         const float invN = 1.0f / (float)N;
         const float2 f1 = Ld2<T>::ld(z1 + (gc & ~1)), f2 = Ld2<T>::ld(z2 + (gc & ~1));
-        const float sh1 = in_round<T>(c ? f1.y : f1.x), sh2 = in_round<T>(c ? f2.y : f2.x);
+        const float s1 = in_round<T>((lc & 1) ? f1.y : f1.x), s2 = in_round<T>((lc & 1) ? f2.y : f2.x);
         const float m1 = t[0] * invN, m2 = t[2] * invN;
         const float var1 = fmaxf(t[1] * invN - m1 * m1, 0.f), var2 = fmaxf(t[3] * invN - m2 * m2, 0.f);
         const float cov = t[4] * invN - m1 * m2;
-        const float mu1 = sh1 + m1, mu2 = sh2 + m2;
+        const float mu1 = s1 + m1, mu2 = s2 + m2;
         const float r1 = rsqrtf(var1 + eps), r2 = rsqrtf(var2 + eps);
         const float r1n = r1 * (1.5f - 0.5f * (var1 + eps) * r1 * r1), r2n = r2 * (1.5f - 0.5f * (var2 + eps) * r2 * r2);
         const float cd = cov * r1n * r2n;
         stats[S_MU1 * D + gc] = mu1; stats[S_R1 * D + gc] = r1n;
         stats[S_MU2 * D + gc] = mu2; stats[S_R2 * D + gc] = r2n;
         stats[S_CDIAG * D + gc] = cd;
-        colstat[0][threadIdx.x] = m1; colstat[1][threadIdx.x] = r1n; colstat[2][threadIdx.x] = m2; colstat[3][threadIdx.x] = r2n;
-        on = (cd - 1.0f) * (cd - 1.0f);
+        colstat[0][lc] = m1; colstat[1][lc] = r1n; colstat[2][lc] = m2; colstat[3][lc] = r2n;
         if (running_mean != nullptr) {
             const float unb = (N > 1) ? (float)N / (float)(N - 1) : 1.0f;
             float rm = running_mean[gc], rv = running_var[gc];
@@ -368,47 +393,51 @@ __global__ void __launch_bounds__(kColThreads) bt_stat_norm_small_kernel(const T
             rm = (1.f - momentum) * rm + momentum * mu2; rv = (1.f - momentum) * rv + momentum * var2 * unb;
             running_mean[gc] = rm; running_var[gc] = rv;
         }
-        on = warp_sum(on);
-        if (lane == 0) on_red[threadIdx.x >> 5] = on;
+        const float on = warp_sum((cd - 1.0f) * (cd - 1.0f));      // kSmallBlockCols == 32: exactly warp 0
+        if (lane == 0) ondiag_part[blockIdx.x] = on;
     }
     __syncthreads();
-    if (threadIdx.x == 0) ondiag_part[blockIdx.x] = on_red[0] + on_red[1];
     // standardise from the registers (the values are already shifted: subtract the shifted mean)
-    const float m1x = colstat[0][lane * 2], m1y = colstat[0][lane * 2 + 1], r1x = colstat[1][lane * 2], r1y = colstat[1][lane * 2 + 1];
-    const float m2x = colstat[2][lane * 2], m2y = colstat[2][lane * 2 + 1], r2x = colstat[3][lane * 2], r2y = colstat[3][lane * 2 + 1];
-    if (tile_img_rows == 0) {
+    float m1c[8], r1c[8], m2c[8], r2c[8];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int n = rg + kRowGroups * k;
-            if (n < N) {
-                Ld2<__half>::st(zh1 + (size_t)n * D + col, (va[k][0] - m1x) * r1x, (va[k][1] - m1y) * r1y);
-                Ld2<__half>::st(zh2 + (size_t)n * D + col, (vb[k][0] - m2x) * r2x, (vb[k][1] - m2y) * r2y);
-            }
-        }
-        return;
+    for (int h = 0; h < 2; ++h) {
+        const float4 a = *reinterpret_cast<const float4*>(&colstat[0][piece * 8 + 4 * h]), b = *reinterpret_cast<const float4*>(&colstat[1][piece * 8 + 4 * h]);
+        const float4 e = *reinterpret_cast<const float4*>(&colstat[2][piece * 8 + 4 * h]), f = *reinterpret_cast<const float4*>(&colstat[3][piece * 8 + 4 * h]);
+        m1c[4 * h] = a.x; m1c[4 * h + 1] = a.y; m1c[4 * h + 2] = a.z; m1c[4 * h + 3] = a.w;
+        r1c[4 * h] = b.x; r1c[4 * h + 1] = b.y; r1c[4 * h + 2] = b.z; r1c[4 * h + 3] = b.w;
+        m2c[4 * h] = e.x; m2c[4 * h + 1] = e.y; m2c[4 * h + 2] = e.z; m2c[4 * h + 3] = e.w;
+        r2c[4 * h] = f.x; r2c[4 * h + 1] = f.y; r2c[4 * h + 2] = f.z; r2c[4 * h + 3] = f.w;
     }
-    // Tile-image layout: this block's 64 columns are ONE operand tile of the tensor-core kernel.  It is written exactly as that
+    // Tile-image layout: 64 columns (two blocks) are ONE operand tile of the tensor-core kernel.  It is written exactly as that
     // kernel wants it in shared memory -- tile_img_rows rows of 128 bytes (one per sample, zero rows beyond N), 16-byte pieces
     // XOR-swizzled with the row index (the 128-byte swizzle of a TMA tile) -- so that the kernel fetches it with ONE contiguous
     // bulk copy instead of a 128-row tensor-map box (which a single SM ingests at only ~24 B / clk).
-    __half* t1 = zh1 + (size_t)blockIdx.x * tile_img_rows * kSmallCols;
-    __half* t2 = zh2 + (size_t)blockIdx.x * tile_img_rows * kSmallCols;
-    const int piece = lane >> 2, within = (lane & 3) * 2;                   // columns 2 lane, 2 lane + 1: 16-byte piece lane / 4
+    const int tile = blockIdx.x >> 1, tpiece = (blockIdx.x & 1) * 4 + piece;
+    __half* t1 = zh1 + (size_t)tile * tile_img_rows * kSmallCols;
+    __half* t2 = zh2 + (size_t)tile * tile_img_rows * kSmallCols;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int n = rg + kRowGroups * k;
+    for (int k = 0; k < 2; ++k) {
+        const int n = rl + kSmallRowLanes * k;
         if (n < tile_img_rows) {
-            const size_t o = (size_t)n * kSmallCols + (size_t)((piece ^ (n & 7)) * 8 + within);
-            const bool live = n < N;
-            Ld2<__half>::st(t1 + o, live ? (va[k][0] - m1x) * r1x : 0.f, live ? (va[k][1] - m1y) * r1y : 0.f);
-            Ld2<__half>::st(t2 + o, live ? (vb[k][0] - m2x) * r2x : 0.f, live ? (vb[k][1] - m2y) * r2y : 0.f);
+            const size_t o = (size_t)n * kSmallCols + (size_t)((tpiece ^ (n & 7)) * 8);
+            uint32_t ha[4] = {0u, 0u, 0u, 0u}, hb[4] = {0u, 0u, 0u, 0u};
+            if (n < N) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    ha[c] = pack_f16x2((va[k][2 * c] - m1c[2 * c]) * r1c[2 * c], (va[k][2 * c + 1] - m1c[2 * c + 1]) * r1c[2 * c + 1]);
+                    hb[c] = pack_f16x2((vb[k][2 * c] - m2c[2 * c]) * r2c[2 * c], (vb[k][2 * c + 1] - m2c[2 * c + 1]) * r2c[2 * c + 1]);
+                }
+            }
+            *reinterpret_cast<uint4*>(t1 + o) = make_uint4(ha[0], ha[1], ha[2], ha[3]);
+            *reinterpret_cast<uint4*>(t2 + o) = make_uint4(hb[0], hb[1], hb[2], hb[3]);
         }
     }
     // D % 128 == 64: the walk of the tensor-core kernel visits one block past the last tile; it must read zeros
-    if (blockIdx.x == 0 && (gridDim.x & 1)) {
-        uint32_t* e1 = reinterpret_cast<uint32_t*>(zh1 + (size_t)gridDim.x * tile_img_rows * kSmallCols);
-        uint32_t* e2 = reinterpret_cast<uint32_t*>(zh2 + (size_t)gridDim.x * tile_img_rows * kSmallCols);
-        for (int i = threadIdx.x; i < tile_img_rows * kSmallCols / 2; i += kColThreads) { e1[i] = 0u; e2[i] = 0u; }
+    const int n_tiles = gridDim.x >> 1;
+    if (blockIdx.x == 0 && (n_tiles & 1)) {
+        uint4* e1 = reinterpret_cast<uint4*>(zh1 + (size_t)n_tiles * tile_img_rows * kSmallCols);
+        uint4* e2 = reinterpret_cast<uint4*>(zh2 + (size_t)n_tiles * tile_img_rows * kSmallCols);
+        for (int i = threadIdx.x; i < tile_img_rows * kSmallCols / 8; i += kColThreads) { e1[i] = make_uint4(0u, 0u, 0u, 0u); e2[i] = make_uint4(0u, 0u, 0u, 0u); }
     }
 }
 
@@ -1337,7 +1366,7 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         //      (S tiles -> loss + fp16 P on chip -> gradient accumulators in TMEM -> batch-norm backward); no memset, no D x D matrix
         float* ondiag_part = partials;
         const int n_pad = (N + 31) / 32 * 32;
-        bt_stat_norm_small_kernel<T><<<D / kSmallCols, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, a.eps,
+        bt_stat_norm_small_kernel<T><<<D / kSmallBlockCols, kColThreads, 0, stream>>>(static_cast<const T*>(a.z1), static_cast<const T*>(a.z2), N, D, a.eps,
                                                                                  a.momentum, stats, a.running_mean, a.running_var, zh1, zh2, ondiag_part,
                                                                                  loss_acc, reinterpret_cast<unsigned int*>(ws + L.misc + 64), n_pad);
         count_launch();
@@ -1358,7 +1387,7 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         p.stats = stats; p.rs1 = rs1; p.rs2 = rs2;
         p.dz1 = a.dz1; p.dz2 = a.dz2;
         p.loss_acc = loss_acc; p.done_counter = reinterpret_cast<unsigned int*>(ws + L.misc + 64); p.loss_out = a.loss_out;
-        p.ondiag_part = ondiag_part; p.n_parts = D / kSmallCols;
+        p.ondiag_part = ondiag_part; p.n_parts = D / kSmallBlockCols;
         p.zimg1 = zh1; p.zimg2 = zh2;
         const int units = p.n_blocks * p.pass_count;
         // programmatic dependent launch: set-up (barriers, TMEM allocation) overlaps the statistics kernel.  Not with HSIC (two more
@@ -1634,6 +1663,7 @@ extern "C" int abt_bt_loss_fwd_bwd(const abt_bt_args* a, abt_stream_t stream) {
     if (a->z1 == nullptr || a->z2 == nullptr || a->loss_out == nullptr || a->workspace == nullptr) return set_error(ABT_ERR_ARG, "null pointer argument");
     if ((a->need_grad_mask & 1) && a->dz1 == nullptr) return set_error(ABT_ERR_ARG, "dz1 is null but requested");
     if ((a->need_grad_mask & 2) && a->dz2 == nullptr) return set_error(ABT_ERR_ARG, "dz2 is null but requested");
+    if (((reinterpret_cast<uintptr_t>(a->z1) | reinterpret_cast<uintptr_t>(a->z2)) & 15) != 0) return set_error(ABT_ERR_ARG, "z1 / z2 must be 16-byte aligned");
     const WsLayout L = ws_layout(a->n_rows, a->n_dims, a->n_dims, a->dtype, false);
     if (a->workspace_bytes < L.total) return set_error(ABT_ERR_ARG, "workspace too small: %zu < %zu", a->workspace_bytes, L.total);
     if ((reinterpret_cast<uintptr_t>(a->workspace) & 255) != 0) return set_error(ABT_ERR_ARG, "workspace must be 256-byte aligned");

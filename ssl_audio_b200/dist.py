@@ -196,12 +196,15 @@ class NativeStep:
     def exchange(cls, group, device, n, world, d):
         """Peer-mapped exchange buffers for the copy-engine embedding gather (torch symmetric memory): every rank allocates one buffer,
         the rendezvous maps all of them into every process.  Returns None when symmetric memory is unavailable (-> NCCL all-gathers) or
-        switched off (ABT_DIST_CE=0).  Collective: every rank must call it with the same arguments."""
+        switched off.  ABT_DIST_CE=1 / 0 forces it on / off; by default it is used at two ranks only -- measured (profiles/r2_scaling.md):
+        0.908 against 0.923 ms per step at two ranks, but 1.45 against 1.16 ms at eight, where fourteen peer copies per step keep the copy
+        engines busier than NCCL's all-gather kernels keep the SMs.  Collective: every rank must call it with the same arguments."""
         key = (id(group) if group is not None else 0, device.index, n, world, d)
         if key in cls._exch:
             return cls._exch[key]
         entry = None
-        if os.environ.get("ABT_DIST_CE", "1") != "0" and world <= 16:
+        want = os.environ.get("ABT_DIST_CE")
+        if (world == 2 if want is None else want != "0") and world <= 16:
             ok = torch.zeros(1, dtype=torch.int32, device=device)
             try:
                 import torch.distributed._symmetric_memory as symm
