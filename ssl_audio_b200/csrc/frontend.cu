@@ -778,7 +778,7 @@ extern "C" int abt_wav_span_gather(const abt_logmel_plan* plan, const float* wav
     }
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-    const int grid = n_clips < n_sm ? n_clips : n_sm;
+    const int grid = n_clips < 2 * n_sm ? n_clips : 2 * n_sm;      // two warps per SM: ~600 KB of reads in flight over PCIe
     wav_span_gather_kernel<<<grid, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, wav_row_stride, n_samples, n_clips, frame_start,
                                                                                      plan->cfg.hop_length, kNfft / 2, span_len, spans, span_origin);
     count_launch();

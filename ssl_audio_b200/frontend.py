@@ -152,15 +152,22 @@ class BatchFrontend(nn.Module):
         self.last_plan = plan
         return tf.views_from_plan(ring, plan.slots_ptr, int(ring.shape[1]), plan)
 
-    # -- two-step form of the crop-first device path: host work first, launches later ------------------------------
-    def prepare(self, wav: torch.Tensor):
-        """Host half of `forward` for device waveforms (path "lms", mode "crop"): draws the batch's random parameters in the
-        reference's order and uploads them (one async copy on the current stream).  `launch(handle)` then only enqueues the two
-        kernels, so a trainer can plan early and launch exactly where it wants the kernels to overlap something else."""
-        if not wav.is_cuda or wav.dtype != torch.float32 or wav.dim() != 2:
-            raise ValueError("wav must be a CUDA float32 tensor (B, L)")
+    # -- two-step form of the crop-first path: host work (and the PCIe transfer) first, launches later ---------------
+    def prepare(self, wav: torch.Tensor, device: Optional[torch.device] = None):
+        """Host half of `forward` (path "lms", mode "crop"): draws the batch's random parameters in the reference's order and
+        uploads them (one async copy on the current stream).  `launch(handle)` then only enqueues the two kernels, so a trainer
+        can plan early and launch exactly where it wants the kernels to overlap something else.
+
+        With waveforms in PINNED host memory, `prepare` also enqueues the crop-first span gather (the only PCIe traffic of the
+        batch) on the current stream, into one of two alternating span buffers: calling `prepare(next_batch)` on a side stream
+        while the current batch computes is the prefetch a `DataLoader` worker would otherwise provide.  `launch` makes its stream
+        wait for that gather."""
+        if wav.dtype != torch.float32 or wav.dim() != 2:
+            raise ValueError("wav must be a float32 tensor (B, L)")
         if self.path != "lms" or self.mode != "crop":
             raise ValueError("prepare/launch cover the crop-first lms path only")
+        if not wav.is_cuda:
+            return self._prepare_host(wav, device)
         wav = wav.contiguous()
         B, L = int(wav.shape[0]), int(wav.shape[1])
         eng = self.transform.engine(B)
@@ -170,7 +177,56 @@ class BatchFrontend(nn.Module):
         plan = eng.planner.plan(B, time_crop_range=crop_range, device=wav.device)
         return (wav, L, ring, plan)
 
+    def _prepare_host(self, wav: torch.Tensor, device: Optional[torch.device]):
+        if not wav.is_contiguous():
+            raise ValueError("wav must be a contiguous float32 host tensor (B, L)")
+        if not wav.is_pinned():
+            raise RuntimeError("host waveforms must be in pinned memory (DataLoader(pin_memory=True) or tensor.pin_memory()); "
+                               "ssl_audio_b200 has no pageable-memory / CPU path")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        B, L = int(wav.shape[0]), int(wav.shape[1])
+        lib = self._lib
+        span_len = C.c_int()
+        _lib.check(lib.abt_wav_span_len(self.logmel_norm.plan(dev), self.crop_frames, C.byref(span_len)))
+        T_full = self.logmel_raw.n_frames(L)
+        if T_full <= self.crop_frames or L < span_len.value or B == 0:      # nothing to skip: the clips are copied whole
+            with torch.cuda.device(dev):
+                return self.prepare(wav.to(dev, non_blocking=True))
+        eng = self.transform.engine(B)
+        ring = eng.ensure_ring(dev)
+        key = (dev.index, B, span_len.value)
+        if getattr(self, "_span_key", None) != key:
+            self._span_bufs = [(torch.empty((B, span_len.value), dtype=torch.float32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev),
+                                torch.cuda.Event(), torch.cuda.Event()) for _ in range(2)]      # spans, origins, gathered, consumed
+            self._span_next = 0
+            self._span_key = key
+        k = self._span_next
+        self._span_next = k ^ 1
+        spans, origin, gathered, consumed = self._span_bufs[k]
+        with torch.cuda.device(dev):
+            st_t = torch.cuda.current_stream(dev)
+            st_t.wait_event(consumed)            # the log-mel launch that last read this buffer (two batches ago)
+            plan = eng.planner.plan(B, time_crop_range=T_full - self.crop_frames, device=dev)
+            _lib.check(lib.abt_wav_span_gather(self.logmel_norm.plan(dev), wav.data_ptr(), 1, L, B, L, plan.starts_ptr, self.crop_frames,
+                                               spans.data_ptr(), origin.data_ptr(), _stream(dev)))
+            gathered.record(st_t)
+        self.h2d_bytes = B * span_len.value * 4
+        return ("host", wav, L, ring, plan, k, dev)
+
     def launch(self, handle) -> List[torch.Tensor]:
+        if handle[0] == "host":
+            _, wav, L, ring, plan, k, dev = handle          # wav is kept alive until its gather has been consumed
+            spans, origin, gathered, consumed = self._span_bufs[k]
+            stride = int(ring.shape[1])
+            B = int(spans.shape[0])
+            with torch.cuda.device(dev):
+                st_t = torch.cuda.current_stream(dev)
+                st_t.wait_event(gathered)
+                _lib.check(self._lib.abt_logmel_span_fwd(self.logmel_norm.plan(dev), spans.data_ptr(), origin.data_ptr(), B, L, plan.starts_ptr,
+                                                         self.crop_frames, ring.data_ptr(), plan.slots_ptr, stride, _stream(dev)))
+                consumed.record(st_t)
+                self.last_plan = plan
+                return self.transform.views_from_plan(ring, plan.slots_ptr, stride, plan)
         wav, L, ring, plan = handle
         stride = int(ring.shape[1])
         self.logmel_norm.crop_into(wav, L, 0, plan.starts_ptr, self.crop_frames, ring, plan.slots_ptr, stride)
@@ -217,37 +273,14 @@ class BatchFrontend(nn.Module):
         Crop-first all the way to the host: the crop is planned first, then a small kernel reads ONLY the samples the
         cropped frames need straight out of the pinned buffer over PCIe (abt_wav_span_gather), so a 10 s clip costs
         65 KB of host->device traffic instead of 640 KB.  Results are bit-identical to `forward(wav.cuda())`.
-        Clips that are not longer than the crop (nothing to skip) are copied whole."""
+        Clips that are not longer than the crop (nothing to skip) are copied whole.  `prepare(wav)` / `launch(handle)` is the
+        same thing in two steps (prefetch the next batch's samples while this one computes)."""
         if wav.is_cuda or wav.dtype != torch.float32 or wav.dim() != 2 or not wav.is_contiguous():
             raise ValueError("wav must be a contiguous float32 host tensor (B, L)")
-        if not wav.is_pinned():
-            raise RuntimeError("host waveforms must be in pinned memory (DataLoader(pin_memory=True) or tensor.pin_memory()); "
-                               "ssl_audio_b200 has no pageable-memory / CPU path")
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        B, L = int(wav.shape[0]), int(wav.shape[1])
-        lib = self._lib
-        span_len = C.c_int()
-        _lib.check(lib.abt_wav_span_len(self.logmel_norm.plan(dev), self.crop_frames, C.byref(span_len)))
-        T_full = self.logmel_raw.n_frames(L)
-        if self.path != "lms" or self.mode != "crop" or T_full <= self.crop_frames or L < span_len.value or B == 0:
+        if self.path != "lms" or self.mode != "crop":
+            if not wav.is_pinned():
+                raise RuntimeError("host waveforms must be in pinned memory (DataLoader(pin_memory=True) or tensor.pin_memory()); "
+                                   "ssl_audio_b200 has no pageable-memory / CPU path")
             return self.forward(wav.to(dev, non_blocking=True))
-        tf = self.transform
-        eng = tf.engine(B)
-        ring = eng.ensure_ring(dev)
-        stride = int(ring.shape[1])
-        key = (dev.index, B)
-        if getattr(self, "_span_key", None) != key:
-            self._spans = torch.empty((B, span_len.value), dtype=torch.float32, device=dev)
-            self._origin = torch.empty((B,), dtype=torch.int32, device=dev)
-            self._span_key = key
-        with torch.cuda.device(dev):
-            plan = eng.planner.plan(B, time_crop_range=T_full - self.crop_frames, device=dev)
-            st = _stream(dev)
-            lm = self.logmel_norm.plan(dev)
-            _lib.check(lib.abt_wav_span_gather(lm, wav.data_ptr(), 1, L, B, L, plan.starts_ptr, self.crop_frames, self._spans.data_ptr(),
-                                               self._origin.data_ptr(), st))
-            _lib.check(lib.abt_logmel_span_fwd(lm, self._spans.data_ptr(), self._origin.data_ptr(), B, L, plan.starts_ptr, self.crop_frames,
-                                               ring.data_ptr(), plan.slots_ptr, stride, st))
-        self.last_plan = plan
-        self.h2d_bytes = B * span_len.value * 4
-        return tf.views_from_plan(ring, plan.slots_ptr, stride, plan)
+        return self.launch(self.prepare(wav, dev))

@@ -242,6 +242,33 @@ def test_pinned_host_waveforms_zero_copy_span_path_is_bit_identical():
         S.BatchFrontend(_args(), norm_stats=AS_STATS)(torch.from_numpy(wav))          # pageable host memory: refused
 
 
+def test_host_prefetch_pipeline_equals_sequential_calls():
+    """prepare(next host batch) on a side stream while the current batch is launched (the e2e loop of bench.py) must give exactly
+    what sequential forward() calls give: same draws, same ring contents, double-buffered spans never overwritten early."""
+    import ssl_audio_b200 as S
+    batches = [torch.from_numpy(O.synth_wave(32, 32000, seed=20 + k)).pin_memory() for k in range(5)]
+    np.random.seed(9); random.seed(9)
+    fe = S.BatchFrontend(_args(), norm_stats=AS_STATS, path="lms", mode="crop")
+    seq = [torch.stack(fe(w), 1).clone() for w in batches]
+    torch.cuda.synchronize()
+    np.random.seed(9); random.seed(9)
+    fe = S.BatchFrontend(_args(), norm_stats=AS_STATS, path="lms", mode="crop")
+    side, main = torch.cuda.Stream(), torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        handle = fe.prepare(batches[0])
+    pipe = []
+    for k in range(len(batches)):
+        with torch.cuda.stream(main):
+            v = fe.launch(handle)
+            pipe.append(torch.stack(v, 1).clone())
+        if k + 1 < len(batches):
+            with torch.cuda.stream(side):
+                handle = fe.prepare(batches[k + 1])
+    torch.cuda.synchronize()
+    for a, b in zip(seq, pipe):
+        assert torch.equal(a, b)
+
+
 def test_bench_size_frontend_1024_clips_of_10s():
     """BASELINE config 2 at full size (1024 clips x 10 s, crop-first): crop starts equal the reference's np.random.randint draws
     interleaved with the view draws (replayed by the oracle), eight spot-checked clips match the oracle's per-sample path, every
