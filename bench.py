@@ -279,9 +279,8 @@ def run_ours(args):
         with torch.cuda.stream(side_stream):
             cur["handle"] = fe.prepare(cur["wav"])
 
-    def frontend_launch():          # kernel launches only: called from the objective's comm-overlap hook
-        with torch.cuda.stream(side_stream):
-            cur["views"] = fe.launch(cur["handle"])
+    def frontend_launch():          # kernel launches only: called (on the side stream) from the objective's comm-overlap hook
+        cur["views"] = fe.launch(cur["handle"])
 
     # Default: one host thread; on several GPUs the frontend is enqueued from the objective's comm-overlap hook (right after the embedding
     # all-gathers have been launched).  BENCH_THREAD=1 moves the frontend's host side to a worker thread instead (measured: no gain, the
@@ -293,7 +292,9 @@ def run_ours(args):
     use_hook = (world > 1 if os.environ.get("BENCH_HOOK") is None else os.environ["BENCH_HOOK"] == "1") and not use_thread
     pool = None
     if use_hook:
-        crit.comm_overlap_hook = frontend_launch
+        # gated on the objective's stream position (ssl_audio_b200.dist.side_stream_hook); BENCH_HOOK_WAIT=0 shows the ungated behaviour
+        from ssl_audio_b200.dist import side_stream_hook
+        crit.comm_overlap_hook = side_stream_hook(side_stream, frontend_launch, gate=os.environ.get("BENCH_HOOK_WAIT", "1") == "1")
     elif use_thread:
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(max_workers=1, initializer=lambda: torch.cuda.set_device(local_rank))
@@ -387,7 +388,7 @@ def run_ours(args):
             v = [float(x) for x in tq.cpu()]
             print(json.dumps({"quick": True, "n_gpus": world, "ms_per_step": v[0] / args.steps, "value": B * world / (v[0] / args.steps * 1e-3),
                               "loss_fwd_bwd_ms": v[1], "corr_ms": v[2], "grad_ms": v[3], "stats_ms": v[4], "host_enqueue_ms": host_ms,
-                              "env": {k: os.environ.get(k) for k in ("ABT_DIST_CE", "ABT_COMM_MAX_CTAS", "ABT_DIST_RESERVE_SMS", "ABT_DIST_XCHG")}}), flush=True)
+                              "env": {k: os.environ.get(k) for k in ("ABT_DIST_CE", "ABT_COMM_MAX_CTAS", "ABT_DIST_RESERVE_SMS", "ABT_DIST_XCHG", "BENCH_HOOK_WAIT", "BENCH_HOOK")}}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return

@@ -18,10 +18,6 @@ def _rel(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
 
 
-@pytest.mark.parametrize("world,n_local,d,hsic,dtype", [
-    (2, 64, 256, False, "f32"), (4, 32, 512, False, "f32"), (8, 16, 1024, True, "f32"), (2, 160, 512, False, "bf16"),
-    (8, 128, 2048, False, "bf16"),
-])
 def _assemble_row_blocks(world, n_local, d, hsic, tdt, z1, z2):
     from ssl_audio_b200 import dist as D
     ng = world * n_local
@@ -156,3 +152,27 @@ def test_native_multi_gpu_step_under_torchrun():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29541", os.path.join(root, "tools", "dist_check.py")], capture_output=True, text=True, timeout=900)
     assert "DIST_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_side_stream_hook_is_gated_on_the_objective_stream():
+    """The comm-overlap hook fires on the host long before the device reaches the hook point: work it puts on a side stream must
+    wait for the objective's stream (ssl_audio_b200.dist.side_stream_hook), and must run on the side stream."""
+    from ssl_audio_b200.dist import side_stream_hook
+    dev = torch.device("cuda", 0)
+    side = torch.cuda.Stream(dev)
+    x = torch.zeros(1, device=dev)
+    seen = {}
+
+    def fn():
+        seen["stream"] = torch.cuda.current_stream(dev)
+        seen["y"] = x.clone()                      # runs on the side stream
+
+    hook = side_stream_hook(side, fn)
+    torch.cuda.synchronize()
+    torch.cuda._sleep(200_000_000)                 # ~0.1 s of device time on the objective's stream ...
+    x.fill_(1.0)                                   # ... then the value the side stream must see
+    hook()
+    torch.cuda.synchronize()
+    assert seen["stream"] == side
+    assert float(seen["y"]) == 1.0
