@@ -380,6 +380,80 @@ def run_ours(args):
     for v in (stats_ms, corr_ms, grad_ms):
         v.value = v.value * calls_per_step
 
+    # ---- e2e: HOST buffers (pinned), through the public API.  Per step, inside the timed region: the frontend reads the
+    # waveforms straight from pinned host memory (crop-first: only the cropped spans cross PCIe), the embeddings are
+    # copied host->device, and the loss value is read back device->host.  Software-pipelined the way a prefetching DataLoader
+    # would: while step s computes, step s+1's spans (BatchFrontend.prepare on a side stream) and embeddings cross PCIe; every
+    # step's transfers, the first step's included, are issued inside the timed region.
+    def run_e2e(n_steps, serial, reserve):
+        """serial: embedding copies behind the span gather on ONE stream (the SM-driven gather and the DMA copies share the link badly
+        side by side: tools/pcie_probe.py) instead of a stream each; reserve: SMs the tensor-core kernels leave free, so that the gather's
+        few warps are never locked out by a persistent GEMM that owns every SM's registers."""
+        wav_h = wav.cpu().pin_memory()
+        z1_h, z2_h = z1.cpu().pin_memory(), z2.cpu().pin_memory()
+        loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+        fe_stream, pf_stream, copy_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        views_done = torch.cuda.Event()
+        zbufs = [(torch.empty_like(z1), torch.empty_like(z2)) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(k):
+            with torch.cuda.stream(pf_stream):
+                handle = fe.prepare(wav_h)               # plan + span gather over PCIe (the frontend's only host->device traffic)
+            zs = pf_stream if serial else copy_stream
+            with torch.cuda.stream(zs):
+                zs.wait_event(freed[k])
+                zbufs[k][0].copy_(z1_h, non_blocking=True)
+                zbufs[k][1].copy_(z2_h, non_blocking=True)
+                ready[k].record(zs)
+            return handle
+
+        def loop(n):
+            for k in range(2):
+                freed[k].record()
+            handle = prefetch(0)
+            for s in range(n):
+                k = s & 1
+                with torch.cuda.stream(fe_stream):       # gathered spans -> log-mel -> views
+                    views = fe.launch(handle)
+                    views_done.record(fe_stream)
+                if s + 1 < n:
+                    handle = prefetch(k ^ 1)             # next step's span gather and embedding H2D overlap this step's kernels
+                torch.cuda.current_stream(dev).wait_event(ready[k])
+                a = zbufs[k][0].requires_grad_(True)
+                b = zbufs[k][1].requires_grad_(True)
+                loss = crit(b, a, ngcrops_each=1)
+                loss.backward()
+                loss_h.copy_(loss.detach(), non_blocking=True)
+                freed[k].record()
+                torch.cuda.current_stream(dev).wait_event(views_done)   # the step is complete when its views exist too
+                a.grad = None; b.grad = None
+                a.requires_grad_(False); b.requires_grad_(False)
+            torch.cuda.synchronize(dev)
+            return views
+
+        S.set_reserved_sms(int(reserve))
+        try:
+            loop(3)
+            sync_all()
+            t0 = time.perf_counter()
+            loop(n_steps)
+            dt = time.perf_counter() - t0
+        finally:
+            S.set_reserved_sms(0)
+        return dt, int(getattr(fe, "h2d_bytes", wav_h.numel() * 4)) + z1_h.numel() * 2 + z2_h.numel() * 2
+
+    if args.e2e_probe:          # which arrangement of the PCIe traffic is fastest (tools: development only; prints one line per variant)
+        crit.comm_overlap_hook = None
+        for blocks, reserve, serials in ((4, 4, (1, 1, 0)), (4, 6, (1,)), (6, 6, (1,)), (3, 4, (1,)), (4, 4, (1,)), (8, 8, (1,)), (4, 8, (1,)), (148, 0, (0,))):
+            _lib.check(lib.abt_debug_set(15, blocks))
+            for serial in serials:
+                dt, nb = run_e2e(20, bool(serial), reserve)
+                print(json.dumps({"e2e_probe": True, "gather_blocks": blocks, "serial": serial, "reserve_sms": reserve, "ms_per_step": dt / 20 * 1e3,
+                                  "clips_per_s": B * 20 / dt, "pcie_gbs": nb * 20 / dt / 1e9}), flush=True)
+        return
+
     if args.quick:
         tq = torch.tensor([ms, loss_ms, corr_ms.value, grad_ms.value, stats_ms.value], dtype=torch.float64, device=dev)
         if world > 1:
@@ -492,66 +566,12 @@ def run_ours(args):
     clocks_sus = sampler2.stop() if rank == 0 else None
     sus_ms = u0.elapsed_time(u1) / sus_steps
 
-    # ---- e2e: HOST buffers (pinned), through the public API.  Per step, inside the timed region: the frontend reads the
-    # waveforms straight from pinned host memory (crop-first: only the cropped spans cross PCIe), the embeddings are
-    # copied host->device, and the loss value is read back device->host.  Software-pipelined the way a prefetching DataLoader
-    # would: while step s computes, step s+1's spans (BatchFrontend.prepare on a side stream) and embeddings (copy stream)
-    # cross PCIe; every step's transfers, the first step's included, are issued inside the timed region.
-    wav_h = wav.cpu().pin_memory()
-    z1_h, z2_h = z1.cpu().pin_memory(), z2.cpu().pin_memory()
-    loss_h = torch.empty((), dtype=torch.float32).pin_memory()
-    copy_stream = torch.cuda.Stream(dev)
-    fe_stream = torch.cuda.Stream(dev)
-    pf_stream = torch.cuda.Stream(dev)
-    views_done = torch.cuda.Event()
-    zbufs = [(torch.empty_like(z1), torch.empty_like(z2)) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    freed = [torch.cuda.Event() for _ in range(2)]
-
-    def upload(k):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[k])
-            zbufs[k][0].copy_(z1_h, non_blocking=True)
-            zbufs[k][1].copy_(z2_h, non_blocking=True)
-            ready[k].record(copy_stream)
-
-    def prefetch():
-        with torch.cuda.stream(pf_stream):          # plan + span gather over PCIe (the frontend's only host->device traffic)
-            return fe.prepare(wav_h)
-
-    def e2e_loop(n):
-        for k in range(2):
-            freed[k].record()
-        upload(0)
-        handle = prefetch()
-        for s in range(n):
-            k = s & 1
-            with torch.cuda.stream(fe_stream):       # gathered spans -> log-mel -> views
-                views = fe.launch(handle)
-                views_done.record(fe_stream)
-            if s + 1 < n:
-                upload(k ^ 1)                        # next step's embedding H2D and span gather overlap this step's kernels
-                handle = prefetch()
-            torch.cuda.current_stream(dev).wait_event(ready[k])
-            a = zbufs[k][0].requires_grad_(True)
-            b = zbufs[k][1].requires_grad_(True)
-            loss = crit(b, a, ngcrops_each=1)
-            loss.backward()
-            loss_h.copy_(loss.detach(), non_blocking=True)
-            freed[k].record()
-            torch.cuda.current_stream(dev).wait_event(views_done)   # the step is complete when its views exist too
-            a.grad = None; b.grad = None
-            a.requires_grad_(False); b.requires_grad_(False)
-        torch.cuda.synchronize(dev)
-        return views
-
-    e2e_loop(3)
-    sync_all()
     e2e_steps = max(2, min(args.steps, args.e2e_steps))
-    t0 = time.perf_counter()
-    e2e_loop(e2e_steps)
-    e2e_s = time.perf_counter() - t0
-    h2d = int(getattr(fe, "h2d_bytes", wav_h.numel() * 4)) + z1_h.numel() * 2 + z2_h.numel() * 2
+    # measured (--e2e-probe, one B200): one PCIe stream + 4 SMs left free for the 4-block gather 1.97-2.02 ms per step; gather and
+    # copies on a stream each and nothing reserved 2.14-2.27 ms
+    e2e_serial = os.environ.get("BENCH_E2E_SERIAL", "1") == "1"
+    e2e_reserve = int(os.environ.get("BENCH_E2E_RESERVE", "4"))
+    e2e_s, h2d = run_e2e(e2e_steps, e2e_serial, e2e_reserve)
     d2h = 4
 
     # ---- reduce over ranks (max time)
@@ -606,9 +626,10 @@ def run_ours(args):
         "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "reserved_sms": e2e_reserve, "pcie_gbs": h2d * e2e_steps / e2e_s / 1e9 if world == 1 else None,
                 "note": "pinned host buffers through BatchFrontend.prepare / launch (host wav) + BarlowTwinsLoss; crop-first span gather reads only the cropped "
-                        "samples over PCIe; the next step's span gather and embedding H2D overlap the current step's kernels (PCIe-bound: "
-                        "h2d_bytes_per_step at the box's ~55 GB/s is the floor)"},
+                        "samples over PCIe; the next step's span gather and embedding H2D run on one side stream under the current step's kernels, "
+                        "which leave reserved_sms SMs to the gather (PCIe-bound: h2d_bytes_per_step at the box's ~52-55 GB/s is the floor)"},
         "roofline": {"bound": "tensor", "kernel": "bt_umma_kernel (CORR + GRAD launches)", "achieved": achieved, "peak": peaks["tf_burst"],
                      "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"], "traffic": _traffic(),
                      "algorithmic_flops_per_step": flops, "corr_ms": corr, "grad_ms": grad, "stats_ms": st_ms, "loss_fwd_bwd_ms": loss_ms,
@@ -674,6 +695,7 @@ def main():
     ap.add_argument("--dim", type=int, default=8192, help="projector_out_dim")
     ap.add_argument("--clip-seconds", type=float, default=10.0)
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-probe", action="store_true", help="single GPU, development: time the e2e loop for several PCIe arrangements and exit")
     ap.add_argument("--ref-budget-s", type=float, default=240.0, help="reference arm: wall-clock budget of the whole K + W step run")
     ap.add_argument("--sweep-iters", type=int, default=30, help="timed iterations per point of the N = 128 loss sweep (BASELINE config 3)")
     ap.add_argument("--sustained-s", type=float, default=2.5, help="length of the sustained-clock loop reported beside the burst number")

@@ -398,6 +398,16 @@ int abt_lars_step(const abt_opt_tensor* tensors_dev, const int* chunk_tensor_dev
 int abt_ema_update(const abt_opt_tensor* tensors_dev, const int* chunk_tensor_dev, int n_tensors, int n_chunks, float beta, abt_stream_t stream);
 
 /* ===================================================================================== *
+ *  Co-scheduling
+ * ===================================================================================== */
+/* The tensor-core kernels of the objective are persistent and own every SM they run on (registers and shared memory), so
+ * nothing else can start on those SMs until they end -- and they cannot start on an SM that holds any other block.  This call
+ * makes them leave `n_sms` SMs (0..64, default 0) free for work that has to run BESIDE them: the pinned-host span gather
+ * (abt_wav_span_gather is confined to 4 SMs for exactly this reason) in a prefetching input pipeline, or the caller's own
+ * copy kernels.  abt_bt_dist_step applies its own reservation for NCCL's kernels.  Process-wide; returns the previous value. */
+int abt_set_reserved_sms(int n_sms);
+
+/* ===================================================================================== *
  *  Debug hooks (not part of the drop-in surface; used by tools/gpu_diag.py)
  * ===================================================================================== */
 int abt_debug_set(int key, int value);

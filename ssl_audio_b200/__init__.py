@@ -14,8 +14,16 @@ from .loss import BarlowTwinsLoss, bt_loss_fwd_bwd, off_diagonal
 from .optim import EMA, LARS, update_moving_average
 from .transforms import AudioPairTransform
 
+
+def set_reserved_sms(n_sms: int) -> int:
+    """SMs the persistent tensor-core kernels of the objective leave free (default 0) for work that must run beside them -- the
+    pinned-host span gather of a prefetching input pipeline (`BatchFrontend.prepare(host_wav)` on a side stream occupies 4 SMs).
+    Returns the previous value.  include/abt_b200.h: abt_set_reserved_sms."""
+    from . import _lib
+    return int(_lib.load().abt_set_reserved_sms(int(n_sms)))
+
 __all__ = [
     "AudioPairTransform", "RandomResizeCrop", "RandomLinearFader", "MixupBYOLA", "MixGaussianNoise", "NormalizeBatch", "RunningNorm", "log_mixup_exp",
     "LogMelSpectrogram", "BatchFrontend", "BarlowTwinsLoss", "bt_loss_fwd_bwd", "off_diagonal",
-    "LARS", "EMA", "update_moving_average",
+    "LARS", "EMA", "update_moving_average", "set_reserved_sms",
 ]

@@ -165,6 +165,7 @@ SIGNATURES = {
     "abt_opt_chunk_elems": (C.c_int, []),
     "abt_lars_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "abt_ema_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "abt_set_reserved_sms": (C.c_int, [C.c_int]),
     "abt_debug_set": (C.c_int, [C.c_int, C.c_int]),
     "abt_debug_launch_count": (C.c_longlong, [C.c_int]),
     "abt_debug_timing": (C.c_int, [C.c_int]),

@@ -11,4 +11,6 @@ int set_error(int code, const char* fmt, ...);
 int check_device_sm100();
 // every kernel launch of the library is counted (bench.py reports it as gpu_launches)
 void count_launch(int n = 1);
+// blocks (of 32 warps) of the pinned-host span gather: it is confined to this many SMs (abt_debug_set key 15)
+extern int g_gather_blocks;
 }  // namespace abt

@@ -1628,6 +1628,12 @@ extern "C" int abt_debug_timing_read(float* stats_ms, float* corr_ms, float* gra
     return 0;
 }
 
+extern "C" int abt_set_reserved_sms(int n_sms) {
+    const int prev = g_reserve_sms;
+    g_reserve_sms = n_sms < 0 ? 0 : (n_sms > 64 ? 64 : n_sms);
+    return prev;
+}
+
 extern "C" int abt_debug_set(int key, int value) {
     int* f[6] = {&g_desc.mn_lbo, &g_desc.mn_sbo, &g_desc.mn_kstep, &g_desc.k_lbo, &g_desc.k_sbo, &g_desc.k_kstep};
     if (key == 6) { g_cta_group = value == 1 ? 1 : 2; return 0; }
@@ -1637,6 +1643,7 @@ extern "C" int abt_debug_set(int key, int value) {
     if (key == 13) { g_comm_max_ctas = value < 0 ? 0 : value; return 0; }
     if (key == 14) { g_dist_reserve_sms = value < 0 ? 0 : (value > 64 ? 64 : value); return 0; }
     if (key == 9) { g_fused = value != 0; return 0; }
+    if (key == 15) { g_gather_blocks = value < 1 ? 1 : (value > 148 ? 148 : value); return 0; }
     if (key == 10) { g_fused_pdl = value != 0; return 0; }
     if (key < 0 || key >= 6) return set_error(ABT_ERR_ARG, "unknown debug key %d", key);
     *f[key] = value;

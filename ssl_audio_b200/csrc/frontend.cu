@@ -445,11 +445,15 @@ __global__ void bank_push_kernel(const float* __restrict__ x, long long x_stride
 // PCIe reads (about 1.3 ms per 1024-clip batch) overlap the compute of the previous step instead of serialising with it.  Four
 // independent 16-byte loads per lane keep ~300 KB in flight over PCIe, enough to saturate it.
 // ------------------------------------------------------------------------------------------
-__global__ void __maxnreg__(32) wav_span_gather_kernel(const float* __restrict__ wav, long long row_stride, int n_samples, int n_clips,
-                                                             const int* __restrict__ frame_start, int hop, int half_fft, int span_len,
-                                                             float* __restrict__ spans, int* __restrict__ origin) {
-    const int lane = threadIdx.x;
-    for (int clip = blockIdx.x; clip < n_clips; clip += gridDim.x) {
+int g_gather_blocks = 4;
+__global__ void __launch_bounds__(1024, 1) wav_span_gather_kernel(const float* __restrict__ wav, long long row_stride, int n_samples, int n_clips,
+                                                                                   const int* __restrict__ frame_start, int hop, int half_fft, int span_len,
+                                                                                   float* __restrict__ spans, int* __restrict__ origin) {
+    // A few fat blocks (one warp per clip, 32 warps per block): PCIe needs only ~100 KB of reads in flight, and confined to a handful
+    // of SMs the gather runs BESIDE a persistent tensor-core kernel that leaves those SMs free (abt_debug_set(12, k)) instead of
+    // waiting for it -- or making it wait: a GEMM CTA needs a whole SM's registers.
+    const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    for (int clip = blockIdx.x * warps + (threadIdx.x >> 5); clip < n_clips; clip += gridDim.x * warps) {
         const int f0 = frame_start ? max(frame_start[clip], 0) : 0;
         int o = f0 * hop - half_fft;                 // first padded-coordinate sample of the crop, in clip coordinates
         o = min(o, n_samples - span_len);
@@ -776,11 +780,9 @@ extern "C" int abt_wav_span_gather(const abt_logmel_plan* plan, const float* wav
         if (e != cudaSuccess) return set_error(ABT_ERR_ARG, "host waveforms must be in mapped pinned memory (cudaHostAlloc / cudaHostRegister): %s", cudaGetErrorString(e));
         src = static_cast<const float*>(dptr);
     }
-    int n_sm = 148;
-    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-    const int grid = n_clips < 2 * n_sm ? n_clips : 2 * n_sm;      // two warps per SM: ~600 KB of reads in flight over PCIe
-    wav_span_gather_kernel<<<grid, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, wav_row_stride, n_samples, n_clips, frame_start,
-                                                                                     plan->cfg.hop_length, kNfft / 2, span_len, spans, span_origin);
+    const int blocks = (n_clips + 31) / 32 < g_gather_blocks ? (n_clips + 31) / 32 : g_gather_blocks;
+    wav_span_gather_kernel<<<blocks, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, wav_row_stride, n_samples, n_clips, frame_start,
+                                                                                       plan->cfg.hop_length, kNfft / 2, span_len, spans, span_origin);
     count_launch();
     ABT_CUDA_OK(cudaGetLastError());
     return 0;

@@ -187,6 +187,21 @@ def test_grad_scaler_small_gradients_fp16(n, d):
     assert _rel(t2.grad.float().cpu().numpy() / scale, r2) < TOL
 
 
+def test_reserved_sms_do_not_change_the_result():
+    """abt_set_reserved_sms: the persistent tensor-core kernels run on fewer SMs (a different tile schedule) with the same outputs."""
+    import ssl_audio_b200 as S
+    z1, z2 = O.synth_embeddings(384, 1024, seed=31)
+    rl, r1, r2 = O.bt_loss_forward_backward(z1, z2, 1.0, 0.005, False)
+    assert S.set_reserved_sms(7) == 0
+    try:
+        loss, g1, g2, _ = _run(z1, z2, torch.float32)
+    finally:
+        assert S.set_reserved_sms(0) == 7
+    loss0, h1, h2, _ = _run(z1, z2, torch.float32)
+    assert abs(loss - rl) <= TOL * abs(rl) and _rel(g1, r1) < TOL and _rel(g2, r2) < TOL
+    assert abs(loss - loss0) <= 1e-5 * abs(loss0) and _rel(g1, h1.astype(np.float64)) < 1e-5 and _rel(g2, h2.astype(np.float64)) < 1e-5
+
+
 def test_error_conventions():
     import ssl_audio_b200 as S
     mod = S.BarlowTwinsLoss(_cfg(64), ncrops=2).cuda()
