@@ -191,7 +191,7 @@ def test_reserved_sms_do_not_change_the_result():
     """abt_set_reserved_sms: the persistent tensor-core kernels run on fewer SMs (a different tile schedule) with the same outputs."""
     import ssl_audio_b200 as S
     z1, z2 = O.synth_embeddings(384, 1024, seed=31)
-    rl, r1, r2 = O.bt_loss_forward_backward(z1, z2, 1.0, 0.005, False)
+    rl, r1, r2, _ = O.bt_loss_forward_backward(z1, z2, 1.0, 0.005, False)
     assert S.set_reserved_sms(7) == 0
     try:
         loss, g1, g2, _ = _run(z1, z2, torch.float32)
