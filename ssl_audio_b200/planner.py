@@ -60,6 +60,17 @@ def _pyrandom_state_address():
     return _PYRANDOM_ADDR
 
 
+class _NoLock:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_LOCK = _NoLock()
+
+
 @dataclass
 class BatchPlan:
     starts: np.ndarray       # (B,) int32 time-crop start per clip, -1 if none was drawn
@@ -72,6 +83,16 @@ class BatchPlan:
     starts_ptr: int = 0
     wav_starts_ptr: int = 0
     slots_ptr: int = 0
+    # staging-ring bookkeeping: the host arrays above and the device copy alias ring slot `_gen % depth`, which is handed out
+    # again `depth` plans later -- `check_live()` refuses a plan whose slot has been reused
+    _staging: Optional["PlanStaging"] = None
+    _gen: int = -1
+
+    def check_live(self):
+        st = self._staging
+        if st is not None and st.gen - self._gen >= len(st.host):
+            raise RuntimeError(f"stale batch plan: {st.gen - self._gen} plans were drawn since this one and its staging slot "
+                               f"(ring depth {len(st.host)}) has been reused; launch a prepared batch before preparing {len(st.host)} more")
 
 
 class PlanStaging:
@@ -87,10 +108,12 @@ class PlanStaging:
         self.dev = [torch.empty(self.nbytes, dtype=torch.uint8, device=device) for _ in range(depth)]
         self.done = [None] * depth
         self.k = 0
+        self.gen = 0            # plans handed out so far
 
     def acquire(self):
         k = self.k
         self.k = (k + 1) % len(self.host)
+        self.gen += 1
         if self.done[k] is not None:
             self.done[k].synchronize()
         return k
@@ -178,6 +201,9 @@ class ViewPlanner:
             buf = st.host_np[slot]
         else:
             buf = np.empty(max(nbytes, 16), dtype=np.uint8)
+        # the native planner advances numpy's global MT19937 state in place: hold numpy's own lock so that another thread drawing
+        # from np.random at the same time cannot interleave (CPython's `random` has no lock: keep its use single-threaded)
+        np_lock = np.random.mtrand._rand._bit_generator.lock if use_np else _NO_LOCK
         np_addr = _numpy_global_state_address() if use_np else None
         py_addr = _pyrandom_state_address() if use_py else None
         if use_py and not py_addr:
@@ -185,13 +211,15 @@ class ViewPlanner:
             pst = _pyrandom.getstate()
             pkey = np.array(pst[1][:624], dtype=np.uint32)
             pidx = C.c_int32(int(pst[1][624]))
-            _lib.check(lib.abt_planner_plan_batch_global(h, n_clips, int(time_crop_range), int(wav_crop_range), np_addr, C.addressof(pidx),
-                                                         pkey.ctypes.data, buf.ctypes.data, buf.nbytes))
+            with np_lock:
+                _lib.check(lib.abt_planner_plan_batch_global(h, n_clips, int(time_crop_range), int(wav_crop_range), np_addr, C.addressof(pidx),
+                                                             pkey.ctypes.data, buf.ctypes.data, buf.nbytes))
             _pyrandom.setstate((pst[0], tuple(pkey.tolist()) + (int(pidx.value),), pst[2]))
         else:
-            _lib.check(lib.abt_planner_plan_batch_global(h, n_clips, int(time_crop_range), int(wav_crop_range), np_addr,
-                                                         py_addr[0] if py_addr else None, py_addr[1] if py_addr else None,
-                                                         buf.ctypes.data, buf.nbytes))
+            with np_lock:
+                _lib.check(lib.abt_planner_plan_batch_global(h, n_clips, int(time_crop_range), int(wav_crop_range), np_addr,
+                                                             py_addr[0] if py_addr else None, py_addr[1] if py_addr else None,
+                                                             buf.ctypes.data, buf.nbytes))
         nv = self.n_views
         params = buf[:VIEW_DTYPE.itemsize * nv * n_clips].view(VIEW_DTYPE).reshape(n_clips, nv)
         starts = buf[off1:off1 + 4 * n_clips].view(np.int32)
@@ -202,5 +230,6 @@ class ViewPlanner:
             dev = st.upload(slot, nbytes)
             base = dev.data_ptr()
             plan.dev = dev
+            plan._staging, plan._gen = st, st.gen
             plan.params_ptr, plan.starts_ptr, plan.wav_starts_ptr, plan.slots_ptr = base, base + off1, base + off2, base + off3
         return plan

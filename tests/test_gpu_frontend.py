@@ -269,6 +269,20 @@ def test_host_prefetch_pipeline_equals_sequential_calls():
         assert torch.equal(a, b)
 
 
+def test_stale_prepared_batch_is_refused():
+    """A prepared batch aliases a slot of the planner's 4-deep staging ring: launching it after the slot has been handed out again
+    must raise instead of silently using another batch's parameters."""
+    import ssl_audio_b200 as S
+    fe = S.BatchFrontend(_args(), norm_stats=AS_STATS, path="lms", mode="crop")
+    wav = torch.from_numpy(O.synth_wave(8, 32000, seed=3)).cuda()
+    first = fe.prepare(wav)
+    later = [fe.prepare(wav) for _ in range(5)]
+    with pytest.raises(RuntimeError, match="stale batch plan"):
+        fe.launch(first)
+    fe.launch(later[-1])                                  # recent handles are still live
+    torch.cuda.synchronize()
+
+
 def test_bench_size_frontend_1024_clips_of_10s():
     """BASELINE config 2 at full size (1024 clips x 10 s, crop-first): crop starts equal the reference's np.random.randint draws
     interleaved with the view draws (replayed by the oracle), eight spot-checked clips match the oracle's per-sample path, every
