@@ -35,3 +35,18 @@ T("bt_loss_fwd_bwd (functional)", lambda: S.bt_loss_fwd_bwd(z1, z2, 1.0, 0.005, 
 def step():
     fe(wav); loss_only()
 T("full step", step)
+
+if os.environ.get("HOST_CPROFILE", "1") == "1":
+    import cProfile, pstats, io
+    for name, fn in (("loss fwd+bwd", loss_only), ("frontend", lambda: fe(wav))):
+        torch.cuda.synchronize()
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(200):
+            fn()
+        pr.disable()
+        torch.cuda.synchronize()
+        out = io.StringIO()
+        pstats.Stats(pr, stream=out).sort_stats("cumulative").print_stats(22)
+        print(f"==== cProfile of 200 x {name} (cumulative seconds / 200 = per call)")
+        print("\n".join(l[:170] for l in out.getvalue().splitlines()[4:40]))
