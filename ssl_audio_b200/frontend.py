@@ -214,8 +214,9 @@ class BatchFrontend(nn.Module):
         return ("host", wav, L, ring, plan, k, dev)
 
     def launch(self, handle) -> List[torch.Tensor]:
-        handle[-3 if handle[0] == "host" else -1].check_live()      # the plan's staging slot must not have been reused
-        if handle[0] == "host":
+        host = isinstance(handle[0], str)                  # ("host", wav, L, ring, plan, k, dev) or (wav, L, ring, plan)
+        handle[4 if host else 3].check_live()              # the plan's staging slot must not have been reused
+        if host:
             _, wav, L, ring, plan, k, dev = handle          # wav is kept alive until its gather has been consumed
             spans, origin, gathered, consumed = self._span_bufs[k]
             stride = int(ring.shape[1])
