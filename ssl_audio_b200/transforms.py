@@ -45,6 +45,27 @@ class AudioPairTransform(nn.Module):
         self._n_local = int(self.local_crops_number) if multi_transform else 0
         self._engine = None
         self._max_batch = 1024
+        # The reference's stage-by-stage pipelines (utils/transforms.py:15-46), for code that uses them directly or prints them:
+        # nn.Sequential of the standalone GPU stages, nn.Identity without train_transform.  `forward` does not go through them (it
+        # runs all stages of all views in one kernel, with its own Mixup ring); a single-view call `global_transform(x)` draws from
+        # the same global generators in the reference's order and keeps its own memory bank, as the reference's MixupBYOLA does.
+        from . import augmentations as A
+        if train_transform is True:
+            stages = []
+            if args.mixup:
+                stages.append(A.MixupBYOLA(ratio=mixup_ratio))
+            if getattr(args, "Gnoise", False):
+                stages.append(A.MixGaussianNoise(ratio=gauss_noise_ratio))
+            if args.RRC:
+                stages.append(A.RandomResizeCrop((args.n_mels, args.crop_frames), virtual_crop_scale=tuple(args.virtual_crop_scale),
+                                                 freq_scale=global_crop_scale, time_scale=global_crop_scale))
+            if args.RLF:
+                stages.append(A.RandomLinearFader())
+            self.global_transform = nn.Sequential(*stages)
+        else:
+            self.global_transform = nn.Identity()
+        self.local_transform = nn.Sequential(A.RandomResizeCrop(tuple(args.local_crops_size), virtual_crop_scale=(1, 1),
+                                                                freq_scale=local_crop_scale, time_scale=local_crop_scale))
 
     # ------------------------------------------------------------------------------------------
     def engine(self, batch: int) -> ViewEngine:

@@ -283,6 +283,21 @@ def test_stale_prepared_batch_is_refused():
     torch.cuda.synchronize()
 
 
+def test_stage_pipelines_run_like_the_reference_attributes():
+    """tfm.global_transform(x) / tfm.local_transform(x) (utils/transforms.py:15-46) on one log-mel: shapes, and the chain equals
+    the standalone stages applied one after the other with the same draws."""
+    import ssl_audio_b200 as S
+    x = torch.from_numpy(O.normalise(O.log_mel(O.synth_wave(1, 16000, seed=8))[:, None][..., :96], AS_STATS)[0]).cuda().float()
+    tfm = S.AudioPairTransform(_args(mixup=False))
+    np.random.seed(3); random.seed(3)
+    g = tfm.global_transform(x)
+    l = tfm.local_transform(x)
+    assert tuple(g.shape) == (1, 64, 96) and tuple(l.shape) == (1, 16, 16)
+    np.random.seed(3); random.seed(3)
+    ref = S.RandomLinearFader()(S.RandomResizeCrop((64, 96), virtual_crop_scale=(1.0, 1.5), freq_scale=(0.6, 1.5), time_scale=(0.6, 1.5))(x))
+    assert torch.equal(g, ref)
+
+
 def test_bench_size_frontend_1024_clips_of_10s():
     """BASELINE config 2 at full size (1024 clips x 10 s, crop-first): crop starts equal the reference's np.random.randint draws
     interleaved with the view draws (replayed by the oracle), eight spot-checked clips match the oracle's per-sample path, every
