@@ -52,10 +52,10 @@ int abt_device_check(void);
  * ===================================================================================== */
 typedef struct {
     int32_t sample_rate; /* 16000 */
-    int32_t n_fft;       /* must be 1024 */
+    int32_t n_fft;       /* must be 1024 (the FFT is a fixed 32 x 32 decomposition; every configuration of the reference uses 1024) */
     int32_t win_length;  /* <= n_fft; centre-padded like torch.stft */
     int32_t hop_length;  /* 160 */
-    int32_t n_mels;      /* must be 64 */
+    int32_t n_mels;      /* 1..256 (reference default 64) */
     float f_min, f_max;  /* 60, 7800 */
     int32_t apply_norm;  /* 1: out = (log_mel - norm_mean) / norm_std */
     float norm_mean, norm_std;

@@ -28,9 +28,9 @@ struct abt_logmel_plan {
     abt_mel_config cfg;
     float* d_window;   // n_fft, win_length window centre-padded
     float2* d_twiddle; // [k2][n1] -> exp(-2 pi i n1 k2 / 1024)
-    int* d_mel_start;  // 64
-    int* d_mel_len;    // 64
-    int* d_mel_off;    // 64, offset into d_mel_w
+    int* d_mel_start;  // n_mels
+    int* d_mel_len;    // n_mels
+    int* d_mel_off;    // n_mels, offset into d_mel_w
     float* d_mel_w;    // nnz
     int nnz;
     int max_len;
@@ -39,7 +39,7 @@ struct abt_logmel_plan {
 namespace abt {
 
 constexpr int kNfft = 1024;
-constexpr int kMels = 64;
+constexpr int kMaxMels = 256;
 constexpr int kTileFrames = 32;
 constexpr int kWarps = 8;
 constexpr int kScratchFloats = 2 * 32 * 33 + 2;   // per warp; the +2 staggers the warps' power spectra over the banks for the mel pass
@@ -68,6 +68,7 @@ struct LogmelArgs {
     const int* mel_off;
     const float* mel_w;
     int nnz;
+    int n_mels;               // bands (64 in every configuration of the reference; any 1..256 works)
 };
 
 __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs a) {
@@ -75,9 +76,9 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
     const int span = (kTileFrames - 1) * a.hop + kNfft;
     float* s_x = smem;                                  // span samples (padded coordinates)
     float* s_scratch = s_x + ((span + 31) & ~31);       // kWarps * kScratchFloats
-    float* s_out = s_scratch + kWarps * kScratchFloats; // kMels * (kTileFrames + 1)
-    float* s_melw = s_out + kMels * (kTileFrames + 1);  // nnz
-    int* s_mel_start = reinterpret_cast<int*>(s_melw + a.nnz);   // 64 start, 64 len, 64 off
+    float* s_out = s_scratch + kWarps * kScratchFloats; // n_mels * (kTileFrames + 1)
+    float* s_melw = s_out + a.n_mels * (kTileFrames + 1);  // nnz
+    int* s_mel_start = reinterpret_cast<int*>(s_melw + a.nnz);   // n_mels start, n_mels len, n_mels off
     __shared__ __align__(8) unsigned long long s_bar;
 
     const int clip = blockIdx.y;
@@ -123,10 +124,10 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
         }
     }
     for (int i = tid; i < a.nnz; i += blockDim.x) s_melw[i] = 0.25f * a.mel_w[i];      // x 1/4: see the power spectrum below (exact scaling)
-    if (tid < kMels) {
-        s_mel_start[tid] = a.mel_start[tid];
-        s_mel_start[kMels + tid] = a.mel_len[tid];
-        s_mel_start[2 * kMels + tid] = a.mel_off[tid];
+    for (int m = tid; m < a.n_mels; m += blockDim.x) {
+        s_mel_start[m] = a.mel_start[m];
+        s_mel_start[a.n_mels + m] = a.mel_len[m];
+        s_mel_start[2 * a.n_mels + m] = a.mel_off[m];
     }
     __syncthreads();      // also orders the mbarrier init before the waits below
     if (interior) {
@@ -203,16 +204,16 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
         // ---- sparse mel projection of the round's 16 frames, across the warps: thread = (frame f, band group g).  The 16 lanes of a
         // half-warp read the same weight (broadcast) and 16 different frames' power -- frame f = 2 * warp + {0, 1} sits at float offset
         // warp * kScratchFloats + 2 k + {0, 1}, i.e. bank (f + 2 k) mod 32: conflict-free.  Band lengths grow with the band index, so a
-        // thread takes bands g, 31 - g, 32 + g, 63 - g: about 61 of the 970 non-zero weights each.
+        // thread takes bands g, 31 - g, 32 + g, 63 - g, ...: about 61 of the 970 non-zero weights each at 64 bands.
         __syncthreads();
         if ((f_first + round * 2 * kWarps) < a.n_frames_total && (tile * kTileFrames + round * 2 * kWarps) < a.n_frames_out) {   // block-uniform
             const int f = tid & 15, g = tid >> 4;
             const float* pf = s_scratch + (f >> 1) * kScratchFloats + (f & 1);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 2 * ((a.n_mels + 31) / 32); ++q) {
                 const int m = (q >> 1) * 32 + ((q & 1) ? 31 - g : g);
-                const int ks = s_mel_start[m], kl = s_mel_start[kMels + m];
-                const float* w = s_melw + s_mel_start[2 * kMels + m];
+                if (m >= a.n_mels) continue;
+                const int ks = s_mel_start[m], kl = s_mel_start[a.n_mels + m];
+                const float* w = s_melw + s_mel_start[2 * a.n_mels + m];
                 const float* pk = pf + 2 * ks;
                 float m0 = 0.f, m1 = 0.f;
                 int k = 0;
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
     const long long slot = a.out_slot ? a.out_slot[clip] : clip;
     float* out = a.out_base + slot * a.out_slot_stride;
     const int t_base = tile * kTileFrames;       // frame offset inside the output row
-    for (int idx = tid; idx < kMels * kTileFrames; idx += blockDim.x) {
+    for (int idx = tid; idx < a.n_mels * kTileFrames; idx += blockDim.x) {
         const int m = idx / kTileFrames, f = idx % kTileFrames;
         const int t_out = t_base + f;
         if (t_out < a.n_frames_out) {
@@ -626,7 +627,8 @@ using namespace abt;
 extern "C" int abt_logmel_plan_create(const abt_mel_config* cfg, abt_logmel_plan** plan_out) {
     if (cfg == nullptr || plan_out == nullptr) return set_error(ABT_ERR_ARG, "null argument");
     if (cfg->n_fft != kNfft) return set_error(ABT_ERR_ARG, "n_fft must be 1024 (got %d)", cfg->n_fft);
-    if (cfg->n_mels != kMels) return set_error(ABT_ERR_ARG, "n_mels must be 64 (got %d)", cfg->n_mels);
+    if (cfg->n_mels < 1 || cfg->n_mels > kMaxMels) return set_error(ABT_ERR_ARG, "n_mels must be in [1, %d] (got %d)", kMaxMels, cfg->n_mels);
+    const int n_mels = cfg->n_mels;
     if (cfg->win_length < 1 || cfg->win_length > kNfft) return set_error(ABT_ERR_ARG, "win_length must be in [1, 1024]");
     if (cfg->hop_length < 1 || cfg->hop_length > 1024) return set_error(ABT_ERR_ARG, "hop_length must be in [1, 1024]");
     if (cfg->apply_norm && !(cfg->norm_std > 0.f)) return set_error(ABT_ERR_ARG, "norm_std must be > 0");
@@ -648,13 +650,13 @@ extern "C" int abt_logmel_plan_create(const abt_mel_config* cfg, abt_logmel_plan
     std::vector<float> all_freqs = linspace_f32(0.0, (double)(cfg->sample_rate / 2), n_freqs);
     const double m_min = 2595.0 * std::log10(1.0 + (double)cfg->f_min / 700.0);
     const double m_max = 2595.0 * std::log10(1.0 + (double)cfg->f_max / 700.0);
-    std::vector<float> m_pts = linspace_f32(m_min, m_max, kMels + 2);
-    std::vector<float> f_pts(kMels + 2);
-    for (int i = 0; i < kMels + 2; ++i) f_pts[i] = 700.0f * (std::pow(10.0f, m_pts[i] / 2595.0f) - 1.0f);
-    std::vector<int> start(kMels), len(kMels), off(kMels);
+    std::vector<float> m_pts = linspace_f32(m_min, m_max, n_mels + 2);
+    std::vector<float> f_pts(n_mels + 2);
+    for (int i = 0; i < n_mels + 2; ++i) f_pts[i] = 700.0f * (std::pow(10.0f, m_pts[i] / 2595.0f) - 1.0f);
+    std::vector<int> start(n_mels), len(n_mels), off(n_mels);
     std::vector<float> weights;
     int max_len = 0;
-    for (int m = 0; m < kMels; ++m) {
+    for (int m = 0; m < n_mels; ++m) {
         const float fd0 = f_pts[m + 1] - f_pts[m], fd1 = f_pts[m + 2] - f_pts[m + 1];
         int first = -1, last = -1;
         std::vector<float> col(n_freqs);
@@ -681,15 +683,15 @@ extern "C" int abt_logmel_plan_create(const abt_mel_config* cfg, abt_logmel_plan
     pl->max_len = max_len;
     ABT_CUDA_OK(cudaMalloc(&pl->d_window, sizeof(float) * kNfft));
     ABT_CUDA_OK(cudaMalloc(&pl->d_twiddle, sizeof(float2) * 1024));
-    ABT_CUDA_OK(cudaMalloc(&pl->d_mel_start, sizeof(int) * kMels));
-    ABT_CUDA_OK(cudaMalloc(&pl->d_mel_len, sizeof(int) * kMels));
-    ABT_CUDA_OK(cudaMalloc(&pl->d_mel_off, sizeof(int) * kMels));
+    ABT_CUDA_OK(cudaMalloc(&pl->d_mel_start, sizeof(int) * n_mels));
+    ABT_CUDA_OK(cudaMalloc(&pl->d_mel_len, sizeof(int) * n_mels));
+    ABT_CUDA_OK(cudaMalloc(&pl->d_mel_off, sizeof(int) * n_mels));
     ABT_CUDA_OK(cudaMalloc(&pl->d_mel_w, sizeof(float) * (weights.empty() ? 1 : weights.size())));
     ABT_CUDA_OK(cudaMemcpy(pl->d_window, win.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
     ABT_CUDA_OK(cudaMemcpy(pl->d_twiddle, tw.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice));
-    ABT_CUDA_OK(cudaMemcpy(pl->d_mel_start, start.data(), sizeof(int) * kMels, cudaMemcpyHostToDevice));
-    ABT_CUDA_OK(cudaMemcpy(pl->d_mel_len, len.data(), sizeof(int) * kMels, cudaMemcpyHostToDevice));
-    ABT_CUDA_OK(cudaMemcpy(pl->d_mel_off, off.data(), sizeof(int) * kMels, cudaMemcpyHostToDevice));
+    ABT_CUDA_OK(cudaMemcpy(pl->d_mel_start, start.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
+    ABT_CUDA_OK(cudaMemcpy(pl->d_mel_len, len.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
+    ABT_CUDA_OK(cudaMemcpy(pl->d_mel_off, off.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
     if (!weights.empty()) ABT_CUDA_OK(cudaMemcpy(pl->d_mel_w, weights.data(), sizeof(float) * weights.size(), cudaMemcpyHostToDevice));
     *plan_out = pl;
     return 0;
@@ -721,10 +723,10 @@ static int launch_logmel(const abt_logmel_plan* pl, const float* wav, int64_t ro
     a.inv_std = pl->cfg.apply_norm ? 1.0f / pl->cfg.norm_std : 1.0f;
     a.pad_value = pl->cfg.apply_norm ? (0.0f - pl->cfg.norm_mean) / pl->cfg.norm_std : 0.0f;
     a.window = pl->d_window; a.twiddle = pl->d_twiddle;
-    a.mel_start = pl->d_mel_start; a.mel_len = pl->d_mel_len; a.mel_off = pl->d_mel_off; a.mel_w = pl->d_mel_w; a.nnz = pl->nnz;
+    a.mel_start = pl->d_mel_start; a.mel_len = pl->d_mel_len; a.mel_off = pl->d_mel_off; a.mel_w = pl->d_mel_w; a.nnz = pl->nnz; a.n_mels = pl->cfg.n_mels;
     const int span = (kTileFrames - 1) * a.hop + kNfft;
-    const size_t smem = sizeof(float) * (((span + 31) & ~31) + kWarps * kScratchFloats + kMels * (kTileFrames + 1) + pl->nnz) + sizeof(int) * 3 * kMels;
-    if (smem > 227 * 1024) return set_error(ABT_ERR_ARG, "hop_length %d needs %zu bytes of shared memory (> 227 KiB)", a.hop, smem);
+    const size_t smem = sizeof(float) * (((span + 31) & ~31) + kWarps * kScratchFloats + pl->cfg.n_mels * (kTileFrames + 1) + pl->nnz) + sizeof(int) * 3 * pl->cfg.n_mels;
+    if (smem > 227 * 1024) return set_error(ABT_ERR_ARG, "hop_length %d with %d mel bands needs %zu bytes of shared memory (> 227 KiB)", a.hop, a.n_mels, smem);
     static size_t smem_set[64] = {};                  // cudaFuncSetAttribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -742,7 +744,7 @@ static int launch_logmel(const abt_logmel_plan* pl, const float* wav, int64_t ro
 extern "C" int abt_logmel_fwd(const abt_logmel_plan* plan, const float* wav, int n_clips, int n_samples, float* out, abt_stream_t stream) {
     if (plan == nullptr) return set_error(ABT_ERR_ARG, "plan is null");
     const int n_frames = 1 + n_samples / plan->cfg.hop_length;
-    return launch_logmel(plan, wav, n_samples, nullptr, nullptr, n_clips, n_samples, nullptr, n_frames, out, nullptr, (int64_t)kMels * n_frames,
+    return launch_logmel(plan, wav, n_samples, nullptr, nullptr, n_clips, n_samples, nullptr, n_frames, out, nullptr, (int64_t)plan->cfg.n_mels * n_frames,
                          reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -750,7 +752,7 @@ extern "C" int abt_logmel_crop_fwd(const abt_logmel_plan* plan, const float* wav
                                    int n_samples, const int32_t* frame_start, int n_frames, float* out_base, const int32_t* out_slot,
                                    int64_t out_slot_stride, abt_stream_t stream) {
     if (plan == nullptr) return set_error(ABT_ERR_ARG, "plan is null");
-    if (out_slot_stride < (int64_t)kMels * n_frames) return set_error(ABT_ERR_ARG, "out_slot_stride smaller than one clip");
+    if (out_slot_stride < (int64_t)plan->cfg.n_mels * n_frames) return set_error(ABT_ERR_ARG, "out_slot_stride smaller than one clip");
     if (wav_row_stride < n_samples) return set_error(ABT_ERR_ARG, "wav_row_stride smaller than n_samples");
     return launch_logmel(plan, wav, wav_row_stride, wav_offset, nullptr, n_clips, n_samples, frame_start, n_frames, out_base, out_slot, out_slot_stride,
                          reinterpret_cast<cudaStream_t>(stream));
@@ -792,7 +794,7 @@ extern "C" int abt_logmel_span_fwd(const abt_logmel_plan* plan, const float* spa
                                    const int32_t* frame_start, int n_frames, float* out_base, const int32_t* out_slot, int64_t out_slot_stride,
                                    abt_stream_t stream) {
     if (plan == nullptr || span_origin == nullptr) return set_error(ABT_ERR_ARG, "null argument");
-    if (out_slot_stride < (int64_t)kMels * n_frames) return set_error(ABT_ERR_ARG, "out_slot_stride smaller than one clip");
+    if (out_slot_stride < (int64_t)plan->cfg.n_mels * n_frames) return set_error(ABT_ERR_ARG, "out_slot_stride smaller than one clip");
     int span_len = 0;
     if (int rc = abt_wav_span_len(plan, n_frames, &span_len)) return rc;
     return launch_logmel(plan, spans, span_len, nullptr, span_origin, n_clips, n_samples, frame_start, n_frames, out_base, out_slot, out_slot_stride,

@@ -55,6 +55,24 @@ def test_logmel_long_clip_and_short_window(golden_dir):
     assert _relerr(out400, g["lms_win400"]) < TOL
 
 
+@pytest.mark.parametrize("n_mels", [40, 80, 128])
+def test_logmel_other_band_counts(golden_dir, n_mels):
+    """n_mels other than the default 64 (a flag of the reference's hyperparameters.py) against torchaudio's output."""
+    import ssl_audio_b200 as S
+    g = np.load(os.path.join(golden_dir, "logmel_nmels.npz"))
+    _, f_min, f_max = (int(v) for v in g[f"cfg_{n_mels}"])
+    mel = S.LogMelSpectrogram(16000, 1024, 1024, 160, n_mels, f_min, f_max)
+    out = mel(torch.from_numpy(g["wav"]).cuda()).cpu().numpy()
+    ref = g[f"lms_{n_mels}"]
+    assert out.shape == ref.shape
+    assert _relerr(out, ref) < TOL, _relerr(out, ref)
+    # the z-scored crop-first path writes the same values into caller-provided slots
+    cfg = O.MelConfig(n_mels=n_mels, f_min=float(f_min), f_max=float(f_max))
+    meln = S.LogMelSpectrogram(16000, 1024, 1024, 160, n_mels, f_min, f_max, norm_stats=AS_STATS)
+    outn = meln(torch.from_numpy(g["wav"]).cuda()).cpu().numpy()
+    assert _relerr(outn, O.normalise(O.log_mel(g["wav"], cfg), AS_STATS)) < TOL
+
+
 def test_logmel_ragged_batch_shapes_and_errors():
     import ssl_audio_b200 as S
     mel = S.LogMelSpectrogram(16000, 1024, 1024, 160, 64, 60, 7800, norm_stats=AS_STATS)
