@@ -398,6 +398,21 @@ int abt_lars_step(const abt_opt_tensor* tensors_dev, const int* chunk_tensor_dev
 int abt_ema_update(const abt_opt_tensor* tensors_dev, const int* chunk_tensor_dev, int n_tensors, int n_chunks, float beta, abt_stream_t stream);
 
 /* ===================================================================================== *
+ *  Projector tail fused with the objective's statistics pass
+ *  Reference: the last bias-free nn.Linear of BarlowTwinsHead (model.py:22, 25-31) followed by
+ *  BarlowTwinsLoss.forward_loss (utils/loss.py:15-30).
+ * ===================================================================================== */
+/* z1 = h1 W^T, z2 = h2 W^T (h*: (n_rows, k_dims) bf16 row-major, w: (n_dims, k_dims) bf16 row-major = nn.Linear.weight,
+ * z*: (n_rows, n_dims) bf16, fp32 accumulation on the tensor cores) and, from the ROUNDED outputs, the per-column hand-over of
+ * the statistics pass: pack[k * n_dims + j], k = 0..6 = sum z1, sum z1^2, sum z2, sum z2^2, sum z1 z2, 0, 0 -- the layout
+ * abt_bt_dist_stats_local writes (5 sums + 2 shifts).  Put it at workspace + abt_bt_dist_layout.pack_all of a world = 1 layout
+ * and continue with abt_bt_dist_normalize / abt_bt_dist_rows_fwd_bwd: the objective then never reads z for its statistics.
+ * Deterministic.  k_dims and n_dims: multiples of 8, >= 64; pointers 16-byte aligned. */
+int abt_proj_tail_workspace_bytes(int n_rows, int n_dims, size_t* bytes);
+int abt_proj_tail_fwd(const void* h1, const void* h2, const void* w, int n_rows, int k_dims, int n_dims, void* z1, void* z2,
+                      float* pack, void* workspace, size_t workspace_bytes, abt_stream_t stream);
+
+/* ===================================================================================== *
  *  Co-scheduling
  * ===================================================================================== */
 /* The tensor-core kernels of the objective are persistent and own every SM they run on (registers and shared memory), so

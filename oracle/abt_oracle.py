@@ -537,6 +537,17 @@ def bt_loss_multicrop(student: np.ndarray, teacher: np.ndarray, ncrops: int, ngc
 # Synthetic inputs shared by tests and bench
 # --------------------------------------------------------------------------------------
 
+def proj_tail_loss(h1: np.ndarray, h2: np.ndarray, w: np.ndarray, alpha=1.0, lmbda=0.005, hsic=False):
+    """Last bias-free Linear of BarlowTwinsHead (model.py:22, 25-31) + forward_loss (utils/loss.py:15-30) with bf16 embeddings:
+    z = round_bf16(h W^T) (float64 accumulation), then the objective on z.  Returns (loss, z1, z2, dz1, dz2, dh1, dh2, dW) with the
+    Linear's backward in float64 (dh = dz W, dW = dz1^T h1 + dz2^T h2)."""
+    h1 = h1.astype(np.float64); h2 = h2.astype(np.float64); w = w.astype(np.float64)
+    z1 = round_bf16((h1 @ w.T).astype(np.float32))
+    z2 = round_bf16((h2 @ w.T).astype(np.float32))
+    loss, dz1, dz2, _ = bt_loss_forward_backward(z1, z2, alpha, lmbda, hsic)
+    return loss, z1, z2, dz1, dz2, dz1 @ w, dz2 @ w, dz1.T @ h1 + dz2.T @ h2
+
+
 def synth_wave(batch: int, length: int, seed: int = 0, sample_rate: int = 16000) -> np.ndarray:
     """0.1*white noise + 3 sinusoids (0.3/0.1/0.03, U(100,7000) Hz, random phase), clamped to
     [-1, 1], float32 (B, L)."""

@@ -686,7 +686,7 @@ struct PassCfg {
 
 struct UmmaParams {
     DescCfg dc;
-    int mode;          // 0 = CORR, 1 = GRAD
+    int mode;          // 0 = CORR, 1 = GRAD, 2 = LINEAR (CTA pairs only)
     int D, N;
     int tiles_m, tiles_n, kblocks;   // per pass
     int pass_count;
@@ -704,6 +704,9 @@ struct UmmaParams {
     const float* rs1; const float* rs2;   // HSIC: row sums of zh1 / zh2 over all dimensions
     float alpha, lambda, grad_scale;
     float* loss_out;                   // written by the GRAD launch (single-GPU); may be null
+    // LINEAR (mode 2, the projector tail z = h W^T for both views with the column statistics of the rounded outputs)
+    void* lin_z1; void* lin_z2;        // (N, D) bf16 outputs
+    float* lin_partials;               // [2 * tiles_n][5][D]: sum z1, sum z1^2, sum z2, sum z2^2, sum z1 z2 over 64 samples each
     PassCfg pass[2];
 };
 
@@ -860,7 +863,11 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const CUtensorMap* mB = half < 0 ? (pass == 1 ? &mapB1 : &mapB0) : (pass == 1 ? &mapC1 : &mapC0);
             const int bn_cta = (half < 0 ? p.bn : p.bn / 2) / CG;               // B columns (or rows) staged by this CTA
             const uint32_t tx = (kABytes + (uint32_t)bn_cta * BK * 2) * CG;     // both CTAs' bytes land on the leader's barrier
-            const int bcol0 = tn * p.bn + (half > 0 ? p.bn / 2 : 0) + (int)rank * bn_cta;
+            int bcol0 = tn * p.bn + (half > 0 ? p.bn / 2 : 0) + (int)rank * bn_cta;
+            if (p.mode == 2) {      // LINEAR: the pair's B tile is [128 samples of view 1 | the same 128 samples of view 2]
+                mB = rank ? &mapB1 : &mapB0;
+                bcol0 = tn * bn_cta;
+            }
             const int a_mn = pc.a_mn;
             const int arow = a_mn ? pc.a_col0 + tm * BM : tm * BM;
             const int bdr = pc.blocked_dr;
@@ -1068,6 +1075,38 @@ bt_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         atomicAdd(p.loss_acc + 0, (double)l2);
                         if (p.hsic) atomicAdd(p.loss_acc + 1, (double)l1);
                     }
+                }
+            } else if (p.mode == 2) {
+                // ---- LINEAR: accumulator (output dimension row, sample) -> bf16 z1 / z2 and the column statistics of the ROUNDED
+                // outputs.  Columns 0..127 are 128 samples of view 1, columns 128..255 the same samples of view 2, and chunk ch of
+                // one view and chunk ch of the other belong to the same warp, so the five sums of a dimension -- the cross term
+                // sum z1 z2 included -- are thread-local.  One partial per (sample tile, warp half) = 64 samples, plain stores.
+                const int n_tile0 = tn * 128;
+                float s1 = 0.f, q1 = 0.f, s2 = 0.f, q2 = 0.f, xx = 0.f;
+                __nv_bfloat16* zo1 = static_cast<__nv_bfloat16*>(p.lin_z1) + (row_ok ? row : 0);
+                __nv_bfloat16* zo2 = static_cast<__nv_bfloat16*>(p.lin_z2) + (row_ok ? row : 0);
+                for (int c = 0; c < 2; ++c) {
+                    const int ch = hf + 2 * c, n_base = n_tile0 + ch * 32;
+                    if (n_base >= p.N) break;                                  // warp-uniform
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_32x32(t_addr + ch * 32, ra);
+                    tmem_ld_32x32(t_addr + 128 + ch * 32, rb);
+                    tmem_ld_wait();
+                    const int n_valid = row_ok ? min(32, p.N - n_base) : 0;
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) {
+                        if (t < n_valid) {
+                            const __nv_bfloat16 a16 = __float2bfloat16_rn(__uint_as_float(ra[t])), b16 = __float2bfloat16_rn(__uint_as_float(rb[t]));
+                            const float fa = __bfloat162float(a16), fb = __bfloat162float(b16);
+                            s1 += fa; q1 = fmaf(fa, fa, q1); s2 += fb; q2 = fmaf(fb, fb, q2); xx = fmaf(fa, fb, xx);
+                            zo1[(size_t)(n_base + t) * D] = a16;
+                            zo2[(size_t)(n_base + t) * D] = b16;
+                        }
+                    }
+                }
+                if (row_ok) {
+                    float* pp = p.lin_partials + (size_t)(tn * 2 + hf) * 5 * D + row;
+                    pp[0] = s1; pp[D] = q1; pp[2 * (size_t)D] = s2; pp[3 * (size_t)D] = q2; pp[4 * (size_t)D] = xx;
                 }
             } else {
                 // ---- GRAD: fp32 accumulator (dimension row, sample n) -> batch-norm backward -> dz[n][row - row0]
@@ -1685,6 +1724,70 @@ extern "C" int abt_bt_loss_fwd_bwd(const abt_bt_args* a, abt_stream_t stream) {
     return dispatch(c, L, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// ------------------------------------------------------------------------------------------
+// Projector tail: z = h W^T for both views on the tensor cores, with the column statistics the objective needs
+// taken from the ROUNDED bf16 outputs in the epilogue.  The result is the hand-over abt_bt_dist_stats_local produces (5 sums + 2
+// shifts per column), so the objective continues with abt_bt_dist_normalize / abt_bt_dist_rows_fwd_bwd (world = 1) and never
+// reads z for its statistics.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bt_pack_fold_kernel(const float* __restrict__ partials, int n_splits, int D, float* __restrict__ pack) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= D) return;
+    for (int k = 0; k < 5; ++k) {
+        double t = 0.0;
+        for (int r = 0; r < n_splits; ++r) t += (double)partials[((size_t)r * 5 + k) * D + c];      // fixed order: deterministic
+        pack[(size_t)k * D + c] = (float)t;
+    }
+    pack[(size_t)5 * D + c] = 0.f;          // the sums are not shifted (a bias-free Linear after BatchNorm + ReLU has |mean| ~ std)
+    pack[(size_t)6 * D + c] = 0.f;
+}
+
+static int proj_tail_splits(int n_rows) { return 2 * ((n_rows + 127) / 128); }
+
+extern "C" int abt_proj_tail_workspace_bytes(int n_rows, int n_dims, size_t* bytes) {
+    if (bytes == nullptr) return set_error(ABT_ERR_ARG, "bytes is null");
+    if (n_rows < 1 || n_dims < 1) return set_error(ABT_ERR_ARG, "bad shape");
+    *bytes = sizeof(float) * 5 * (size_t)proj_tail_splits(n_rows) * (size_t)n_dims;
+    return 0;
+}
+
+extern "C" int abt_proj_tail_fwd(const void* h1, const void* h2, const void* w, int n_rows, int k_dims, int n_dims, void* z1, void* z2,
+                                 float* pack, void* workspace, size_t workspace_bytes, abt_stream_t stream_) {
+    if (h1 == nullptr || h2 == nullptr || w == nullptr || z1 == nullptr || z2 == nullptr || pack == nullptr || workspace == nullptr)
+        return set_error(ABT_ERR_ARG, "null pointer argument");
+    if (n_rows < 2 || k_dims < 64 || (k_dims % 8) != 0 || n_dims < 64 || (n_dims % 8) != 0)
+        return set_error(ABT_ERR_ARG, "need n_rows >= 2, k_dims and n_dims >= 64 and multiples of 8 (got %d, %d, %d)", n_rows, k_dims, n_dims);
+    if (((reinterpret_cast<uintptr_t>(h1) | reinterpret_cast<uintptr_t>(h2) | reinterpret_cast<uintptr_t>(w)) & 15) != 0)
+        return set_error(ABT_ERR_ARG, "h1 / h2 / w must be 16-byte aligned");
+    size_t need = 0;
+    abt_proj_tail_workspace_bytes(n_rows, n_dims, &need);
+    if (workspace_bytes < need) return set_error(ABT_ERR_ARG, "workspace too small: %zu < %zu", workspace_bytes, need);
+    if (int rc = check_device_sm100()) return rc;
+    if (int rc = ensure_umma_attr()) return rc;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CUtensorMap mW, mH1, mH2;
+    if (int rc = make_map_16(&mW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w, n_dims, k_dims, 64, 128)) return rc;         // A: 128 output dimensions per CTA, K-major
+    if (int rc = make_map_16(&mH1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, h1, n_rows, k_dims, 64, 128)) return rc;       // B: 128 samples of one view per CTA
+    if (int rc = make_map_16(&mH2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, h2, n_rows, k_dims, 64, 128)) return rc;
+    UmmaParams p{};
+    p.dc = g_desc;
+    p.mode = 2; p.D = n_dims; p.N = n_rows; p.bn = 256; p.ab_format = 1;
+    p.tiles_m = (n_dims + 2 * BM - 1) / (2 * BM); p.tiles_n = (n_rows + 127) / 128;
+    p.kblocks = (k_dims + BK - 1) / BK;
+    p.pass_count = 1;
+    p.split_from = p.tiles_m * p.tiles_n;
+    p.lin_z1 = z1; p.lin_z2 = z2; p.lin_partials = static_cast<float*>(workspace);
+    PassCfg pc{};
+    pc.a_mn = 0; pc.row0 = 0; pc.row_end = n_dims;
+    p.pass[0] = pc; p.pass[1] = pc;
+    if (int rc = launch_umma(2, mW, mH1, mW, mH2, mW, mW, p, stream)) return rc;
+    bt_pack_fold_kernel<<<(n_dims + 255) / 256, 256, 0, stream>>>(static_cast<const float*>(workspace), proj_tail_splits(n_rows), n_dims, pack);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "projector tail launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int abt_bt_rows_workspace_bytes(int n_rows, int n_dims, int row_count, int dtype, size_t* bytes) {
     if (bytes == nullptr) return set_error(ABT_ERR_ARG, "bytes is null");
     if (int rc = check_shape(n_rows, n_dims, dtype)) return rc;
@@ -1831,7 +1934,9 @@ static int dist_rows_call(int dtype, int n_local, int world, int n_dims, int row
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     LossCall c{};
     c.z1 = zh1_base ? zh1_base : ws + L.zh1; c.z2 = zh2_base ? zh2_base : ws + L.zh2; c.dtype = dtype; c.N = ng; c.D = n_dims;
-    c.row_begin = row_begin; c.row_count = row_count; c.rows_mode = true; c.zh_mode = true; c.phase = phase; c.xchg = xchg;
+    // one rank owning every dimension (the fused projector tail continues here): C^T is the same matrix read transposed, no second CORR pass
+    const bool whole = world == 1 && row_begin == 0 && row_count == n_dims && !xchg;
+    c.row_begin = row_begin; c.row_count = row_count; c.rows_mode = !whole; c.zh_mode = true; c.phase = phase; c.xchg = xchg;
     c.alpha = alpha; c.lambda = lambda; c.hsic = hsic; c.eps = 0.f; c.momentum = 0.f; c.grad_scale = grad_scale;
     c.need = need; c.loss_out = nullptr; c.loss_parts_out = loss_parts;
     c.dz1 = dzr1; c.dz2 = dzr2; c.ld_dz = row_count;
