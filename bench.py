@@ -547,6 +547,47 @@ def run_ours(args):
         del crit_s
     del flush
 
+    # ---- projector tail fused with the statistics pass, single GPU only: last bias-free Linear (hidden 8192 -> D) of both
+    # views + column statistics in one tensor-core launch, against the library GEMMs + the separate statistics kernels it replaces
+    proj = None
+    if world == 1 and not args.no_proj_tail:
+        from ssl_audio_b200.projector import proj_tail_fwd, proj_tail_forward_loss
+        Kp = args.proj_hidden
+        gp = torch.Generator(device=dev).manual_seed(7)
+        hp1 = torch.relu(torch.randn(B, Kp, device=dev, generator=gp)).bfloat16()
+        hp2 = torch.relu(0.7 * hp1.float() + 0.7 * torch.randn(B, Kp, device=dev, generator=gp)).bfloat16()
+        Wp = (torch.randn(D, Kp, device=dev, generator=gp) / Kp ** 0.5).bfloat16()
+        packp = torch.empty(7 * D, device=dev)
+        crit_p = S.BarlowTwinsLoss(cfg, ncrops=2).to(dev)
+
+        def t_ms(fn, n=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(dev)
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(n):
+                fn()
+            b_.record()
+            torch.cuda.synchronize(dev)
+            return a_.elapsed_time(b_) / n
+
+        def chain(fused):
+            a_ = hp1.detach().requires_grad_(True); b_ = hp2.detach().requires_grad_(True); w_ = Wp.detach().requires_grad_(True)
+            if fused:
+                lo_ = proj_tail_forward_loss(crit_p, a_, b_, w_)
+            else:
+                lo_ = crit_p.forward_loss(torch.nn.functional.linear(a_, w_), torch.nn.functional.linear(b_, w_))
+            lo_.backward()
+            return lo_
+        fused_ms = t_ms(lambda: proj_tail_fwd(hp1, hp2, Wp, packp))
+        lib_ms = t_ms(lambda: (torch.nn.functional.linear(hp1, Wp), torch.nn.functional.linear(hp2, Wp)))
+        chain_fused = t_ms(lambda: chain(True), 5)
+        chain_lib = t_ms(lambda: chain(False), 5)
+        lf_, lu_ = float(chain(True).detach()), float(chain(False).detach())
+        proj = [fused_ms, lib_ms, chain_fused, chain_lib, lf_, lu_, Kp]
+        del hp1, hp2, Wp, crit_p
+
     # ---- sustained loop (>= 2 s of back-to-back steps, clocks sampled throughout): the burst number above is 12 ms of work
     sus_steps = int(max(args.steps, min(20000, args.sustained_s / max(ms / args.steps * 1e-3, 1e-5))))
     if world > 1:       # every rank must run the same number of (collective) steps: take rank 0's count
@@ -658,6 +699,16 @@ def run_ours(args):
                              "profiles/r1_ncu_summary.md; fp32 peak = 148 SMs x 128 FMA/clk x 1.965 GHz"},
         "loss_value": loss_val,
     }
+    if proj is not None:
+        pf = 2 * 2.0 * B * proj[6] * D
+        line["proj_tail"] = {
+            "workload": "projector tail fused with the statistics pass (SURVEY 8 f2): z = h W^T for both views, N = %d, K = %d, D = %d, bf16" % (B, proj[6], D),
+            "fused_ms": proj[0], "library_gemms_ms": proj[1], "statistics_kernel_it_replaces_ms": 0.0145,
+            "roofline": {"bound": "tensor", "kernel": "bt_umma_kernel<2> LINEAR mode + bt_pack_fold_kernel", "achieved": pf / (proj[0] * 1e-3) / 1e12,
+                         "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": pf / (proj[0] * 1e-3) / 1e12 / peaks["tf_burst"], "traffic": None,
+                         "algorithmic_flops": pf},
+            "chain_fwd_bwd_ms": {"fused_node": proj[2], "linear_plus_loss_module": proj[3]},
+            "loss_fused_vs_unfused": [proj[4], proj[5]]}
     if args.cpu_baseline and world == 1:          # the CPU baseline is timed on rank 0 of the single-GPU run only
         line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line), flush=True)
@@ -695,6 +746,8 @@ def main():
     ap.add_argument("--dim", type=int, default=8192, help="projector_out_dim")
     ap.add_argument("--clip-seconds", type=float, default=10.0)
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--no-proj-tail", action="store_true", help="skip the projector-tail (f2) measurement")
+    ap.add_argument("--proj-hidden", type=int, default=8192, help="input features of the projector's last Linear (projector_hidden_dim)")
     ap.add_argument("--e2e-probe", action="store_true", help="single GPU, development: time the e2e loop for several PCIe arrangements and exit")
     ap.add_argument("--ref-budget-s", type=float, default=240.0, help="reference arm: wall-clock budget of the whole K + W step run")
     ap.add_argument("--sweep-iters", type=int, default=30, help="timed iterations per point of the N = 128 loss sweep (BASELINE config 3)")

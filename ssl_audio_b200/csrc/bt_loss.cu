@@ -1865,7 +1865,6 @@ static int dist_stats_local(const void* z1, const void* z2, int N, int D, uint8_
     const int chunk = (N + splits - 1) / splits;
     splits = (N + chunk - 1) / chunk;
     const dim3 sgrid((D + kStatCols - 1) / kStatCols, splits);
-    cudaMemsetAsync(ws + L.keep, 0, 256, stream);
     bt_colstat_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(z1), static_cast<const T*>(z2), N, D, chunk, partials, nullptr, nullptr,
                                                             nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr);
     bt_stat_pack_kernel<T><<<(D + 255) / 256, 256, 0, stream>>>(static_cast<const T*>(z1), static_cast<const T*>(z2), D, splits, partials,
@@ -1901,6 +1900,8 @@ static void dist_normalize(const void* z1, const void* z2, int N, int world, int
     const dim3 sgrid((D + kColsPerBlock - 1) / kColsPerBlock, splits);
     __half* zh1 = (zh1_base ? zh1_base : reinterpret_cast<__half*>(ws + L.zh1)) + (size_t)rank * N * D;     // this rank's slot of the gather buffers
     __half* zh2 = (zh2_base ? zh2_base : reinterpret_cast<__half*>(ws + L.zh2)) + (size_t)rank * N * D;
+    cudaMemsetAsync(ws + L.keep, 0, 256, stream);      // the on-diagonal loss sum this kernel accumulates (cleared here, so that the statistics
+                                                       // hand-over may come from anywhere: abt_bt_dist_stats_local or the fused projector tail)
     bt_normalize_global_kernel<T><<<sgrid, kColThreads, 0, stream>>>(static_cast<const T*>(z1), static_cast<const T*>(z2), N, world, D, chunk, eps, momentum,
                                                                      reinterpret_cast<const float*>(ws + L.pack_all), reinterpret_cast<float*>(ws + L.stats),
                                                                      zh1, zh2, reinterpret_cast<__half*>(ws + L.zh1_blk), row_count, rm, rv,

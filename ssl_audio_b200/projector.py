@@ -98,22 +98,29 @@ class _TailLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("proj_tail_forward_loss: the gradients of this evaluation were already consumed (they are scaled in place by "
+                               "grad_output); call it again instead of back-propagating twice through the same graph")
+        ctx.consumed = True
         h1, h2, w, dz1, dz2 = ctx.saved_tensors
-        g = grad_out.detach().to(torch.float32)
+        g1 = dz1 if dz1.numel() else None
+        g2 = dz2 if dz2.numel() else None
         dh1 = dh2 = dw = None
-        # dz = d loss / d z comes straight from the GRAD launch; the Linear's own backward is three library GEMMs with fp32 outputs,
-        # scaled by grad_output and rounded to bf16 once
-        def mm32(a, b):
-            try:
-                return torch.mm(a, b, out_dtype=torch.float32)
-            except (TypeError, NotImplementedError):      # older torch: no out_dtype
-                return torch.mm(a.float(), b.float())
+        # dz = d loss / d z comes straight from the GRAD launch (this call's own buffers): scaled by grad_output in place with one launch
+        # (a no-op when it is 1), then the Linear's own backward is three library GEMMs, exactly what nn.Linear's backward runs
+        ref = g1 if g1 is not None else g2
+        if ref is not None:
+            scale = grad_out.detach().to(torch.float32).contiguous()
+            with torch.cuda.device(ref.device):
+                _lib.check(_lib.load().abt_scale_inplace(g1.data_ptr() if g1 is not None else None, g2.data_ptr() if g2 is not None else None,
+                                                         ref.numel(), _lib.DTYPE_BF16, scale.data_ptr(),
+                                                         torch.cuda.current_stream(ref.device).cuda_stream))
         if ctx.needs_input_grad[0]:
-            dh1 = (mm32(dz1, w) * g).to(torch.bfloat16)
+            dh1 = g1 @ w
         if ctx.needs_input_grad[1]:
-            dh2 = (mm32(dz2, w) * g).to(torch.bfloat16)
+            dh2 = g2 @ w
         if ctx.needs_input_grad[2]:
-            dw = ((mm32(dz1.t(), h1) + mm32(dz2.t(), h2)) * g).to(torch.bfloat16)
+            dw = torch.cat((g1, g2)).t() @ torch.cat((h1, h2))       # one GEMM over both views: a single rounding of dW
         return dh1, dh2, dw, None
 
 
