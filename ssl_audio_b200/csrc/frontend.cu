@@ -209,8 +209,10 @@ __global__ void __launch_bounds__(kWarps * 32, 2) logmel_kernel(const LogmelArgs
         if ((f_first + round * 2 * kWarps) < a.n_frames_total && (tile * kTileFrames + round * 2 * kWarps) < a.n_frames_out) {   // block-uniform
             const int f = tid & 15, g = tid >> 4;
             const float* pf = s_scratch + (f >> 1) * kScratchFloats + (f & 1);
-            for (int q = 0; q < 2 * ((a.n_mels + 31) / 32); ++q) {
-                const int m = (q >> 1) * 32 + ((q & 1) ? 31 - g : g);
+            for (int mb = 0; mb < a.n_mels; mb += 64)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int m = mb + (q >> 1) * 32 + ((q & 1) ? 31 - g : g);
                 if (m >= a.n_mels) continue;
                 const int ks = s_mel_start[m], kl = s_mel_start[a.n_mels + m];
                 const float* w = s_melw + s_mel_start[2 * a.n_mels + m];

@@ -1,3 +1,3 @@
-timeout 120 python tools/proj_only.py 1024 8192 8192 20 && timeout 300 ncu --set full --clock-control none -k regex:bt_umma_kernel -c 1 -o gpurun_out/r2_proj_tail -f python tools/proj_only.py 1024 8192 8192 3 2>&1 | tail -2
-python tools/ncu_summary.py gpurun_out/r2_proj_tail.ncu-rep 2>&1 | grep -i "dram__bytes\|duration\|tensor_cycles_active.avg.pct_of_peak_sustained_elapsed\|registers\|xbar\|lts__t_sector_hit" | head
-timeout 120 python tools/proj_only.py 1024 2048 8192 20; timeout 120 python tools/proj_only.py 256 8192 8192 20; timeout 120 python tools/proj_only.py 4096 2048 2048 20
+timeout 200 python -m pytest tests/test_gpu_frontend.py tests/test_gpu_offline.py -m gpu -x -q 2>&1 | tail -2
+timeout 120 python tools/frontend_only.py 2>&1 | tail -3
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:logmel_kernel -c 6 python tools/frontend_only.py 2>&1 | grep -i "duration" | tail -4
