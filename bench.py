@@ -324,6 +324,41 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    # ---- single GPU: the step's launches (frontend kernels on the side stream, objective forward + backward) are captured ONCE in a CUDA
+    # graph and replayed; per step the host only draws the batch's random parameters (native planner), uploads them into the static plan
+    # buffer and launches the graph.  Same kernels, same streams, same results as the eager step (tests/test_gpu_graph.py); BENCH_GRAPH=0
+    # runs the eager step.  (Multi-GPU steps stay eager: their collectives run on the library's own streams.)
+    graph_note = {"cuda_graph": False}
+    if world == 1 and not use_thread and os.environ.get("BENCH_GRAPH", "1") == "1":
+        eager_step = step
+        for _ in range(3):                      # every lazy allocation / kernel attribute happens before the capture
+            eager_step(wav, z1, z2)
+        torch.cuda.synchronize(dev)
+        ga = z1.detach().requires_grad_(True)
+        gb = z2.detach().requires_grad_(True)
+        handle = fe.prepare(wav, static=True)
+        graph = torch.cuda.CUDAGraph()
+        lib.abt_debug_launch_count(1)
+        with torch.cuda.graph(graph):
+            cap = torch.cuda.current_stream(dev)
+            fork = torch.cuda.Event()
+            fork.record(cap)
+            side_stream.wait_event(fork)
+            with torch.cuda.stream(side_stream):
+                g_views = fe.launch(handle)
+            g_loss = crit(gb, ga, ngcrops_each=1)
+            g_loss.backward()
+            cap.wait_stream(side_stream)
+        launches_per_replay = int(lib.abt_debug_launch_count(0))
+        graph_note = {"cuda_graph": True, "launches_per_replay": launches_per_replay}
+
+        def step(wav_d, z1_d, z2_d):            # noqa: F811
+            assert wav_d is wav and z1_d is z1 and z2_d is z2, "the captured step reads the buffers it was captured with"
+            fe.prepare(wav_d, static=True)       # this batch's draws -> static plan buffer (ordered before the replay on this stream)
+            graph.replay()
+            crit._pending_batches += 2           # host-side BatchNorm bookkeeping of the captured forward
+            return g_views, g_loss, ga.grad, gb.grad
+
     for _ in range(args.warmup):
         step(wav, z1, z2)
     sync_all()
@@ -342,6 +377,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     launches = int(lib.abt_debug_launch_count(0))
+    if graph_note["cuda_graph"]:                # replays do not pass through the library's launch counter
+        launches = graph_note["launches_per_replay"] * args.steps
     # host time to ENQUEUE one step, each step timed alone with the device idle before it: inside the loop above the enqueueing thread
     # is paced by the device (launch queue, plan staging ring), so its wall time there would only repeat ms_per_step
     host_samples = []
@@ -664,7 +701,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": _config(args),
-        "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms,
+        "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "step_launch": graph_note,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "reserved_sms": e2e_reserve, "pcie_gbs": h2d * e2e_steps / e2e_s / 1e9 if world == 1 else None,

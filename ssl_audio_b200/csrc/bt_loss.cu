@@ -1437,7 +1437,10 @@ static int run_loss(const LossCall& a, const WsLayout& L, cudaStream_t stream) {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = (!a.hsic && !timed && g_fused_pdl) ? 1 : 0;
+        // (not inside a stream capture either: a graph replay has no launch gap to hide, and the captured graph stays free of programmatic edges)
+        cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cap_status) != cudaSuccess) cap_status = cudaStreamCaptureStatusNone;
+        cfg.numAttrs = (!a.hsic && !timed && g_fused_pdl && cap_status == cudaStreamCaptureStatusNone) ? 1 : 0;
         const cudaError_t le = fused_launch<T>(cfg, p);
         if (le != cudaSuccess) return set_error(ABT_ERR_CUDA, "bt_fused_kernel launch: %s", cudaGetErrorString(le));
         count_launch();

@@ -153,7 +153,7 @@ class BatchFrontend(nn.Module):
         return tf.views_from_plan(ring, plan.slots_ptr, int(ring.shape[1]), plan)
 
     # -- two-step form of the crop-first path: host work (and the PCIe transfer) first, launches later ---------------
-    def prepare(self, wav: torch.Tensor, device: Optional[torch.device] = None):
+    def prepare(self, wav: torch.Tensor, device: Optional[torch.device] = None, static: bool = False):
         """Host half of `forward` (path "lms", mode "crop"): draws the batch's random parameters in the reference's order and
         uploads them (one async copy on the current stream).  `launch(handle)` then only enqueues the two kernels, so a trainer
         can plan early and launch exactly where it wants the kernels to overlap something else.
@@ -161,12 +161,17 @@ class BatchFrontend(nn.Module):
         With waveforms in PINNED host memory, `prepare` also enqueues the crop-first span gather (the only PCIe traffic of the
         batch) on the current stream, into one of two alternating span buffers: calling `prepare(next_batch)` on a side stream
         while the current batch computes is the prefetch a `DataLoader` worker would otherwise provide.  `launch` makes its stream
-        wait for that gather."""
+        wait for that gather.
+
+        `static=True` (device waveforms): the plan is uploaded into ONE fixed device buffer, so that `launch(handle)` can be captured
+        in a CUDA graph once and replayed after every later `prepare(wav, static=True)` on the same stream (same `wav` storage)."""
         if wav.dtype != torch.float32 or wav.dim() != 2:
             raise ValueError("wav must be a float32 tensor (B, L)")
         if self.path != "lms" or self.mode != "crop":
             raise ValueError("prepare/launch cover the crop-first lms path only")
         if not wav.is_cuda:
+            if static:
+                raise ValueError("static plans are for device waveforms (graph capture); host waveforms use the prefetch form")
             return self._prepare_host(wav, device)
         wav = wav.contiguous()
         B, L = int(wav.shape[0]), int(wav.shape[1])
@@ -174,7 +179,7 @@ class BatchFrontend(nn.Module):
         ring = eng.ensure_ring(wav.device)
         T_full = self.logmel_raw.n_frames(L)
         crop_range = T_full - self.crop_frames if T_full > self.crop_frames else 0
-        plan = eng.planner.plan(B, time_crop_range=crop_range, device=wav.device)
+        plan = eng.planner.plan(B, time_crop_range=crop_range, device=wav.device, static=static)
         return (wav, L, ring, plan)
 
     def _prepare_host(self, wav: torch.Tensor, device: Optional[torch.device]):

@@ -109,6 +109,7 @@ class PlanStaging:
         self.done = [None] * depth
         self.k = 0
         self.gen = 0            # plans handed out so far
+        self.dev_static = None
 
     def acquire(self):
         k = self.k
@@ -118,13 +119,18 @@ class PlanStaging:
             self.done[k].synchronize()
         return k
 
-    def upload(self, k: int, nbytes: int):
+    def upload(self, k: int, nbytes: int, static: bool = False):
+        """`static`: always the same device buffer (for kernels captured in a CUDA graph, whose pointers are frozen): the copy is ordered
+        on the current stream, so a graph replayed on that stream afterwards reads this plan and the next upload waits for the replay."""
         import torch
-        self.dev[k][:nbytes].copy_(self.host[k][:nbytes], non_blocking=True)
+        if static and self.dev_static is None:
+            self.dev_static = torch.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+        dst = self.dev_static if static else self.dev[k]
+        dst[:nbytes].copy_(self.host[k][:nbytes], non_blocking=True)
         ev = self.done[k] if self.done[k] is not None else torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self.done[k] = ev
-        return self.dev[k]
+        return dst
 
 
 class ViewPlanner:
@@ -179,9 +185,10 @@ class ViewPlanner:
         self._lib.abt_planner_bank_reset(self._h)
 
     # -- planning ------------------------------------------------------------------------------
-    def plan(self, n_clips: int, time_crop_range: int = 0, wav_crop_range: int = 0, device=None) -> BatchPlan:
+    def plan(self, n_clips: int, time_crop_range: int = 0, wav_crop_range: int = 0, device=None, static: bool = False) -> BatchPlan:
         """Draw the parameters of `n_clips` samples.  With `device`, the packed plan is also uploaded to that CUDA
-        device (one asynchronous copy on the current stream) and the device pointers are filled in."""
+        device (one asynchronous copy on the current stream) and the device pointers are filled in.  `static`: the upload goes to ONE
+        fixed device buffer (CUDA-graph capture of the consuming kernels); such a plan is valid until the next static plan."""
         lib, h = self._lib, self._h
         use_np = self._uses_numpy or time_crop_range > 0
         use_py = self._uses_pyrandom or wav_crop_range > 0
@@ -227,9 +234,10 @@ class ViewPlanner:
         slots = buf[off3:off3 + 4 * n_clips].view(np.int32)
         plan = BatchPlan(starts, wav_starts, params, slots)
         if device is not None:
-            dev = st.upload(slot, nbytes)
+            dev = st.upload(slot, nbytes, static)
             base = dev.data_ptr()
             plan.dev = dev
-            plan._staging, plan._gen = st, st.gen
+            if not static:
+                plan._staging, plan._gen = st, st.gen
             plan.params_ptr, plan.starts_ptr, plan.wav_starts_ptr, plan.slots_ptr = base, base + off1, base + off2, base + off3
         return plan
