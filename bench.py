@@ -330,34 +330,41 @@ def run_ours(args):
     # runs the eager step.  (Multi-GPU steps stay eager: their collectives run on the library's own streams.)
     graph_note = {"cuda_graph": False}
     if world == 1 and not use_thread and os.environ.get("BENCH_GRAPH", "1") == "1":
-        eager_step = step
-        for _ in range(3):                      # every lazy allocation / kernel attribute happens before the capture
-            eager_step(wav, z1, z2)
-        torch.cuda.synchronize(dev)
-        ga = z1.detach().requires_grad_(True)
-        gb = z2.detach().requires_grad_(True)
-        handle = fe.prepare(wav, static=True)
-        graph = torch.cuda.CUDAGraph()
-        lib.abt_debug_launch_count(1)
-        with torch.cuda.graph(graph):
-            cap = torch.cuda.current_stream(dev)
-            fork = torch.cuda.Event()
-            fork.record(cap)
-            side_stream.wait_event(fork)
-            with torch.cuda.stream(side_stream):
-                g_views = fe.launch(handle)
-            g_loss = crit(gb, ga, ngcrops_each=1)
-            g_loss.backward()
-            cap.wait_stream(side_stream)
-        launches_per_replay = int(lib.abt_debug_launch_count(0))
-        graph_note = {"cuda_graph": True, "launches_per_replay": launches_per_replay}
+        try:
+            eager_step = step
+            for _ in range(3):                      # every lazy allocation / kernel attribute happens before the capture
+                eager_step(wav, z1, z2)
+            torch.cuda.synchronize(dev)
+            ga = z1.detach().requires_grad_(True)
+            gb = z2.detach().requires_grad_(True)
+            handle = fe.prepare(wav, static=True)
+            graph = torch.cuda.CUDAGraph()
+            lib.abt_debug_launch_count(1)
+            with torch.cuda.graph(graph):
+                cap = torch.cuda.current_stream(dev)
+                fork = torch.cuda.Event()
+                fork.record(cap)
+                side_stream.wait_event(fork)
+                with torch.cuda.stream(side_stream):
+                    g_views = fe.launch(handle)
+                g_loss = crit(gb, ga, ngcrops_each=1)
+                g_loss.backward()
+                cap.wait_stream(side_stream)
+            launches_per_replay = int(lib.abt_debug_launch_count(0))
+            graph_note = {"cuda_graph": True, "launches_per_replay": launches_per_replay}
 
-        def step(wav_d, z1_d, z2_d):            # noqa: F811
-            assert wav_d is wav and z1_d is z1 and z2_d is z2, "the captured step reads the buffers it was captured with"
-            fe.prepare(wav_d, static=True)       # this batch's draws -> static plan buffer (ordered before the replay on this stream)
-            graph.replay()
-            crit._pending_batches += 2           # host-side BatchNorm bookkeeping of the captured forward
-            return g_views, g_loss, ga.grad, gb.grad
+            def step(wav_d, z1_d, z2_d):            # noqa: F811
+                assert wav_d is wav and z1_d is z1 and z2_d is z2, "the captured step reads the buffers it was captured with"
+                fe.prepare(wav_d, static=True)       # this batch's draws -> static plan buffer (ordered before the replay on this stream)
+                graph.replay()
+                crit._pending_batches += 2           # host-side BatchNorm bookkeeping of the captured forward
+                return g_views, g_loss, ga.grad, gb.grad
+        except Exception as e:                   # capture refused: run the eager step and say so in the line
+            try:
+                torch.cuda.synchronize(dev)
+            except Exception:
+                pass
+            graph_note = {"cuda_graph": False, "capture_error": str(e)[:200]}
 
     for _ in range(args.warmup):
         step(wav, z1, z2)
