@@ -512,10 +512,30 @@ def run_ours(args):
         return
 
     # frontend-only and loss-only device times (explain `value`; not the headline)
+    # (the eager call costs the host 0.23 ms, about what the two kernels take: on a box with a slower host an eager loop measures the
+    # host; when graphs are available the launch pair is captured and the replays are timed, with a fresh plan per replay)
+    fe_replay = None
+    if graph_note["cuda_graph"]:
+        try:
+            fh = fe.prepare(wav, static=True)
+            fgraph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(fgraph):
+                fe.launch(fh)
+
+            def fe_replay():
+                fe.prepare(wav, static=True)
+                fgraph.replay()
+        except Exception:
+            fe_replay = None
+            torch.cuda.synchronize(dev)
+    fe_call = fe_replay if fe_replay is not None else (lambda: fe(wav))
+    for _ in range(3):
+        fe_call()
+    torch.cuda.synchronize(dev)
     fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fe0.record()
     for _ in range(args.steps):
-        fe(wav)
+        fe_call()
     fe1.record()
     torch.cuda.synchronize(dev)
     fe_ms = fe0.elapsed_time(fe1) / args.steps
