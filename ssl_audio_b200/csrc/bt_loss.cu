@@ -2194,11 +2194,14 @@ static int all_to_all(abt_comm* c, ncclComm_t comm, const void* send, void* recv
         return 0;
     }
     ABT_NCCL_OK(g_nccl.GroupStart());
-    for (int q = 0; q < c->world; ++q) {
-        ABT_NCCL_OK(g_nccl.Send(static_cast<const uint8_t*>(send) + (size_t)q * slice_elems * esz, slice_elems, nccl_dtype(dtype), q, comm, st));
-        ABT_NCCL_OK(g_nccl.Recv(static_cast<uint8_t*>(recv) + (size_t)q * slice_elems * esz, slice_elems, nccl_dtype(dtype), q, comm, st));
+    ncclResult_t first = ncclSuccess;          // an error inside the group must not leave it open: remember it, close the group, then report
+    for (int q = 0; q < c->world && first == ncclSuccess; ++q) {
+        first = g_nccl.Send(static_cast<const uint8_t*>(send) + (size_t)q * slice_elems * esz, slice_elems, nccl_dtype(dtype), q, comm, st);
+        if (first == ncclSuccess) first = g_nccl.Recv(static_cast<uint8_t*>(recv) + (size_t)q * slice_elems * esz, slice_elems, nccl_dtype(dtype), q, comm, st);
     }
-    ABT_NCCL_OK(g_nccl.GroupEnd());
+    const ncclResult_t end = g_nccl.GroupEnd();
+    ABT_NCCL_OK(first);
+    ABT_NCCL_OK(end);
     return 0;
 }
 
@@ -2339,9 +2342,11 @@ extern "C" int abt_bt_dist_step(const abt_bt_dist_step_args* a, abt_comm* c, abt
             if (int rc = gather_view(1)) return rc;
         } else {
             ABT_NCCL_OK(g_nccl.GroupStart());
-            ABT_NCCL_OK(g_nccl.AllGather(zh1 + (size_t)rank * N * D, zh1, (size_t)N * D, ncclFloat16, c->comm, c->cs));
-            ABT_NCCL_OK(g_nccl.AllGather(zh2 + (size_t)rank * N * D, zh2, (size_t)N * D, ncclFloat16, c->comm, c->cs));
-            ABT_NCCL_OK(g_nccl.GroupEnd());
+            ncclResult_t first = g_nccl.AllGather(zh1 + (size_t)rank * N * D, zh1, (size_t)N * D, ncclFloat16, c->comm, c->cs);
+            if (first == ncclSuccess) first = g_nccl.AllGather(zh2 + (size_t)rank * N * D, zh2, (size_t)N * D, ncclFloat16, c->comm, c->cs);
+            const ncclResult_t end = g_nccl.GroupEnd();      // never leave the group open on an error
+            ABT_NCCL_OK(first);
+            ABT_NCCL_OK(end);
         }
         cudaEventRecord(c->ev[E_A], c->cs);
         if (a->overlap_cb != nullptr) a->overlap_cb(a->overlap_user);
