@@ -17,7 +17,7 @@ for R in $BENCHES; do
   python - <<PY
 import json
 try:
-    d = json.load(open("gpurun_out/r2_bench_n$R${TAG}.json"))
+    d = [json.loads(l) for l in open("gpurun_out/r2_bench_n$R${TAG}.json") if l.startswith("{")][-1]
     print("N=$R value", d["value"], "ms/step", d["ms_per_step"], "loss_fwd_bwd_ms", d["roofline"]["loss_fwd_bwd_ms"], "frac", d["roofline"]["frac"], "spread", d["loss_spread_over_ranks"])
     print("   sweep", [(p["D"], round(p["ms"], 4), round(p["roofline"]["frac"], 3)) for p in d["loss_sweep"]["points"]], "sustained", d["sustained"]["value"])
 except Exception as e:
