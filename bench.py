@@ -280,7 +280,17 @@ def run_ours(args):
             cur["handle"] = fe.prepare(cur["wav"])
 
     def frontend_launch():          # kernel launches only: called (on the side stream) from the objective's comm-overlap hook
+        side_stream.wait_event(inputs_ready)
         cur["views"] = fe.launch(cur["handle"])
+
+    # Plan-ahead (multi-GPU eager step): the NEXT step's random parameters are drawn and uploaded by a worker thread while this step is
+    # being enqueued -- what a DataLoader worker does for the reference.  The native planner releases the GIL, the draw order is unchanged
+    # (one plan per step, in step order; nothing else draws from the global generators), and the plan does not depend on the waveforms.
+    plan_pool = None
+
+    def plan_on_worker():
+        with torch.cuda.stream(side_stream):
+            return fe.prepare(cur["wav"])
 
     # Default: one host thread; on several GPUs the frontend is enqueued from the objective's comm-overlap hook (right after the embedding
     # all-gathers have been launched).  BENCH_THREAD=1 moves the frontend's host side to a worker thread instead (measured: no gain, the
@@ -295,6 +305,9 @@ def run_ours(args):
         # gated on the objective's stream position (ssl_audio_b200.dist.side_stream_hook); BENCH_HOOK_WAIT=0 shows the ungated behaviour
         from ssl_audio_b200.dist import side_stream_hook
         crit.comm_overlap_hook = side_stream_hook(side_stream, frontend_launch, gate=os.environ.get("BENCH_HOOK_WAIT", "1") == "1")
+        if os.environ.get("BENCH_PLAN_AHEAD", "1") == "1":
+            from concurrent.futures import ThreadPoolExecutor
+            plan_pool = ThreadPoolExecutor(max_workers=1, initializer=lambda: torch.cuda.set_device(local_rank))
     elif use_thread:
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(max_workers=1, initializer=lambda: torch.cuda.set_device(local_rank))
@@ -307,6 +320,10 @@ def run_ours(args):
         fut = None
         if pool is not None:
             fut = pool.submit(frontend_on_side_stream)
+        elif use_hook and plan_pool is not None:
+            pending = cur.pop("plan_future", None)
+            cur["handle"] = pending.result() if pending is not None else plan_on_worker()
+            cur["plan_future"] = plan_pool.submit(plan_on_worker)       # the next step's plan, drawn while this step is enqueued
         elif use_hook:
             frontend_plan()
         else:
@@ -396,10 +413,17 @@ def run_ours(args):
         host_samples.append(time.perf_counter() - h0)
     sync_all()
     host_ms = sorted(host_samples)[len(host_samples) // 2] * 1e3
+
+    def drain_plan_ahead():         # the worker may still hold the next step's plan: finish it before anybody else uses the planner
+        pending = cur.pop("plan_future", None)
+        if pending is not None:
+            pending.result()
+    drain_plan_ahead()
     loss_val = float(out[1].detach())
 
     # loss-only pass with per-launch CUDA events on the launching stream (the roofline numbers: in the step above the tensor-core
     # launches share the SMs with the frontend stream, which would inflate their event times)
+    step_hook = crit.comm_overlap_hook
     crit.comm_overlap_hook = None
 
     def loss_only():
@@ -419,6 +443,7 @@ def run_ours(args):
     stats_ms, corr_ms, grad_ms, ncalls = C.c_float(), C.c_float(), C.c_float(), C.c_int()
     _lib.check(lib.abt_debug_timing_read(C.byref(stats_ms), C.byref(corr_ms), C.byref(grad_ms), C.byref(ncalls)))
     _lib.check(lib.abt_debug_timing(0))
+    crit.comm_overlap_hook = step_hook          # the multi-GPU step launches its frontend from this hook: the sustained loop below needs it
     # the library averages over CALLS; a multi-GPU step makes several (front / dz1 / dz2 phases): account per STEP
     calls_per_step = ncalls.value / float(args.steps)
     for v in (stats_ms, corr_ms, grad_ms):
@@ -478,6 +503,7 @@ def run_ours(args):
             return views
 
         S.set_reserved_sms(int(reserve))
+        saved_hook, crit.comm_overlap_hook = crit.comm_overlap_hook, None      # this loop launches its frontend itself
         try:
             loop(3)
             sync_all()
@@ -486,6 +512,7 @@ def run_ours(args):
             dt = time.perf_counter() - t0
         finally:
             S.set_reserved_sms(0)
+            crit.comm_overlap_hook = saved_hook
         return dt, int(getattr(fe, "h2d_bytes", wav_h.numel() * 4)) + z1_h.numel() * 2 + z2_h.numel() * 2
 
     if args.e2e_probe:          # which arrangement of the PCIe traffic is fastest (tools: development only; prints one line per variant)
@@ -506,7 +533,7 @@ def run_ours(args):
             v = [float(x) for x in tq.cpu()]
             print(json.dumps({"quick": True, "n_gpus": world, "ms_per_step": v[0] / args.steps, "value": B * world / (v[0] / args.steps * 1e-3),
                               "loss_fwd_bwd_ms": v[1], "corr_ms": v[2], "grad_ms": v[3], "stats_ms": v[4], "host_enqueue_ms": host_ms,
-                              "env": {k: os.environ.get(k) for k in ("ABT_DIST_CE", "ABT_COMM_MAX_CTAS", "ABT_DIST_RESERVE_SMS", "ABT_DIST_XCHG", "BENCH_HOOK_WAIT", "BENCH_HOOK")}}), flush=True)
+                              "env": {k: os.environ.get(k) for k in ("ABT_DIST_CE", "ABT_COMM_MAX_CTAS", "ABT_DIST_RESERVE_SMS", "ABT_DIST_XCHG", "BENCH_HOOK_WAIT", "BENCH_HOOK", "BENCH_PLAN_AHEAD")}}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -669,6 +696,7 @@ def run_ours(args):
     u1.record()
     sync_all()
     clocks_sus = sampler2.stop() if rank == 0 else None
+    drain_plan_ahead()
     sus_ms = u0.elapsed_time(u1) / sus_steps
 
     e2e_steps = max(2, min(args.steps, args.e2e_steps))
