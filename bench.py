@@ -540,7 +540,7 @@ def run_ours(args):
 
     # frontend-only and loss-only device times (explain `value`; not the headline)
     # (the eager call costs the host 0.23 ms, about what the two kernels take: on a box with a slower host an eager loop measures the
-    # host; when graphs are available the launch pair is captured and the replays are timed, with a fresh plan per replay)
+    # host; when graphs are available the launch pair is captured once and its replays are timed)
     fe_replay = None
     if graph_note["cuda_graph"]:
         try:
@@ -549,9 +549,8 @@ def run_ours(args):
             with torch.cuda.graph(fgraph):
                 fe.launch(fh)
 
-            def fe_replay():
-                fe.prepare(wav, static=True)
-                fgraph.replay()
+            def fe_replay():            # the kernels only (one plan for all replays: a per-replay plan upload would put the box's
+                fgraph.replay()         # host-to-device copy latency, 10-150 us by box, in series with every launch pair)
         except Exception:
             fe_replay = None
             torch.cuda.synchronize(dev)
