@@ -87,7 +87,9 @@ int abt_logmel_crop_fwd(const abt_logmel_plan* plan, const float* wav, int64_t w
  * memory and the kernel reads it in place over PCIe (no staging copy of the whole clip); otherwise it is a device pointer.
  * spans: (n_clips, span_len) fp32 device; span_origin: (n_clips) int32 device, first clip sample held by each span row.
  * Requires n_samples >= span_len.  abt_logmel_span_fwd is abt_logmel_crop_fwd reading those spans; it gives bit-identical
- * results (reflect padding is resolved in clip coordinates, and a span always contains the mirrored samples). */
+ * results (reflect padding is resolved in clip coordinates, and a span always contains the mirrored samples).
+ * The gather runs as 4 blocks of 32 warps (one warp per clip): enough reads in flight for PCIe, and confined to 4 SMs it can run
+ * beside the persistent tensor-core kernels when those leave them free (abt_set_reserved_sms). */
 int abt_wav_span_len(const abt_logmel_plan* plan, int n_frames, int* span_len);
 int abt_wav_span_gather(const abt_logmel_plan* plan, const float* wav, int wav_on_host, int64_t wav_row_stride, int n_clips, int n_samples,
                         const int32_t* frame_start, int n_frames, float* spans, int32_t* span_origin, abt_stream_t stream);
