@@ -393,7 +393,7 @@ typedef struct {
 } abt_opt_tensor;
 /* elements per chunk; tensor t owns ceil(n / chunk) consecutive chunks starting at chunk0, chunk_tensor[c] = t */
 int abt_opt_chunk_elems(void);
-/* tensors_dev / chunk_tensor_dev: DEVICE copies of the table and the chunk map; partial_dev: 8 bytes per chunk of scratch */
+/* tensors_dev / chunk_tensor_dev: DEVICE copies of the table and the chunk map; partial_dev: scratch, 8 bytes per chunk + 4 bytes per tensor */
 int abt_lars_step(const abt_opt_tensor* tensors_dev, const int* chunk_tensor_dev, int n_tensors, int n_chunks, float lr, float weight_decay,
                   float momentum, float eta, void* partial_dev, abt_stream_t stream);
 /* ma = beta * ma + (1 - beta) * cur for every tensor of the table (utils/utils.py:320-331) */

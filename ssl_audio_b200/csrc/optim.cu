@@ -5,7 +5,7 @@
 //                                                     mu = momentum mu + q dp;  p -= lr mu          (2 torch.norm + ~8 launches per tensor)
 //   * update_moving_average utils/utils.py:328-331 -- ma = beta ma + (1 - beta) p                    (BYOL target network, per tensor)
 // All tensors of a step are described by one device table (pointer, element count, flags) and a chunk map (chunk -> tensor, offset),
-// so a step costs two launches (norms, apply) regardless of the number of parameters.  fp32 parameters only (the reference keeps
+// so a step costs three launches (chunk norms, per-tensor trust ratios, apply) regardless of the number of parameters.  fp32 parameters only (the reference keeps
 // fp32 master weights under autocast).  Norm partials are reduced in a fixed order: results are deterministic.
 #include "abt_internal.h"
 
@@ -65,33 +65,61 @@ __global__ void __launch_bounds__(kOptThreads) lars_norm_kernel(const TensorRec*
     if (threadIdx.x == 0) partial[c] = make_float2(tp, td);
 }
 
-__global__ void __launch_bounds__(kOptThreads) lars_apply_kernel(const TensorRec* __restrict__ tensors, const int* __restrict__ chunk_tensor, int n_chunks,
-                                                                 float lr, float weight_decay, float momentum, float eta,
-                                                                 const float2* __restrict__ partial) {
-    __shared__ float q_s;
-    const int c = blockIdx.x;
-    const TensorRec t = tensors[chunk_tensor[c]];
-    const long long off = (long long)(c - t.chunk0) * kOptChunk;
-    const int n = (int)((t.n - off) < kOptChunk ? (t.n - off) : kOptChunk);
-    const float wd = (t.flags & 1) ? weight_decay : 0.f;
+// q[t] = eta |p_t| / |dp_t| (1 when tensor t is excluded from the adaptation or either norm is zero): one block per tensor sums the
+// tensor's chunk partials -- fixed assignment, fixed tree, double: deterministic.  (Summing them in every block of the apply kernel
+// made an 8192 x 8192 weight cost 8192 serial additions in each of its 8192 blocks: 7 ms per step for a 156 M-parameter model.)
+__global__ void __launch_bounds__(kOptThreads) lars_ratio_kernel(const TensorRec* __restrict__ tensors, float eta, const float2* __restrict__ partial,
+                                                                 float* __restrict__ q_out) {
+    __shared__ double sp_s[kOptThreads], sd_s[kOptThreads];
+    const TensorRec t = tensors[blockIdx.x];
+    double sp = 0.0, sd = 0.0;
+    if (t.flags & 2) {
+        const int nc = (int)((t.n + kOptChunk - 1) / kOptChunk);
+        for (int k = threadIdx.x; k < nc; k += kOptThreads) { const float2 v = partial[t.chunk0 + k]; sp += (double)v.x; sd += (double)v.y; }
+    }
+    sp_s[threadIdx.x] = sp; sd_s[threadIdx.x] = sd;
+    __syncthreads();
+    for (int o = kOptThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { sp_s[threadIdx.x] += sp_s[threadIdx.x + o]; sd_s[threadIdx.x] += sd_s[threadIdx.x + o]; }
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         float q = 1.f;
         if (t.flags & 2) {
-            // the tensor's norms: fixed-order sum of its chunks' partials (double: the partials themselves are fp32 block sums)
-            const int nc = (int)((t.n + kOptChunk - 1) / kOptChunk);
-            double sp = 0.0, sd = 0.0;
-            for (int k = 0; k < nc; ++k) { const float2 v = partial[t.chunk0 + k]; sp += (double)v.x; sd += (double)v.y; }
-            const float pn = (float)sqrt(sp), un = (float)sqrt(sd);
+            const float pn = (float)sqrt(sp_s[0]), un = (float)sqrt(sd_s[0]);
             q = (pn > 0.f && un > 0.f) ? eta * pn / un : 1.f;
         }
-        q_s = q;
+        q_out[blockIdx.x] = q;
     }
-    __syncthreads();
-    const float q = q_s;
+}
+
+__global__ void __launch_bounds__(kOptThreads) lars_apply_kernel(const TensorRec* __restrict__ tensors, const int* __restrict__ chunk_tensor, int n_chunks,
+                                                                 float lr, float weight_decay, float momentum, const float* __restrict__ q_arr) {
+    const int c = blockIdx.x;
+    const int ti = chunk_tensor[c];
+    const TensorRec t = tensors[ti];
+    const long long off = (long long)(c - t.chunk0) * kOptChunk;
+    const int n = (int)((t.n - off) < kOptChunk ? (t.n - off) : kOptChunk);
+    const float wd = (t.flags & 1) ? weight_decay : 0.f;
+    const float q = q_arr[ti];
     float* p = t.p + off;
     const float* g = t.g + off;
     float* mu = t.aux + off;
-    for (int i = threadIdx.x; i < n; i += kOptThreads) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(mu)) & 15) == 0;
+    int done = 0;
+    if (vec) {
+        for (int i = threadIdx.x * 4; i + 3 < n; i += kOptThreads * 4) {
+            const float4 a = *reinterpret_cast<const float4*>(p + i), b = *reinterpret_cast<const float4*>(g + i), m0 = *reinterpret_cast<const float4*>(mu + i);
+            float4 m, o;
+            m.x = fmaf(momentum, m0.x, fmaf(wd, a.x, b.x) * q); m.y = fmaf(momentum, m0.y, fmaf(wd, a.y, b.y) * q);
+            m.z = fmaf(momentum, m0.z, fmaf(wd, a.z, b.z) * q); m.w = fmaf(momentum, m0.w, fmaf(wd, a.w, b.w) * q);
+            o.x = fmaf(-lr, m.x, a.x); o.y = fmaf(-lr, m.y, a.y); o.z = fmaf(-lr, m.z, a.z); o.w = fmaf(-lr, m.w, a.w);
+            *reinterpret_cast<float4*>(mu + i) = m;
+            *reinterpret_cast<float4*>(p + i) = o;
+        }
+        done = n & ~3;
+    }
+    for (int i = done + threadIdx.x; i < n; i += kOptThreads) {
         const float a = p[i];
         const float dp = fmaf(wd, a, g[i]) * q;
         const float m = fmaf(momentum, mu[i], dp);
@@ -130,12 +158,14 @@ extern "C" int abt_opt_chunk_elems(void) { return kOptChunk; }
 extern "C" int abt_lars_step(const abt_opt_tensor* tensors_dev, const int* chunk_tensor_dev, int n_tensors, int n_chunks, float lr, float weight_decay,
                              float momentum, float eta, void* partial_dev, abt_stream_t stream) {
     if (int rc = check_table(tensors_dev, chunk_tensor_dev, n_tensors, n_chunks)) return rc;
-    if (partial_dev == nullptr) return set_error(ABT_ERR_ARG, "partial buffer is null (8 bytes per chunk)");
+    if (partial_dev == nullptr) return set_error(ABT_ERR_ARG, "partial buffer is null (8 bytes per chunk + 4 bytes per tensor)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const TensorRec* T = reinterpret_cast<const TensorRec*>(tensors_dev);
+    float* q_arr = static_cast<float*>(partial_dev) + 2 * (size_t)n_chunks;       // per-tensor trust ratios, behind the chunk partials
     lars_norm_kernel<<<n_chunks, kOptThreads, 0, st>>>(T, chunk_tensor_dev, n_chunks, weight_decay, static_cast<float2*>(partial_dev));
-    lars_apply_kernel<<<n_chunks, kOptThreads, 0, st>>>(T, chunk_tensor_dev, n_chunks, lr, weight_decay, momentum, eta, static_cast<const float2*>(partial_dev));
-    count_launch(2);
+    lars_ratio_kernel<<<n_tensors, kOptThreads, 0, st>>>(T, eta, static_cast<const float2*>(partial_dev), q_arr);
+    lars_apply_kernel<<<n_chunks, kOptThreads, 0, st>>>(T, chunk_tensor_dev, n_chunks, lr, weight_decay, momentum, q_arr);
+    count_launch(3);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(ABT_ERR_CUDA, "LARS launch: %s", cudaGetErrorString(e));
     return 0;

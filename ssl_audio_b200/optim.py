@@ -53,7 +53,7 @@ class _Table:
         self._host = host                                  # keep the pinned staging buffer alive until the copy has run
         self.rec_bytes = rec_bytes
         self.n_tensors, self.n_chunks = n, len(chunk_tensor)
-        self.partial = torch.empty(2 * self.n_chunks, dtype=torch.float32, device=device)
+        self.partial = torch.empty(2 * self.n_chunks + self.n_tensors, dtype=torch.float32, device=device)     # chunk norms + one trust ratio per tensor
         self.key = key
 
     @property
